@@ -1,0 +1,106 @@
+/*
+ * lidbox_b200 — C-ABI of the B200-native (sm_100a) log-mel + x-vector hot path.
+ *
+ * The reference (py-lidbox/lidbox @ e60d5ad) has no FFI of its own: its operator API for this path is the
+ * Python call surface of lidbox/features/audio.py, lidbox/features/mel_ops.py, lidbox/models/xvector.py,
+ * lidbox/losses.py and lidbox/data/tf_utils.py, all dispatching into TensorFlow.  Each entry point below
+ * replaces the TensorFlow op chain behind one of those call sites (cited as file:line relative to
+ * /root/reference); the Python host package `lidbox_b200` binds them with ctypes.
+ *
+ * Conventions
+ *  - every function returns int: 0 = OK, <0 = LBX_E* code; lbx_last_error() gives a thread-local message;
+ *  - all tensor pointers are DEVICE pointers owned by the caller unless the name ends in `_host`;
+ *    the library never allocates, frees or synchronises the device (the *_host convenience entry points are the
+ *    only exception: they stage through caller-visible pinned/pageable host buffers and synchronise the stream);
+ *  - all work is enqueued on the cudaStream_t passed as `void* stream` (NULL = legacy default stream);
+ *  - tensors are contiguous row-major; `long long` is used for sizes;
+ *  - re-entrant and thread-safe: no mutable global state except write-once function attributes.
+ */
+#ifndef LIDBOX_B200_H
+#define LIDBOX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBX_OK 0
+#define LBX_EINVAL (-1)      /* bad argument (shape, dtype, alignment) */
+#define LBX_EUNSUPPORTED (-2) /* valid in the reference but not implemented by this library */
+#define LBX_ECUDA (-3)       /* CUDA runtime / driver error */
+#define LBX_EWORKSPACE (-4)  /* workspace missing or too small */
+
+/* dtype tags used by the TDNN entry points */
+#define LBX_F32 0
+#define LBX_BF16 1
+
+const char* lbx_last_error(void);
+int lbx_version(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches claim) */
+long long lbx_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-side integer / table helpers
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* lidbox/features/audio.py:185-189  ms_to_frames: int32(float32(sr) * 1e-3f * float32(ms)) */
+int lbx_ms_to_frames(int sample_rate, int ms);
+/* tf.signal.frame(pad_end=False) as used by tf.signal.stft at audio.py:229: max(0, 1 + (N - L) / step) */
+long long lbx_num_frames(long long n_samples, int frame_length, int frame_step);
+/* lidbox/features/mel_ops.py:28-75 (bug-compatible, fp32): writes W_host[n_bins * n_mel] row-major [n_bins, n_mel] */
+int lbx_mel_weight_matrix(int n_mel, int n_bins, int sample_rate, float lower_edge_hertz, float upper_edge_hertz,
+                          float* W_host);
+/* Band-compress a [n_bins, n_mel] weight matrix: for every mel column the contiguous range of non-zero rows.
+ * start_host/len_host/off_host have n_mel entries, packed_host must hold n_bins*n_mel floats in the worst case;
+ * returns the number of packed weights (>= 0) or <0 on error. */
+int lbx_mel_pack_bands(const float* W_host, int n_bins, int n_mel, int* start_host, int* len_host, int* off_host,
+                       float* packed_host);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Feature kernels (replace tf.signal.stft / abs / pow / tensordot / log behind lidbox.features.audio)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* lidbox/features/audio.py:219-230  spectrograms(): frame + periodic Hann + rFFT(fft_length) + |.|^power.
+ * sig [B, N] f32 -> out [B, T, fft_length/2+1] f32, T = lbx_num_frames(N, frame_length, frame_step).
+ * fft_length must be a power of two in [32, 4096] and >= frame_length. */
+int lbx_spectrogram_f32(const float* sig, long long B, long long N, int frame_length, int frame_step, int fft_length,
+                        float power, float* out, void* stream);
+
+/* lidbox/features/audio.py:247-261  linear_to_mel(): S [rows, n_bins] x band-packed W -> out [rows, n_mel].
+ * log_mode 0: none; 1: ln(x + eps) (lidbox/data/tf_utils.py:178). */
+int lbx_linear_to_mel_f32(const float* S, long long rows, int n_bins, int n_mel, const int* band_start,
+                          const int* band_len, const int* band_off, const float* band_w, int n_packed, int log_mode,
+                          float eps, float* out, void* stream);
+
+/* Fused spectrograms -> linear_to_mel -> [ln(x+eps)] (tf_utils.py:172-178) in one pass: sig [B,N] -> out [B,T,n_mel].
+ * Same argument rules as lbx_spectrogram_f32. workspace is needed only when the fused 512-point fast path does not
+ * apply (lbx_logmel_workspace_bytes() > 0); it then holds the intermediate power spectrogram. */
+size_t lbx_logmel_workspace_bytes(long long B, long long N, int frame_length, int frame_step, int fft_length,
+                                  int n_mel);
+int lbx_logmel_f32(const float* sig, long long B, long long N, int frame_length, int frame_step, int fft_length,
+                   float power, int n_mel, const int* band_start, const int* band_len, const int* band_off,
+                   const float* band_w, int n_packed, int log_mode, float eps, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* lidbox/features/audio.py:167-174  power_to_db(): 20*(log10(max(amin,S)) - log10(max(amin,max_all S))),
+ * floored at max_all(db) - top_db.  workspace: >= 16 bytes of device memory. */
+int lbx_power_to_db_f32(const float* S, long long numel, float amin, float top_db, float* out, void* workspace,
+                        void* stream);
+
+/* tf.debugging.assert_all_finite (tf_utils.py:173-194): writes 1 to *flag_dev (int32, device) if any element is
+ * NaN/Inf, leaves it untouched otherwise (caller zeroes it first). */
+int lbx_check_finite_f32(const float* x, long long numel, int* flag_dev, void* stream);
+
+/* Host-buffer entry point (the e2e path a non-torch caller binds): pageable or pinned HOST signals in,
+ * HOST log-mel out; device staging buffers are supplied by the caller (dev_sig >= B*N floats, dev_out >= B*T*n_mel). */
+int lbx_logmel_f32_host(const float* sig_host, long long B, long long N, int sample_rate, int frame_length_ms,
+                        int frame_step_ms, int fft_length, float power, int n_mel, float fmin, float fmax,
+                        int log_mode, float eps, float* out_host, float* dev_sig, float* dev_out, void* dev_tables,
+                        size_t dev_tables_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDBOX_B200_H */

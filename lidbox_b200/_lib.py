@@ -1,0 +1,84 @@
+"""ctypes binding of liblidbox_b200.so (include/lidbox_b200.h).  There is no CPU fallback: if the library is
+missing or a call fails, the error is raised to the caller."""
+import ctypes
+import os
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "liblidbox_b200.so")
+
+c_int, c_ll, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+_P = c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/lidbox_b200.h declares (tests/test_abi.py checks this)
+SIGNATURES = {
+    "lbx_last_error": (ctypes.c_char_p, []),
+    "lbx_version": (c_int, []),
+    "lbx_launch_count": (c_ll, []),
+    "lbx_ms_to_frames": (c_int, [c_int, c_int]),
+    "lbx_num_frames": (c_ll, [c_ll, c_int, c_int]),
+    "lbx_mel_weight_matrix": (c_int, [c_int, c_int, c_int, c_float, c_float, _P]),
+    "lbx_mel_pack_bands": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
+    "lbx_spectrogram_f32": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_float, _P, _P]),
+    "lbx_linear_to_mel_f32": (c_int, [_P, c_ll, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_float, _P, _P]),
+    "lbx_logmel_workspace_bytes": (c_size_t, [c_ll, c_ll, c_int, c_int, c_int, c_int]),
+    "lbx_logmel_f32": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_int, c_int,
+                               c_float, _P, _P, c_size_t, _P]),
+    "lbx_power_to_db_f32": (c_int, [_P, c_ll, c_float, c_float, _P, _P, _P]),
+    "lbx_check_finite_f32": (c_int, [_P, c_ll, _P, _P]),
+    "lbx_logmel_f32_host": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_float,
+                                    c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),
+}
+
+_lib = None
+
+
+class LidboxB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LidboxB200Error(
+                "%s is missing: build it with `python -m lidbox_b200.build` (nvcc, sm_100a). "
+                "lidbox_b200 has no CPU or library fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().lbx_last_error()
+        text = msg.decode() if msg else ""
+        if rc == -2:
+            raise NotImplementedError("lidbox_b200: " + text)
+        if rc == -1:
+            raise ValueError("lidbox_b200: " + text)
+        raise LidboxB200Error("lidbox_b200 error %d: %s" % (rc, text))
+
+
+def ptr(t):
+    """Device (or host) pointer of a contiguous tensor as a void*; None -> NULL."""
+    if t is None:
+        return None
+    assert t.is_contiguous()
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise LidboxB200Error("lidbox_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

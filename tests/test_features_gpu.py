@@ -1,0 +1,184 @@
+"""GPU parity tests (-m gpu): the CUDA feature kernels, called through the C-ABI, against the CPU oracle.
+
+Tolerances (fp32 kernels vs the fp64 oracle):
+  spectrograms / linear_to_mel : normwise per utterance, max|a-b| <= 1e-4 * max|b|  (SURVEY §7 hard part 6)
+  log-mel                      : elementwise atol 1e-4 + rtol 1e-4
+  power_to_db                  : atol 2e-3 dB (20*log10 amplifies fp32 log rounding near the clip floor)
+  frame counts / shapes        : exact
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lidbox_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def audio(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from lidbox_b200.features import audio as a
+    return a
+
+
+def _signals(B, N, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(N, dtype=torch.float64) / 16000.0
+    f = 100.0 + 3900.0 * torch.rand(B, 1, generator=g, dtype=torch.float64)
+    x = 0.5 * torch.sin(2 * np.pi * f * t) + 0.05 * torch.randn(B, N, generator=g, dtype=torch.float64)
+    return x.to(torch.float32).numpy()
+
+
+def _normwise(a, b):
+    a = a.reshape(a.shape[0], -1).astype(np.float64)
+    b = b.reshape(b.shape[0], -1).astype(np.float64)
+    return (np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1e-30)).max()
+
+
+def test_cfg1_sweeps_logmel(audio):
+    # BASELINE config 1: 4 x 1 s @ 16 kHz exponential sine sweeps, amplitude -3 dBFS
+    import scipy.signal
+    t = np.arange(16000) / 16000.0
+    sig = np.stack([0.7079 * scipy.signal.chirp(t, 100 * 2 ** i, 1.0, min(7900, 1600 * 2 ** i), method="logarithmic",
+                                                phi=-90) for i in range(4)]).astype(np.float32)
+    ref = O.logmel(sig, 16000, dtype=np.float64)
+    out = audio.logmelspectrograms(sig, 16000).cpu().numpy()
+    assert out.shape == (4, 98, 40)
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)
+    # unfused chain through the drop-in names gives the same result
+    S = audio.spectrograms(sig, 16000)
+    M = audio.linear_to_mel(S, 16000)
+    np.testing.assert_allclose(torch.log(M + 1e-6).cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,sec", [(1, 1), (3, 2), (64, 2), (5, 5)])
+def test_spectrogram_and_mel_values(audio, B, sec):
+    sig = _signals(B, 16000 * sec)
+    S_ref = O.spectrograms(sig, 16000, dtype=np.float64)
+    S = audio.spectrograms(sig, 16000).cpu().numpy()
+    assert S.shape == S_ref.shape == (B, 1 + (16000 * sec - 400) // 160, 257)
+    assert _normwise(S, S_ref) < 1e-4
+    M_ref = O.linear_to_mel(S_ref, 16000, dtype=np.float64)
+    M = audio.linear_to_mel(S, 16000).cpu().numpy()
+    assert _normwise(M, M_ref) < 1e-4
+    lm = audio.logmelspectrograms(sig, 16000).cpu().numpy()
+    np.testing.assert_allclose(lm, O.log_eps(M_ref), rtol=1e-4, atol=1e-4)
+
+
+def test_golden_wav_fixtures(audio):
+    g = np.load(os.path.join(GOLDEN, "wav_fixtures.npz"))
+    sig = g["pcm"].astype(np.float32) / np.float32(32768.0)
+    lm = audio.logmelspectrograms(sig, 16000).cpu().numpy()
+    np.testing.assert_allclose(lm, g["logmel"], rtol=1e-4, atol=1e-4)
+    S = audio.spectrograms(sig, 16000)
+    np.testing.assert_allclose(S.sum(dim=2).cpu().numpy(), g["spec_rowsum"], rtol=1e-4)
+    db = audio.power_to_db(S).cpu().numpy()[:, ::8, ::16]
+    np.testing.assert_allclose(db, g["db"], atol=2e-3)
+
+
+def test_reference_test_spectrograms_grid(audio):
+    # /root/reference/tests/test_features_audio.py:131-145 on a synthetic 3 s signal + value parity (generic FFT path)
+    s = _signals(1, 48000, seed=5)
+    for len_ms in range(20, 101, 20):
+        for n_fft in (256, 512, 1024, 2048):
+            if n_fft < audio.ms_to_frames(16000, len_ms):
+                continue
+            step_ms = len_ms // 2
+            P = audio.spectrograms(s, 16000, frame_length_ms=len_ms, frame_step_ms=step_ms, fft_length=n_fft)[0]
+            P = P.cpu().numpy()
+            assert not np.isnan(P).any()
+            assert P.shape[0] == s.shape[1] // audio.ms_to_frames(16000, step_ms) - 1
+            assert P.shape[1] == n_fft // 2 + 1
+            ref = O.spectrograms(s, 16000, len_ms, step_ms, 2.0, n_fft, dtype=np.float64)[0]
+            assert _normwise(P[None], ref[None]) < 1e-4
+
+
+def test_reference_test_linear_to_mel_grid(audio):
+    # tests/test_features_audio.py:147-155 + values
+    s = _signals(1, 48000, seed=6)
+    P = audio.spectrograms(s, 16000)
+    P_ref = O.spectrograms(s, 16000, dtype=np.float64)
+    for num_mel_bins in range(10, 100, 15):
+        M = audio.linear_to_mel(P, 16000, num_mel_bins=num_mel_bins)[0].cpu().numpy()
+        assert not np.isnan(M).any()
+        assert M.shape == (P.shape[1], num_mel_bins)
+        ref = O.linear_to_mel(P_ref, 16000, num_mel_bins=num_mel_bins, dtype=np.float64)[0]
+        assert _normwise(M[None], ref[None]) < 1e-4
+        # fused kernel with a non-default mel count
+        lm = audio.logmelspectrograms(s, 16000, num_mel_bins=num_mel_bins)[0].cpu().numpy()
+        np.testing.assert_allclose(lm, np.log(ref + 1e-6), rtol=1e-4, atol=1e-4)
+
+
+def test_reference_test_power_to_db(audio):
+    # tests/test_features_audio.py:115-123 (+ oracle values)
+    s = _signals(2, 16000, seed=7)
+    P = O.spectrograms(s, 16000)
+    for top_db in range(10, 110, 10):
+        db = audio.power_to_db(P, top_db=float(top_db)).cpu().numpy()
+        assert not np.isnan(db).any()
+        assert db.max() <= 0
+        np.testing.assert_allclose(db, O.power_to_db(P, top_db=float(top_db)), atol=2e-3)
+
+
+def test_power_and_frame_parameter_variants(audio):
+    s = _signals(2, 12345, seed=8)        # odd length
+    for (len_ms, step_ms, power, n_fft) in ((25, 10, 1.0, 512), (25, 10, 1.5, 512), (20, 7, 2.0, 512),
+                                           (32, 16, 2.0, 512), (25, 10, 2.0, 1024), (5, 3, 2.0, 128)):
+        ref = O.spectrograms(s, 16000, len_ms, step_ms, power, n_fft, dtype=np.float64)
+        out = audio.spectrograms(s, 16000, len_ms, step_ms, power, n_fft).cpu().numpy()
+        assert out.shape == ref.shape
+        assert _normwise(out, ref) < 1e-4
+    # 11.025 kHz: frame_length 275 (odd), frame_step 110 -> exercises the unaligned shared-memory path
+    ref = O.spectrograms(s, 11025, dtype=np.float64)
+    out = audio.spectrograms(s, 11025).cpu().numpy()
+    assert out.shape == ref.shape and _normwise(out, ref) < 1e-4
+    ref = O.spectrograms(s, 22050, 5, 1, dtype=np.float64)    # L = 110, step = 22
+    out = audio.spectrograms(s, 22050, 5, 1).cpu().numpy()
+    assert out.shape == ref.shape and _normwise(out, ref) < 1e-4
+
+
+def test_edge_cases(audio):
+    # shorter than one frame -> T == 0; exactly one frame; ragged tail; empty batch
+    assert audio.spectrograms(np.zeros((2, 399), np.float32), 16000).shape == (2, 0, 257)
+    assert audio.logmelspectrograms(np.zeros((2, 399), np.float32), 16000).shape == (2, 0, 40)
+    assert audio.spectrograms(np.zeros((0, 16000), np.float32), 16000).shape == (0, 98, 257)
+    one = _signals(1, 400, seed=9)
+    np.testing.assert_allclose(audio.logmelspectrograms(one, 16000).cpu().numpy(), O.logmel(one, 16000, dtype=np.float64),
+                               rtol=1e-4, atol=1e-4)
+    for N in (559, 560, 561, 400 + 160 * 32, 400 + 160 * 33 - 1):
+        x = _signals(2, N, seed=N)
+        ref = O.logmel(x, 16000, dtype=np.float64)
+        out = audio.logmelspectrograms(x, 16000).cpu().numpy()
+        assert out.shape == ref.shape
+        np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)
+    # all-zero signal: log(0 + 1e-6)
+    z = audio.logmelspectrograms(np.zeros((1, 16000), np.float32), 16000).cpu().numpy()
+    np.testing.assert_allclose(z, np.log(1e-6), rtol=1e-6)
+    with pytest.raises(ValueError):
+        audio.spectrograms(np.zeros(16000, np.float32), 16000)          # rank 1 (tf_utils.py:168)
+    with pytest.raises(NotImplementedError):
+        audio.spectrograms(np.zeros((1, 16000), np.float32), 16000, fft_length=500)
+
+
+def test_full_size_properties(audio):
+    # BASELINE sweep maximum (2048 x 5 s): linearity and batch-invariance instead of a CPU comparison
+    B, N = 2048, 80000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(B, N, generator=g, device="cuda") * 0.1
+    S = audio.spectrograms(x[:64], 16000)
+    S2 = audio.spectrograms(2.0 * x[:64], 16000)
+    assert torch.allclose(S2, 4.0 * S, rtol=1e-5, atol=0)              # |2x|^2 = 4|x|^2 exactly in fp32
+    lm = audio.logmelspectrograms(x, 16000)
+    assert lm.shape == (B, 498, 40) and torch.isfinite(lm).all()
+    # each utterance is independent of its position in the batch
+    lm_b = audio.logmelspectrograms(x[1000:1003], 16000)
+    assert torch.equal(lm_b, lm[1000:1003])
+    # Parseval on the power spectrogram of one frame: sum_k c_k |X_k|^2 = 512 * sum_n (x_n w_n)^2
+    fr = x[7, :400].double().cpu().numpy() * O.hann_window(400, np.float64)
+    P = S[7, 0].double().cpu().numpy()
+    lhs = P[0] + P[256] + 2 * P[1:256].sum()
+    assert abs(lhs - 512 * (fr ** 2).sum()) / lhs < 1e-5

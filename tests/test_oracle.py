@@ -1,0 +1,202 @@
+"""CPU tests (-m "not gpu"): pin the oracle against everything the reference's own tests hold for this path
+ and against the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lidbox_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_ms_to_frames_reference_kat():
+    # /root/reference/tests/test_features_audio.py:125-129 (exact)
+    for sr in range(1000, 60000, 1000):
+        for ms in range(1, 5000, 100):
+            assert O.ms_to_frames(sr, ms) == (sr // 1000) * ms
+
+
+def test_ms_to_frames_truncation():
+    assert O.ms_to_frames(16000, 25) == 400 and O.ms_to_frames(16000, 10) == 160
+    assert O.ms_to_frames(44100, 25) == 1102
+
+
+def test_fft_frequencies_reference():
+    # tests/test_features_audio.py:99-104 compares with librosa.fft_frequencies == np.linspace(0, sr/2, 1+n//2)
+    # at 1e-9; the reference returns fp32, so the bound that can hold for non-representable points is fp32 rounding.
+    for sr in range(4000, 60000, 4000):
+        for n_fft in (2 ** i for i in range(1, 13)):
+            a = O.fft_frequencies(sr, n_fft)
+            b = np.linspace(0, sr / 2, 1 + n_fft // 2)
+            assert a.shape == b.shape
+            assert np.abs(a - b).max() <= np.spacing(np.float32(sr / 2))
+
+
+def test_log10_reference():
+    # tests/test_features_audio.py:106-113
+    rng = np.random.default_rng(0)
+    for rank in range(1, 5):
+        x = np.maximum(1e-12, rng.normal(1e6, 1e4, size=rng.integers(1, 10, size=rank)))
+        assert np.abs(np.log10(x) - O.log10(x.astype(np.float32))).max() < 1e-6
+
+
+def test_spectrogram_shapes_reference():
+    # tests/test_features_audio.py:131-145: T == N // step - 1 when step = len/2, bins == n_fft//2 + 1
+    s = np.random.default_rng(1).standard_normal(48000).astype(np.float32) * 0.1
+    for len_ms in range(20, 101, 20):
+        for n_fft in (256, 512, 1024, 2048):
+            if n_fft < O.ms_to_frames(16000, len_ms):
+                continue
+            step_ms = len_ms // 2
+            P = O.spectrograms(s[None], 16000, frame_length_ms=len_ms, frame_step_ms=step_ms, fft_length=n_fft)[0]
+            assert not np.isnan(P).any()
+            assert P.shape[0] == s.shape[0] // O.ms_to_frames(16000, step_ms) - 1
+            assert P.shape[1] == n_fft // 2 + 1
+
+
+def test_linear_to_mel_shapes_reference():
+    # tests/test_features_audio.py:147-155
+    s = np.random.default_rng(2).standard_normal((1, 16000)).astype(np.float32) * 0.1
+    P = O.spectrograms(s, 16000)
+    for num_mel_bins in range(10, 100, 15):
+        M = O.linear_to_mel(P, 16000, num_mel_bins=num_mel_bins)[0]
+        assert not np.isnan(M).any()
+        assert M.shape == (P.shape[1], num_mel_bins)
+
+
+def test_power_to_db_reference():
+    # tests/test_features_audio.py:115-123
+    s = np.random.default_rng(3).standard_normal((1, 16000)).astype(np.float32) * 0.1
+    P = O.spectrograms(s, 16000)
+    for top_db in range(10, 110, 10):
+        db = O.power_to_db(P, top_db=float(top_db))
+        assert not np.isnan(db).any()
+        assert db.max() <= 0
+        assert db.min() >= -top_db - 1e-4
+
+
+def test_stft_matches_direct_dft():
+    # independent check of frame + periodic Hann + end zero-padding against a literal DFT sum
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(700)
+    L, step, nfft = 400, 160, 512
+    S = O.stft(x[None], L, step, nfft, dtype=np.float64)[0]
+    assert S.shape == (2, 257)
+    n = np.arange(L)
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * n / L)
+    for t in range(2):
+        fr = x[t * step:t * step + L] * w
+        for k in (0, 1, 17, 128, 256):
+            ref = (fr * np.exp(-2j * np.pi * k * n / nfft)).sum()
+            assert abs(S[t, k] - ref) < 1e-9
+
+
+def test_mel_matrix_quirks():
+    # _linspace divides by num -> FFT bins 241..256 carry no weight, <= 2 non-zeros per bin
+    W = O.linear_to_mel_weight_matrix(40, 257, 16000, 0.0, 8000.0)
+    assert W.shape == (257, 40) and W.dtype == np.float32
+    assert (W[0] == 0).all() and (W[241:] == 0).all()
+    assert ((W != 0).sum(axis=1) <= 2).all()
+    assert (W != 0).sum() == 464
+    assert W.min() >= 0 and W.max() <= 1
+    # differs from the true-linspace (TF/HTK) matrix: this oracle is deliberately bug-compatible
+    lin = np.linspace(0, 8000, 257)[1:]
+    mel = 1127.0 * np.log1p(lin / 700.0)
+    e = np.linspace(1127.0 * np.log1p(0 / 700.0), 1127.0 * np.log1p(8000 / 700.0), 42)
+    Wt = np.maximum(0, np.minimum((mel[:, None] - e[None, :40]) / (e[None, 1:41] - e[None, :40]),
+                                  (e[None, 2:] - mel[:, None]) / (e[None, 2:] - e[None, 1:41])))
+    assert np.abs(W[1:] - Wt).max() > 0.5
+
+
+def test_golden_mel_tables():
+    g = np.load(os.path.join(GOLDEN, "mel_tables.npz"))
+    for key in g.files:
+        _, m, k, sr = key.split("_")
+        lo, hi = {"16000": (0.0, 8000.0), "8000": (125.0, 3800.0), "44100": (20.0, 11025.0)}[sr]
+        W = O.linear_to_mel_weight_matrix(int(m), int(k), int(sr), lo, hi)
+        assert np.array_equal(W, g[key])
+
+
+def test_golden_wav_fixtures():
+    g = np.load(os.path.join(GOLDEN, "wav_fixtures.npz"))
+    sig = g["pcm"].astype(np.float32) / np.float32(32768.0)
+    lm = O.logmel(sig, 16000, dtype=np.float64)
+    assert lm.shape == (5, 48, 40)
+    np.testing.assert_allclose(lm, g["logmel"], rtol=1e-5, atol=1e-5)
+    lm32 = O.logmel(sig, 16000, dtype=np.float32)
+    np.testing.assert_allclose(lm32, g["logmel"], rtol=1e-4, atol=1e-4)
+
+
+def test_conv_lengths_and_causality():
+    rng = np.random.default_rng(5)
+    for T in (1, 2, 5, 6, 7, 198):
+        x = rng.standard_normal((2, T, 3))
+        for k, s in ((5, 1), (3, 2), (3, 3), (1, 1)):
+            w = rng.standard_normal((k, 3, 4))
+            y = O.conv1d_causal(x, w, np.zeros(4), s, relu=False)
+            assert y.shape == (2, -(-T // s), 4)
+            # literal definition, SURVEY App. A.8
+            t = y.shape[1] - 1
+            ref = sum(x[:, t * s + j - (k - 1), :] @ w[j] for j in range(k) if t * s + j - (k - 1) >= 0)
+            np.testing.assert_allclose(y[:, t], ref, atol=1e-12)
+
+
+def test_xvector_edge_shapes_reference():
+    # tests/test_models.py:104-107 + testutil.py:29-35: B,T,F >= 1, num_outputs 1..100, no NaN, shape (B, n_out)
+    rng = np.random.default_rng(6)
+    for (B, T, F, n_out) in ((1, 1, 1, 1), (2, 7, 3, 100), (10, 400, 100, 4), (3, 2, 40, 7)):
+        x = rng.uniform(-1e3, 1e3, size=(B, T, F)).astype(np.float32)
+        p = O.xvector_init(F, n_out, seed=B)
+        y = O.xvector_forward(p, x)
+        assert y.shape == (B, n_out) and not np.isnan(y).any()
+        np.testing.assert_allclose(np.exp(y.astype(np.float64)).sum(axis=1), 1.0, rtol=1e-4)
+    # T == 1 -> std = sqrt(clip) = 1e-5
+    x = rng.standard_normal((1, 1, 4)).astype(np.float64)
+    _, acts = O.xvector_forward(O.xvector_init(4, 3, dtype=np.float64), x, return_activations=True)
+    np.testing.assert_allclose(acts["stats_pooling"][0, 1500:], 1e-5)
+
+
+def test_xvector_numpy_vs_torch_twin_and_golden():
+    import torch
+    g = np.load(os.path.join(GOLDEN, "xvector_small.npz"))
+    params = O.xvector_init(24, 5, seed=11, bias_scale=0.05)
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    logp = O.xvector_forward(p64, g["x"].astype(np.float64))
+    np.testing.assert_allclose(logp, g["logp"], atol=1e-10)
+    np.testing.assert_allclose(O.xvector_forward(p64, g["x"].astype(np.float64), embedding=True), g["emb"], atol=1e-10)
+    tp = {k: torch.tensor(v, dtype=torch.float64) for k, v in p64.items()}
+    lp_t = O.torch_xvector_forward(tp, torch.tensor(g["x"], dtype=torch.float64)).numpy()
+    np.testing.assert_allclose(lp_t, logp, atol=1e-10)
+    assert abs(O.sparse_xent_on_logprobs(g["y"], logp) - float(g["loss"])) < 1e-12
+
+
+def test_param_count_reference():
+    # 4 508 124 + 513 * num_outputs parameters for F = 40
+    for n_out in (4, 50):
+        n = sum(int(np.prod(s)) for s in O.xvector_param_shapes(40, n_out).values())
+        assert n == 4508124 + 513 * n_out
+
+
+def test_ap_loss_golden_and_properties():
+    g = np.load(os.path.join(GOLDEN, "ap_loss.npz"))
+    N, w = int(g["N"]), float(g["delta_weight"])
+    per = O.ap_loss_per_sample(g["y"], g["z"], N, w)
+    np.testing.assert_allclose(per, g["per_sample"], atol=1e-12)
+    assert abs(per.mean() - float(g["loss"])) < 1e-12
+    # losses.py:48-49 with one-hot c_T: theta == acos of the first N coordinates
+    c_T = np.eye(N, g["z"].shape[1]).T
+    np.testing.assert_allclose(O.ap_theta(g["z"], N), np.arccos(g["z"] @ c_T), atol=1e-12)
+    # gradient is zero for coordinates >= N
+    assert np.abs(g["grad"][:, N:]).max() == 0
+    # a perfectly aligned vector has the smallest loss for its class
+    z = np.eye(12)[:3] * 0.999
+    assert O.ap_loss_per_sample([0, 1, 2], z, N).max() < O.ap_loss_per_sample([1, 2, 0], z, N).min()
+
+
+def test_torch_logmel_baseline_matches_oracle():
+    import torch
+    s = np.random.default_rng(8).standard_normal((2, 16000)).astype(np.float32) * 0.1
+    a = O.torch_logmel(torch.from_numpy(s)).numpy()
+    b = O.logmel(s, 16000, dtype=np.float64)
+    np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-4)

@@ -1,0 +1,498 @@
+// TMA-fed tcgen05 GEMM for the x-vector TDNN (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every dense contraction of lidbox/models/xvector.py:
+//   layout NT :  C[M,N] = A[M,K] . B[N,K]^T      forward Conv1D / Dense (xvector.py:38-43,53-64) and data gradients
+//   layout TN :  C[M,N] = A[K,M]^T . B[K,N]      weight gradients (contraction over the batch*time rows), split-K
+// A causal strided Conv1D is an NT GEMM without im2col: activations are NWC with k-1 zero rows in front of every
+// utterance, so row (b,t) of the implicit matrix is the k*C_in contiguous elements starting at padded time t*stride;
+// the A operand is a plain 2-D TMA view whose row pitch (stride*C_in) is smaller than its width (k*C_in).
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/mask -> global).  Operands are bf16 in 128B-swizzled
+// shared memory (4 stages x 48 KB), accumulators fp32 in TMEM, double-buffered (2 x 256 columns) so the epilogue
+// of tile i overlaps the main loop of tile i+1.  "bf16x3" mode runs three accumulating passes
+// (A_hi B_hi + A_hi B_lo + A_lo B_hi) for fp32-grade results from bf16 tensor cores.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
+namespace lbx {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES = BN * BK * 2;          // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 512;                // 2 accumulator stages x 256 fp32 columns
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  int M, N, K;             // output rows, output cols, contraction length
+  int layout;              // 0 NT, 1 TN
+  int n_terms;             // 1 or 3 (bf16x3)
+  int k_splits;            // split-K partitions (>= 1)
+  int epi_atomic;          // 1: atomicAdd fp32 into out (split-K / gradient accumulation)
+  int out_dtype;           // LBX_F32 / LBX_BF16
+  void* out;
+  void* out_lo;            // optional bf16 residual plane (x - bf16(x)); out_dtype must be BF16
+  long long ldo;           // output row pitch in elements (may be < N for the overlapping dgrad view)
+  const float* bias;       // [N] or NULL
+  int relu;
+  int rows_per_utt;        // > 0: rows with (m % rows_per_utt) >= valid_rows are not stored
+  int valid_rows;
+  const __nv_bfloat16* mask_src;   // optional: keep x only where mask_src[m*ldo + n] > 0 (ReLU backward)
+  int accumulate;          // 1: out = out + x (read-modify-write, non-atomic)
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address  [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // leading byte offset [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;       // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                                 // descriptor version = 1
+  d |= (uint64_t)2 << 61;                                 // layout type: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M=128, N=256
+__host__ __device__ constexpr uint32_t make_idesc(int a_mn_major, int b_mn_major) {
+  return (1u << 4)                       // c_format = F32
+         | (1u << 7)                     // a_format = BF16
+         | (1u << 10)                    // b_format = BF16
+         | ((uint32_t)a_mn_major << 15)  // a_major
+         | ((uint32_t)b_mn_major << 16)  // b_major
+         | ((uint32_t)(BN >> 3) << 17)   // n_dim
+         | ((uint32_t)(BM >> 4) << 24);  // m_dim
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                     const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+                     const GemmParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int total_tiles = mn_tiles * p.k_splits;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapB0);
+    if (p.n_terms == 3) {
+      tma_prefetch_desc(&mapA1);
+      tma_prefetch_desc(&mapB1);
+    }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar + i, 1);
+      mbar_init(empty_bar + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + i, 1);
+      mbar_init(tempty_bar + i, 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / mn_tiles, rem = tile - split * mn_tiles;
+        const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
+        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int term = 0; term < p.n_terms; ++term) {
+          const CUtensorMap* mA = (term == 2) ? &mapA1 : &mapA0;
+          const CUtensorMap* mB = (term == 1) ? &mapB1 : &mapB0;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            unsigned char* sA = smem + (size_t)stage * STAGE_BYTES;
+            unsigned char* sB = sA + A_BYTES;
+            mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+            if (LAYOUT == 0) {
+              tma_load_2d(mA, full_bar + stage, sA, kb * BK, m_blk * BM);
+              tma_load_2d(mB, full_bar + stage, sB, kb * BK, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_2d(mA, full_bar + stage, sA + i * 8192, m_blk * BM + i * 64, kb * BK);
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(mB, full_bar + stage, sB + i * 8192, n_blk * BN + i * 64, kb * BK);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(LAYOUT, LAYOUT);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / mn_tiles;
+        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        const int iters = (kb1 - kb0) * p.n_terms;
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            uint64_t da, db;
+            if (LAYOUT == 0) {   // K-major: 8-row groups are 1024 B apart; advance 32 B per UMMA_K inside the swizzle atom
+              da = make_smem_desc(sA + k * (UMMA_K * 2), 16, 1024);
+              db = make_smem_desc(sB + k * (UMMA_K * 2), 16, 1024);
+            } else {             // MN-major: 64-element blocks are 8192 B apart (LBO), 8 k-rows = 1024 B (SBO)
+              da = make_smem_desc(sA + k * (UMMA_K * 128), 8192, 1024);
+              db = make_smem_desc(sB + k * (UMMA_K * 128), 8192, 1024);
+            }
+            tc_mma_bf16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar + stage);          // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar + acc);              // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    const int sub = warp & 3;                    // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / mn_tiles, rem = tile - split * mn_tiles;
+      const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
+      (void)split;
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const int m = m_blk * BM + sub * 32 + lane;
+      bool row_ok = m < p.M;
+      if (p.rows_per_utt > 0) row_ok = row_ok && ((m % p.rows_per_utt) < p.valid_rows);
+      const long long row_off = (long long)m * p.ldo;
+      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= p.N) break;
+        uint32_t v[32];
+        tc_ld32(taddr + c * 32, v);
+        tc_wait_ld();
+        if (row_ok) {
+          const int ncols = min(32, p.N - n0);
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) x[j] += __ldg(p.bias + n0 + j);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+          }
+          if (p.mask_src != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols && !(__bfloat162float(p.mask_src[row_off + n0 + j]) > 0.0f)) x[j] = 0.0f;
+          }
+          if (p.epi_atomic) {
+            float* o = reinterpret_cast<float*>(p.out) + row_off + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) atomicAdd(o + j, x[j]);
+          } else if (p.out_dtype == LBX_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + row_off + n0;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) x[j] += o[j];
+            }
+            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(o)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) o[j] = x[j];
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n0;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) x[j] += __bfloat162float(o[j]);
+            }
+            const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+            if (vec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                reinterpret_cast<uint4*>(o)[q] =
+                    make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
+                               pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) o[j] = __float2bfloat16_rn(x[j]);
+            }
+            if (p.out_lo != nullptr) {
+              __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + row_off + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] -= __bfloat162float(__float2bfloat16_rn(x[j]));
+              if (vec && ((reinterpret_cast<uintptr_t>(ol) & 15) == 0)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  reinterpret_cast<uint4*>(ol)[q] =
+                      make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
+                                 pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) ol[j] = __float2bfloat16_rn(x[j]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner extent `cols` (pitch 1), outer extent `rows` with pitch `ld` elements (ld may be < cols)
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
+                    int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(LBX_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LBX_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld base=%p", (int)r, rows,
+                     cols, ld, base);
+  return LBX_OK;
+}
+
+static int g_num_sms = 0;
+
+}  // namespace lbx
+
+using namespace lbx;
+
+extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
+  LBX_CHECK_ARG(g != nullptr, "NULL gemm descriptor");
+  LBX_CHECK_ARG(g->layout == 0 || g->layout == 1, "layout must be 0 (NT) or 1 (TN)");
+  LBX_CHECK_ARG(g->n_terms == 1 || g->n_terms == 3, "n_terms must be 1 or 3");
+  LBX_CHECK_ARG(g->a_rows >= 0 && g->a_cols >= 0 && g->b_rows >= 0 && g->b_cols >= 0, "negative extent");
+  GemmParams p{};
+  p.layout = g->layout;
+  if (g->layout == 0) {
+    LBX_CHECK_ARG(g->a_cols == g->b_cols, "NT: A and B must share the contraction length (%d vs %d)", g->a_cols,
+                  g->b_cols);
+    LBX_CHECK_ARG(g->a_rows <= 2147483647LL && g->b_rows <= 2147483647LL, "extent too large");
+    p.M = (int)g->a_rows; p.N = (int)g->b_rows; p.K = g->a_cols;
+  } else {
+    LBX_CHECK_ARG(g->a_rows == g->b_rows, "TN: A and B must share the contraction length (%lld vs %lld)", g->a_rows,
+                  g->b_rows);
+    LBX_CHECK_ARG(g->a_rows <= 2147483647LL, "extent too large");
+    p.M = g->a_cols; p.N = g->b_cols; p.K = (int)g->a_rows;
+  }
+  if (p.M == 0 || p.N == 0) return LBX_OK;
+  LBX_CHECK_ARG(p.K > 0, "empty contraction");
+  LBX_CHECK_ARG(g->a0 && g->b0 && g->out, "NULL operand");
+  LBX_CHECK_ARG(g->n_terms == 1 || (g->a1 && g->b1), "bf16x3 needs the lo planes a1/b1");
+  LBX_CHECK_ARG(g->lda % 8 == 0 && g->ldb % 8 == 0, "operand pitches must be multiples of 8 elements (16 bytes)");
+  LBX_CHECK_ARG((reinterpret_cast<uintptr_t>(g->a0) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->b0) & 15) == 0,
+                "operands must be 16-byte aligned");
+  LBX_CHECK_ARG(g->out_dtype == LBX_F32 || g->out_dtype == LBX_BF16, "bad out_dtype");
+  LBX_CHECK_ARG(!g->epi_atomic || g->out_dtype == LBX_F32, "atomic epilogue needs an fp32 output");
+  LBX_CHECK_ARG(g->out_lo == nullptr || g->out_dtype == LBX_BF16, "out_lo needs a bf16 output");
+  LBX_CHECK_ARG(g->k_splits >= 1, "k_splits must be >= 1");
+  LBX_CHECK_ARG(g->k_splits == 1 || g->epi_atomic, "split-K needs the atomic epilogue");
+  p.n_terms = g->n_terms;
+  const int kb_total = (p.K + BK - 1) / BK;
+  int ks = g->k_splits < kb_total ? g->k_splits : kb_total;
+  const int per = (kb_total + ks - 1) / ks;
+  ks = (kb_total + per - 1) / per;      // no empty split
+  p.k_splits = ks;
+  p.epi_atomic = g->epi_atomic;
+  p.out_dtype = g->out_dtype;
+  p.out = g->out; p.out_lo = g->out_lo; p.ldo = g->ldo;
+  p.bias = g->bias; p.relu = g->relu;
+  p.rows_per_utt = g->rows_per_utt; p.valid_rows = g->valid_rows;
+  p.mask_src = reinterpret_cast<const __nv_bfloat16*>(g->mask_src);
+  p.accumulate = g->accumulate;
+
+  CUtensorMap mA0, mA1, mB0, mB1;
+  int rc;
+  const int boxA_rows = g->layout == 0 ? BM : 64, boxB_rows = g->layout == 0 ? BN : 64;
+  if ((rc = make_map(&mA0, g->a0, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
+  if ((rc = make_map(&mB0, g->b0, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
+  if (g->n_terms == 3) {
+    if ((rc = make_map(&mA1, g->a1, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
+    if ((rc = make_map(&mB1, g->b1, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
+  } else {
+    mA1 = mA0; mB1 = mB0;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    LBX_CUDA(cudaGetDevice(&dev));
+    LBX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    g_num_sms = n;
+    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  }
+  const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.k_splits;
+  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g->layout == 0)
+    gemm_bf16_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(mA0, mA1, mB0, mB1, p);
+  else
+    gemm_bf16_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(mA0, mA1, mB0, mB1, p);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}

@@ -100,6 +100,40 @@ int lbx_logmel_f32_host(const float* sig_host, long long B, long long N, int sam
                         int log_mode, float eps, float* out_host, float* dev_sig, float* dev_out, void* dev_tables,
                         size_t dev_tables_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * TDNN contractions (replace Keras Conv1D / Dense behind lidbox/models/xvector.py:38-43,53-64 and their gradients)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* One bf16 tensor-core GEMM (tcgen05, fp32 accumulation in TMEM) with a fused epilogue.
+ *   layout 0 (NT):  C[M,N] = A[M,K] . B[N,K]^T   M = a_rows, K = a_cols = b_cols, N = b_rows
+ *   layout 1 (TN):  C[M,N] = A[K,M]^T . B[K,N]   K = a_rows = b_rows, M = a_cols, N = b_cols
+ * A/B are bf16 views: `rows` x `cols` with row pitch ld (elements, multiple of 8; may be SMALLER than cols: a causal
+ * Conv1D with kernel k and stride s over NWC activations is the NT GEMM whose A view has cols = k*C_in and
+ * lda = s*C_in on the zero-left-padded activation buffer — no im2col).
+ * n_terms = 3 ("bf16x3"): a1/b1 hold the bf16 residual planes (x - bf16(x)); the kernel accumulates
+ * a0.b0 + a0.b1 + a1.b0 for fp32-grade results (forward fp32 config).
+ * Epilogue, per output element (m, n), in this order: + bias[n]; ReLU; zero unless mask_src[m*ldo+n] > 0;
+ * then either atomicAdd into fp32 out (epi_atomic, required for k_splits > 1), or out (+)= x as fp32 / bf16
+ * (plus out_lo = bf16 residual).  Rows with (m % rows_per_utt) >= valid_rows are not stored when rows_per_utt > 0. */
+typedef struct lbx_gemm_t {
+  const void* a0; const void* a1;
+  long long a_rows; int a_cols; long long lda;
+  const void* b0; const void* b1;
+  long long b_rows; int b_cols; long long ldb;
+  int layout;
+  int n_terms;
+  int k_splits;
+  int epi_atomic;
+  int out_dtype;            /* LBX_F32 | LBX_BF16 */
+  void* out; void* out_lo; long long ldo;
+  const float* bias;
+  int relu;
+  int rows_per_utt; int valid_rows;
+  const void* mask_src;     /* bf16, indexed like out */
+  int accumulate;
+} lbx_gemm_t;
+int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

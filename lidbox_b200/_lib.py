@@ -11,6 +11,19 @@ LIB_PATH = os.path.join(_PKG_DIR, "liblidbox_b200.so")
 c_int, c_ll, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 _P = c_void_p
 
+
+
+class GemmDesc(ctypes.Structure):
+    """lbx_gemm_t (include/lidbox_b200.h)."""
+    _fields_ = [
+        ("a0", c_void_p), ("a1", c_void_p), ("a_rows", c_ll), ("a_cols", c_int), ("lda", c_ll),
+        ("b0", c_void_p), ("b1", c_void_p), ("b_rows", c_ll), ("b_cols", c_int), ("ldb", c_ll),
+        ("layout", c_int), ("n_terms", c_int), ("k_splits", c_int), ("epi_atomic", c_int), ("out_dtype", c_int),
+        ("out", c_void_p), ("out_lo", c_void_p), ("ldo", c_ll), ("bias", c_void_p), ("relu", c_int),
+        ("rows_per_utt", c_int), ("valid_rows", c_int), ("mask_src", c_void_p), ("accumulate", c_int),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/lidbox_b200.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
     "lbx_last_error": (ctypes.c_char_p, []),
@@ -27,6 +40,7 @@ SIGNATURES = {
                                c_float, _P, _P, c_size_t, _P]),
     "lbx_power_to_db_f32": (c_int, [_P, c_ll, c_float, c_float, _P, _P, _P]),
     "lbx_check_finite_f32": (c_int, [_P, c_ll, _P, _P]),
+    "lbx_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), _P]),
     "lbx_logmel_f32_host": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_float,
                                     c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),
 }

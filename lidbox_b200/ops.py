@@ -1,0 +1,40 @@
+"""Thin Python wrappers over the TDNN entry points of the C-ABI (include/lidbox_b200.h).  Tensors are torch CUDA
+tensors used purely as device memory; every function enqueues hand-written kernels on the current stream."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+
+
+def _addr(t, offset_elems=0):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr() + offset_elems * t.element_size())
+
+
+def gemm(a, a_rows, a_cols, lda, b, b_rows, b_cols, ldb, out, ldo, *, layout=0, a_lo=None, b_lo=None, out_lo=None,
+         a_off=0, b_off=0, out_off=0, k_splits=1, epi_atomic=False, bias=None, relu=False, rows_per_utt=0,
+         valid_rows=0, mask_src=None, mask_off=0, accumulate=False):
+    """lbx_gemm_bf16: see lbx_gemm_t.  `a`, `b` are bf16 buffers; offsets are in elements from their data_ptr."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    d = _lib.GemmDesc()
+    d.a0, d.a1 = _addr(a, a_off), _addr(a_lo, a_off)
+    d.a_rows, d.a_cols, d.lda = a_rows, a_cols, lda
+    d.b0, d.b1 = _addr(b, b_off), _addr(b_lo, b_off)
+    d.b_rows, d.b_cols, d.ldb = b_rows, b_cols, ldb
+    d.layout = layout
+    d.n_terms = 3 if a_lo is not None else 1
+    d.k_splits = k_splits
+    d.epi_atomic = int(epi_atomic)
+    d.out_dtype = BF16 if out.dtype == torch.bfloat16 else F32
+    assert out.dtype in (torch.bfloat16, torch.float32)
+    d.out, d.out_lo, d.ldo = _addr(out, out_off), _addr(out_lo, out_off), ldo
+    d.bias = _addr(bias)
+    d.relu = int(relu)
+    d.rows_per_utt, d.valid_rows = rows_per_utt, valid_rows
+    d.mask_src = _addr(mask_src, mask_off)
+    d.accumulate = int(accumulate)
+    _lib.check(_lib.lib().lbx_gemm_bf16(ctypes.byref(d), _lib.stream_ptr(a.device)))

@@ -1,0 +1,132 @@
+"""GPU tests (-m gpu) of the tcgen05 GEMM behind the TDNN: compared with an fp64 matmul of the SAME bf16-rounded
+operands (so the only difference is fp32 accumulation order): tolerance 1e-5 * sum|a||b| per element."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+    assert torch.cuda.is_available()
+    from lidbox_b200 import ops as o
+    return o
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale)
+
+
+def _check(out, ref, absref, tol=1e-5):
+    err = (out.double() - ref).abs()
+    bound = tol * absref + 1e-30
+    assert bool((err <= bound).all()), "max err/bound = %g" % float((err / bound).max())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (300, 512, 200), (1000, 1500, 512),
+                                   (64, 4, 512), (7, 512, 3000), (20000, 512, 1536)])
+def test_nt_plain(ops, M, N, K):
+    a = _rand((M, K), 1).bfloat16()
+    b = _rand((N, K), 2, 0.05).bfloat16()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(a, M, K, K, b, N, K, K, out, N)
+    ref = a.double() @ b.double().T
+    _check(out, ref, a.double().abs() @ b.double().abs().T)
+
+
+def test_nt_bias_relu_bf16_out_and_lo(ops):
+    M, N, K = 513, 1500, 512
+    a = _rand((M, K), 3).bfloat16()
+    b = _rand((N, K), 4, 0.05).bfloat16()
+    bias = _rand((N,), 5)
+    out = torch.zeros((M, 1504), device="cuda", dtype=torch.bfloat16)
+    lo = torch.zeros_like(out)
+    ops.gemm(a, M, K, K, b, N, K, K, out, 1504, bias=bias, relu=True, out_lo=lo)
+    ref = torch.relu(a.double() @ b.double().T + bias.double())
+    got = out[:, :N].double() + lo[:, :N].double()
+    absref = a.double().abs() @ b.double().abs().T + bias.double().abs()
+    _check(got, ref, absref, tol=2e-5)          # hi + lo carries ~16 mantissa bits
+    assert float((out[:, :N].double() - ref).abs().max()) < 0.02 * float(ref.abs().max())
+    assert bool((out[:, N:] == 0).all())
+
+
+def test_nt_bf16x3_matches_fp32_inputs(ops):
+    M, N, K = 400, 512, 1536
+    a = _rand((M, K), 6)
+    b = _rand((N, K), 7, 0.03)
+    ah, bh = a.bfloat16(), b.bfloat16()
+    al, bl = (a - ah.float()).bfloat16(), (b - bh.float()).bfloat16()
+    out = torch.empty((M, N), device="cuda")
+    ops.gemm(ah, M, K, K, bh, N, K, K, out, N, a_lo=al, b_lo=bl)
+    ref = a.double() @ b.double().T
+    absref = a.double().abs() @ b.double().abs().T
+    _check(out, ref, absref, tol=3e-5)
+    # normwise: what the fp32 forward config needs (<< 1e-4)
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 2e-5
+    # and the plain bf16 result is visibly worse, i.e. the extra terms are really accumulated
+    out1 = torch.empty((M, N), device="cuda")
+    ops.gemm(ah, M, K, K, bh, N, K, K, out1, N)
+    assert float((out1.double() - ref).abs().max()) > 20 * float((out.double() - ref).abs().max())
+
+
+def test_nt_overlapping_conv_view(ops):
+    # causal strided Conv1D as a GEMM over an overlapping A view: k=3, stride=2, C=64, per-utterance pitch = 2*R
+    B, C, k, s, R, T_out, N = 5, 64, 3, 2, 20, 18, 512
+    Tpad = s * R
+    x = torch.zeros((B * Tpad + 8, C), device="cuda", dtype=torch.bfloat16)
+    data = _rand((B, 2 * T_out - 1, C), 8).bfloat16()
+    xv = x[:B * Tpad].view(B, Tpad, C)
+    xv[:, k - 1:k - 1 + data.shape[1]] = data
+    w = _rand((N, k * C), 9, 0.05).bfloat16()
+    out = torch.zeros((B * R + 2, N), device="cuda")
+    ops.gemm(x, B * R, k * C, s * C, w, N, k * C, k * C, out, N, rows_per_utt=R, valid_rows=T_out, out_off=2 * N,
+             relu=True)
+    xp = xv.double()
+    cols = torch.stack([xp[:, t * s:t * s + k].reshape(B, k * C) for t in range(T_out)], dim=1)
+    ref = torch.relu(cols @ w.double().T)
+    got = out[2:].view(B, R, N)
+    _check(got[:, :T_out], ref, cols.abs() @ w.double().abs().T)
+    assert bool((got[:, T_out:] == 0).all()) and bool((out[:2] == 0).all())
+
+
+@pytest.mark.parametrize("Kc,M,N,splits", [(64, 128, 256, 1), (1000, 200, 512, 1), (5000, 1536, 512, 6),
+                                           (2600, 512, 1500, 3), (256, 3000, 512, 2)])
+def test_tn_wgrad_splitk_atomic(ops, Kc, M, N, splits):
+    ldb = (N + 7) // 8 * 8                      # operand pitches are multiples of 8 elements (1500 -> 1504)
+    a = _rand((Kc, M), 10).bfloat16()
+    bfull = _rand((Kc, ldb), 11, 0.05).bfloat16()
+    b = bfull[:, :N]
+    out = torch.zeros((M, N), device="cuda")
+    ops.gemm(a, Kc, M, M, bfull, Kc, N, ldb, out, N, layout=1, k_splits=splits, epi_atomic=True)
+    ref = a.double().T @ b.double()
+    _check(out, ref, a.double().abs().T @ b.double().abs())
+    # accumulates on top of what is there
+    ops.gemm(a, Kc, M, M, bfull, Kc, N, ldb, out, N, layout=1, k_splits=splits, epi_atomic=True)
+    _check(out, 2 * ref, 2 * (a.double().abs().T @ b.double().abs()))
+
+
+def test_tn_overlapping_view_wgrad(ops):
+    # weight gradient of the k=3, stride=2 conv: A^T view has pitch s*C < k*C
+    B, C, k, s, R, N = 4, 64, 3, 2, 24, 512
+    x = _rand((B * s * R + 8, C), 12).bfloat16()
+    dy = _rand((B * R, N), 13).bfloat16()
+    out = torch.zeros((k * C, N), device="cuda")
+    ops.gemm(x, B * R, k * C, s * C, dy, B * R, N, N, out, N, layout=1, k_splits=2, epi_atomic=True)
+    xf = x.double().reshape(-1)
+    cols = torch.stack([xf[m * s * C:m * s * C + k * C] for m in range(B * R)])
+    _check(out, cols.T @ dy.double(), cols.abs().T @ dy.double().abs())
+
+
+def test_dgrad_mask_and_accumulate(ops):
+    M, N, K = 300, 512, 512
+    dz = _rand((M, K), 14).bfloat16()
+    w = _rand((N, K), 15, 0.05).bfloat16()
+    y = _rand((M, N), 16).bfloat16()
+    out = _rand((M, N), 17).bfloat16()
+    prev = out.clone()
+    ops.gemm(dz, M, K, K, w, N, K, K, out, N, mask_src=y, accumulate=True)
+    ref = torch.where(y.double() > 0, dz.double() @ w.double().T, torch.zeros((), device="cuda", dtype=torch.double))
+    ref = ref + prev.double()
+    assert float((out.double() - ref).abs().max()) < 0.01 * float(ref.abs().max()) + 0.05

@@ -176,13 +176,227 @@ class LogmelWorkload:
                           "TensorFlow is not installable)" % (n, Bs, self.sec)}
 
 
-WORKLOADS = {"logmel": LogmelWorkload}
-try:
-    from lidbox_b200.bench_workloads import EXTRA_WORKLOADS   # x-vector workloads register themselves here
-    WORKLOADS.update(EXTRA_WORKLOADS)
-except ImportError:
-    pass
-DEFAULT_WORKLOAD = os.environ.get("LBX_BENCH_WORKLOAD", "xvector_train" if "xvector_train" in WORKLOADS else "logmel")
+def tdnn_forward_flops(T, n_out=4, F=40):
+    """Algorithmic forward FLOPs of one utterance: frames 1-5 + segments (+ output layer)."""
+    T2 = -(-T // 2)
+    T3 = -(-T2 // 3)
+    frame1 = 2 * T * 5 * F * 512
+    rest = 2 * (T2 * 1536 * 512 + T3 * 1536 * 512 + T3 * 512 * 512 + T3 * 512 * 1500)
+    dense = 2 * (3000 * 512 + 512 * 512 + 512 * n_out)
+    return frame1 + rest + dense, frame1
+
+
+def class_signals(B, N, n_classes, seed, pin=False):
+    """SURVEY §8(d) cfg3/cfg4 law: label y_b = b mod C, tone frequency drawn from C disjoint bands of [100, 4000] Hz."""
+    g = torch.Generator().manual_seed(seed)
+    y = torch.arange(B) % n_classes
+    width = 3900.0 / n_classes
+    f = 100.0 + (y.float() + torch.rand(B, generator=g)) * width
+    t = torch.arange(N, dtype=torch.float32) / SR
+    x = 0.5 * torch.sin(2 * np.pi * f[:, None] * t) + 0.05 * torch.randn(B, N, generator=g)
+    if pin:
+        x = x.pin_memory()
+    return x, y.to(torch.int32)
+
+
+class XVectorTrainWorkload:
+    """BASELINE config 3: x-vector training, 4 synthetic language labels, cross-entropy, bf16 (fp32 master weights,
+    statistics, loss), Adam; per-GPU batch 256 x 2 s; data-parallel with one NCCL all-reduce of the flat gradient.
+    A step = log-mel of the resident signals -> forward -> backward -> all-reduce -> Adam + bf16 weight refresh."""
+    name = "xvector_train"
+    metric = "x-vector training audio-sec/s (log-mel + TDNN fwd/bwd + Adam)"
+    unit = "audio-sec/s"
+    dtype = "bf16"
+    n_classes, n_out, loss, head = 4, 4, "xent", "log_softmax"
+    default_seconds = 2
+    label = "BASELINE config 3"
+
+    def __init__(self, args, rank, world):
+        self.B, self.sec = args.batch or 256, args.seconds or self.default_seconds
+        self.N = self.sec * SR
+        self.T = 1 + (self.N - 400) // 160
+        self.rank, self.world = rank, world
+        self.use_graph = os.environ.get("LBX_BENCH_GRAPH", "1") != "0"
+        self.dist = None
+
+    def config(self):
+        return {"workload": "%s: x-vector train, batch %d x %d s per GPU, %d labels, %s, bf16, Adam; signals resident "
+                            "in HBM; L2 flushed by the step itself (activations+gradients %.0f MB > 126 MB L2)"
+                            % (self.label, self.B, self.sec, self.n_classes, self.loss, self._act_mb()),
+                "batch_per_gpu": self.B, "global_batch": self.B * self.world, "seconds": self.sec,
+                "frames_per_utt": self.T, "cuda_graph": self.use_graph,
+                "parallelism": "dp%d (NCCL all-reduce of the 18 MB fp32 gradient)" % self.world}
+
+    def _act_mb(self):
+        return self.B * self.T * (512 * 2 * 2 + 256 * 2 * 2 + 2 * 1504 * 2 / 6 + 160) / 1e6
+
+    def setup(self, device):
+        from lidbox_b200.features import audio
+        from lidbox_b200.models import xvector
+        self.audio, self.device = audio, device
+        self.x_host, y = class_signals(self.B, self.N, self.n_classes, 1234 + self.rank, pin=True)
+        self.x = self.x_host.to(device)
+        self.y = y.to(device)
+        self.feats = torch.empty((self.B, self.T, 40), dtype=torch.float32, device=device)
+        self.model = xvector.create((self.T, 40), self.n_out, precision="bf16", head=self.head, seed=0)
+        self.model.configure_optimizer(lr=1e-3)
+        self.loss_host = torch.empty((self.B,), dtype=torch.float32).pin_memory()
+        self.pg = self.dist.group.WORLD if self.dist is not None else None
+        self.kw = dict(ap_classes=self.n_classes) if self.loss == "ap" else {}
+        self.graphed = None
+        if self.use_graph:
+            self.graphed = xvector.GraphedTrainStep(self.model, self.feats, self.y, loss=self.loss,
+                                                    process_group=self.pg, pre=self._features, **self.kw)
+
+    def _features(self):
+        return self.audio.logmelspectrograms(self.x, SR, out=self.feats)
+
+    def _eager_step(self):
+        return self.model.train_step(self._features(), self.y, loss=self.loss, process_group=self.pg, **self.kw)
+
+    def units_per_step(self):
+        return self.B * self.sec
+
+    def step(self):
+        return self.graphed() if self.graphed is not None else self._eager_step()
+
+    def launches_per_step(self):
+        return self.graphed.kernels_per_step if self.graphed is not None else None
+
+    def step_e2e(self):
+        self.x.copy_(self.x_host, non_blocking=True)
+        losses = self.step()
+        self.loss_host.copy_(losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def e2e_bytes(self):
+        return self.B * self.N * 4, self.B * 4
+
+    def roofline_measure(self, peaks):
+        """Times every GEMM launch of one eager step with CUDA events on the launching stream (3 repetitions, best)."""
+        from lidbox_b200 import ops
+        fwd, f1 = tdnn_forward_flops(self.T, self.n_out)
+        alg = self.B * (3 * fwd - f1)
+        best, n_launch, issued = None, 0, 0
+        for _ in range(3):
+            ops.GEMM_TIMER = []
+            self._eager_step()
+            torch.cuda.synchronize()
+            rec, ops.GEMM_TIMER = ops.GEMM_TIMER, None
+            ms = sum(e0.elapsed_time(e1) for (e0, e1, *_r) in rec)
+            if best is None or ms < best:
+                best, n_launch = ms, len(rec)
+                issued = sum(2.0 * M * N * K * nt for (_a, _b, M, N, K, nt, _l) in rec)
+        ach = alg / (best * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        return {"bound": "tensor", "kernel": "gemm_bf16_kernel (all %d launches of one training step)" % n_launch,
+                "achieved": ach, "peak": peak, "peak_source": peaks["source"] + " (sustained: timed inside a step)",
+                "unit": "TFLOP/s", "frac": ach / peak, "algorithmic_flops_per_step": alg,
+                "issued_flops_per_step": issued, "gemm_ms_per_step": best, "traffic": None}
+
+    def cpu_sample(self, budget_s=20.0):
+        from oracle import lidbox_oracle as O
+        torch.set_num_threads(os.cpu_count())
+        Bs = 32
+        x, y = class_signals(Bs, self.N, self.n_classes, 99)
+        params = {k: torch.tensor(v, requires_grad=True) for k, v in O.xvector_init(40, self.n_out, seed=0).items()}
+        opt = torch.optim.Adam(params.values(), lr=1e-3, eps=1e-7)
+
+        def one():
+            feats = O.torch_logmel(x)
+            opt.zero_grad()
+            if self.loss == "ap":
+                l = O.torch_ap_loss(y, O.torch_xvector_forward(params, feats, l2_normalize=True), self.n_classes)
+            else:
+                lp = O.torch_xvector_forward(params, feats)
+                l = -lp[torch.arange(Bs), y.long()].mean()
+            l.backward()
+            opt.step()
+        one()
+        n, t0 = 0, time.perf_counter()
+        while True:
+            one()
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > budget_s or n >= 200:
+                break
+        return {"value": n * Bs * self.sec / dt, "unit": self.unit, "cores": os.cpu_count(), "kind": "port",
+                "sample": "%d training steps of batch %d x %d s through the torch-CPU fp32 restatement "
+                          "(oracle.torch_logmel + torch_xvector_forward + autograd + Adam; TensorFlow is not "
+                          "installable)" % (n, Bs, self.sec)}
+
+    def extra(self):
+        """Secondary BASELINE lines measured in the same run (device-timed, signals resident)."""
+        out = {}
+        try:
+            out["also"] = {"logmel_2048x5s": bench_logmel_quick(self.device),
+                           "config2_embed_64x2s_fp32": bench_embed_quick(self.device)}
+        except Exception as e:      # secondary numbers must never take the headline down
+            out["also"] = {"error": repr(e)}
+        return out
+
+
+class XVectorAPTrainWorkload(XVectorTrainWorkload):
+    """BASELINE config 4: x-vector -> 64-d L2-normalised vector -> SparseAngularProximity(N=50, D=64), 3 s utterances."""
+    name = "xvector_ap_train"
+    metric = "x-vector + angular-proximity training audio-sec/s"
+    n_classes, n_out, loss, head = 50, 64, "ap", "l2_normalize"
+    default_seconds = 3
+    label = "BASELINE config 4"
+
+
+def _time_cuda(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_logmel_quick(device, B=2048, sec=5):
+    from lidbox_b200.features import audio
+    N = sec * SR
+    T = 1 + (N - 400) // 160
+    x = torch.randn((B, N), device=device) * 0.1
+    out = torch.empty((B, T, 40), dtype=torch.float32, device=device)
+    ms = _time_cuda(lambda: audio.logmelspectrograms(x, SR, out=out), 10)
+    peaks = load_peaks()
+    gbs = B * (4 * N + 4 * T * 40) / (ms * 1e-3) / 1e9
+    return {"frames_per_s": B * T / (ms * 1e-3), "ms": ms, "hbm_GBps_algorithmic": gbs,
+            "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"]}
+
+
+def bench_embed_quick(device, B=64, sec=2):
+    from lidbox_b200.features import audio
+    from lidbox_b200.models import xvector
+    N = sec * SR
+    T = 1 + (N - 400) // 160
+    x = synth_signals(B, N, 1234, device=device)
+    feats = torch.empty((B, T, 40), dtype=torch.float32, device=device)
+    emb = xvector.as_embedding_extractor(xvector.create((T, 40), 4, precision="fp32", seed=0))
+
+    def run():
+        audio.logmelspectrograms(x, SR, out=feats)
+        return emb(feats)
+    ms = _time_cuda(run, 20)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run()
+    ms_graph = _time_cuda(g.replay, 50)
+    fwd, _ = tdnn_forward_flops(T)
+    return {"audio_sec_per_s": B * sec / (ms_graph * 1e-3), "ms_eager": ms, "ms_cuda_graph": ms_graph,
+            "precision": "fp32 via bf16x3 tensor-core accumulation (3x the bf16 FLOPs)",
+            "algorithmic_tflops": B * fwd / (ms_graph * 1e-3) / 1e12}
+
+
+WORKLOADS = {"logmel": LogmelWorkload, "xvector_train": XVectorTrainWorkload,
+             "xvector_ap_train": XVectorAPTrainWorkload}
+DEFAULT_WORKLOAD = os.environ.get("LBX_BENCH_WORKLOAD", "xvector_train")
 
 
 def run_reference(args, rank, world):
@@ -267,6 +481,8 @@ def main():
     ev1.record()
     barrier()
     launches = lib.lbx_launch_count() - n0
+    if launches == 0 and getattr(wl, "launches_per_step", None) and wl.launches_per_step():
+        launches = wl.launches_per_step() * args.steps      # CUDA-graph replays: kernels counted at capture time
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:

@@ -134,6 +134,55 @@ typedef struct lbx_gemm_t {
 } lbx_gemm_t;
 int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * TDNN non-GEMM stages and losses
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* features [B,T,F] f32 -> bf16 activation rows of the first frame layer: element (b,t,c) goes to row
+ * b*rows_per_utt + row_off + t, column c of a [*, pitch] buffer (hi, and lo = residual when lo != NULL);
+ * columns F..pitch-1 are written as zero.  drop_rate > 0 applies SpatialDropout1D (xvector.py:50-51): whole
+ * channels of a sample are zeroed with probability drop_rate, the rest scaled by 1/(1-drop_rate). */
+int lbx_pack_rows_bf16(const float* x, long long B, int T, int F, void* hi, void* lo, int rows_per_utt, int row_off,
+                       int pitch, float drop_rate, unsigned long long seed, void* stream);
+
+/* lidbox/models/xvector.py:25-35 GlobalMeanStddevPooling1D: y [B*rows_per_utt, pitch] (first T rows of every
+ * utterance, C channels; f32 or bf16) -> out [B, 2C] f32 (mean | std), two-pass population variance in fp32,
+ * std = sqrt(clip(var, clip_min, FLT_MAX)).  Optional: var_raw [B,C] (needed by the backward), bf16 copies. */
+int lbx_stats_pool_fwd(const void* y, int y_dtype, long long B, int rows_per_utt, int T, int C, int pitch,
+                       float clip_min, float* out, float* var_raw, void* out_hi, void* out_lo, void* stream);
+/* backward of the pooling fused with the ReLU mask of the producing layer: dz = (y > 0) * d pool / d y . gpool */
+int lbx_stats_pool_bwd(const void* y_bf16, long long B, int rows_per_utt, int T, int C, int pitch, float clip_min,
+                       const float* pooled, const float* var_raw, const float* gpool, void* dz_bf16, void* stream);
+
+/* log_softmax (xvector.py:64-65) + sparse categorical cross-entropy on the log-probs, forward + gradient:
+ * logp [B,n] (optional), loss [B] = -logp[b, y_b] (optional), dlogits bf16 [B, dl_pitch] =
+ * (softmax - onehot) * grad_scale (optional). */
+int lbx_logsoftmax_xent(const float* logits, const int* labels, long long B, int n, float* logp, float* loss,
+                        void* dlogits_bf16, int dl_pitch, float grad_scale, void* stream);
+
+/* lidbox/losses.py:12-52 SparseAngularProximity(N, D, delta_weight): theta = acos(z[:, :N]),
+ * loss[b] = sum_{l != y_b} sigmoid(delta_weight * (theta[b,y_b] - theta[b,l])).  normalize = 1 first maps
+ * z = h / |h| (the L2-normalising head of the AP training config).  Optional outputs: z_out [B,D], theta_out [B,N],
+ * loss [B], and the gradient w.r.t. h as f32 and/or bf16 [B, g_pitch], multiplied by gloss[b] (or 1) * grad_scale.
+ * Constructor asserts of losses.py:14-16 are returned as LBX_EINVAL. */
+int lbx_ap_loss(const float* h, const int* labels, long long B, int D, int N, float delta_weight, int normalize,
+                float* z_out, float* theta_out, float* loss, float* grad_f32, void* grad_bf16, int g_pitch,
+                const float* gloss, float grad_scale, void* stream);
+
+/* bias gradient: out[n] += sum_m x[m, n], x bf16 [rows, pitch] */
+int lbx_colsum_bf16(const void* x, long long rows, int n, int pitch, float* out, void* stream);
+
+/* Keras-compatible Adam on flat fp32 buffers: g' = g * grad_scale; m,v updates;
+ * p -= lr * sqrt(1-beta2^t)/(1-beta1^t) * m / (sqrt(v) + eps).  The step counter t (*step_dev, incremented by the
+ * call) and the bias-corrected rate (*lr_t_dev) live in device memory so the call can be replayed from a CUDA graph. */
+int lbx_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* stream);
+
+/* fp32 master weight [K, N] (Keras kernel flattened) -> bf16 operand copies: W [K, ldw] (data-gradient operand) and
+ * W^T [N, ldt] (forward operand), each as hi (+ lo residual) planes; any of w_hi / t_hi may be NULL. */
+int lbx_refresh_weights(const float* w, int K, int N, void* w_hi, void* w_lo, int ldw, void* t_hi, void* t_lo, int ldt,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

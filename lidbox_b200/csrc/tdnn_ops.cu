@@ -1,0 +1,441 @@
+// Non-GEMM pieces of the x-vector TDNN (lidbox/models/xvector.py) and its losses (lidbox/losses.py), sm_100a.
+// All of them are HBM- or latency-bound: plain coalesced CUDA kernels, fp32 statistics.
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace lbx {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// counter-based hash RNG (one draw per (sample, channel)) for SpatialDropout1D
+__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned int a, unsigned int b) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * ((unsigned long long)a * 0x100000001B3ULL + b + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// features [B,T,F] f32 -> zero-left-padded bf16 activation rows (hi [+ lo]); optional SpatialDropout1D
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ x, long long B, int T, int F,
+                                                       bf16* __restrict__ hi, bf16* __restrict__ lo, int rows_per_utt,
+                                                       int row_off, int pitch, float drop_rate,
+                                                       unsigned long long seed) {
+  const long long total = B * T * (long long)pitch;
+  const float keep_scale = drop_rate > 0.0f ? 1.0f / (1.0f - drop_rate) : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % pitch);
+    const long long bt = i / pitch;
+    const int t = (int)(bt % T);
+    const long long b = bt / T;
+    float v = 0.0f;
+    if (c < F) {
+      v = __ldg(x + bt * F + c);
+      if (drop_rate > 0.0f) v = hash_uniform(seed, (unsigned)b, (unsigned)c) < drop_rate ? 0.0f : v * keep_scale;
+    }
+    const long long o = (b * rows_per_utt + row_off + t) * pitch + c;
+    const bf16 h = __float2bfloat16_rn(v);
+    hi[o] = h;
+    if (lo != nullptr) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GlobalMeanStddevPooling1D (xvector.py:25-35): two-pass population variance in fp32, clip 1e-10, sqrt
+// ------------------------------------------------------------------------------------------------------------
+template <typename TIn>
+__device__ __forceinline__ float load_act(const TIn* p);
+template <>
+__device__ __forceinline__ float load_act<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_act<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const TIn* __restrict__ y, int rows_per_utt, int T, int C,
+                                                            int pitch, float clip_min, float* __restrict__ out,
+                                                            float* __restrict__ var_raw, bf16* __restrict__ out_hi,
+                                                            bf16* __restrict__ out_lo) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const long long b = blockIdx.y;
+  const TIn* base = y + b * rows_per_utt * (long long)pitch + c;
+  float s = 0.0f;
+  if (c < C)
+    for (int t = tl; t < T; t += 8) s += load_act<TIn>(base + (long long)t * pitch);
+  red[tl][cl] = s;
+  __syncthreads();
+  float mean = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mean += red[i][cl];
+  mean /= (float)T;
+  __syncthreads();
+  float q = 0.0f;
+  if (c < C)
+    for (int t = tl; t < T; t += 8) {
+      const float d = load_act<TIn>(base + (long long)t * pitch) - mean;
+      q = fmaf(d, d, q);
+    }
+  red[tl][cl] = q;
+  __syncthreads();
+  if (tl == 0 && c < C) {
+    float var = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) var += red[i][cl];
+    var /= (float)T;
+    const float sd = sqrtf(fminf(fmaxf(var, clip_min), 3.402823466e+38f));
+    out[b * 2 * C + c] = mean;
+    out[b * 2 * C + C + c] = sd;
+    if (var_raw) var_raw[b * C + c] = var;
+    if (out_hi) {
+      const bf16 mh = __float2bfloat16_rn(mean), sh = __float2bfloat16_rn(sd);
+      out_hi[b * 2 * C + c] = mh;
+      out_hi[b * 2 * C + C + c] = sh;
+      if (out_lo) {
+        out_lo[b * 2 * C + c] = __float2bfloat16_rn(mean - __bfloat162float(mh));
+        out_lo[b * 2 * C + C + c] = __float2bfloat16_rn(sd - __bfloat162float(sh));
+      }
+    }
+  }
+}
+
+// backward of pooling fused with the ReLU mask of the producing frame layer:
+//   dZ[b,t,c] = (y > 0) * ( g_mean/T + [var > clip] * g_std * (y - mean) / (T * std) )
+__global__ void __launch_bounds__(256) stats_pool_bwd_kernel(const bf16* __restrict__ y, int rows_per_utt, int T, int C,
+                                                            int pitch, float clip_min, const float* __restrict__ pooled,
+                                                            const float* __restrict__ var_raw,
+                                                            const float* __restrict__ gpool, bf16* __restrict__ dz) {
+  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const long long b = blockIdx.y;
+  if (c >= C) return;
+  const float mean = pooled[b * 2 * C + c], sd = pooled[b * 2 * C + C + c];
+  const float gm = gpool[b * 2 * C + c] / (float)T;
+  const float gs = var_raw[b * C + c] > clip_min ? gpool[b * 2 * C + C + c] / ((float)T * sd) : 0.0f;
+  const long long base = b * rows_per_utt * (long long)pitch + c;
+  for (int t = tl; t < T; t += 8) {
+    const float v = __bfloat162float(y[base + (long long)t * pitch]);
+    const float g = v > 0.0f ? fmaf(gs, v - mean, gm) : 0.0f;
+    dz[base + (long long)t * pitch] = __float2bfloat16_rn(g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// log_softmax (xvector.py:65) + sparse cross-entropy on the log-probs, forward and backward in one pass
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) logsoftmax_xent_kernel(const float* __restrict__ logits, const int* __restrict__ y,
+                                                             long long B, int n, float* __restrict__ logp,
+                                                             float* __restrict__ loss, bf16* __restrict__ dlogits,
+                                                             int dl_pitch, float grad_scale) {
+  const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* row = logits + b * n;
+  float mx = -INFINITY;
+  for (int j = lane; j < n; j += 32) mx = fmaxf(mx, row[j]);
+  mx = warp_max(mx);
+  float s = 0.0f;
+  for (int j = lane; j < n; j += 32) s += expf(row[j] - mx);
+  s = warp_sum(s);
+  const float lse = mx + logf(s);
+  const int label = y ? y[b] : -1;
+  for (int j = lane; j < n; j += 32) {
+    const float lp = row[j] - lse;
+    if (logp) logp[b * n + j] = lp;
+    if (dlogits) dlogits[b * dl_pitch + j] = __float2bfloat16_rn((expf(lp) - (j == label ? 1.0f : 0.0f)) * grad_scale);
+    if (loss && j == label) loss[b] = -lp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SparseAngularProximity (losses.py:12-52): theta = acos(z[:, :N]); L_b = sum_{l != y} sigmoid(w (theta_y - theta_l))
+// optional L2-normalising head in front (z = h / |h|), as used by the AP training config
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ap_loss_kernel(const float* __restrict__ h, const int* __restrict__ y, long long B,
+                                                     int D, int N, float w, int normalize, float* __restrict__ z_out,
+                                                     float* __restrict__ theta_out, float* __restrict__ loss,
+                                                     float* __restrict__ grad_f32, bf16* __restrict__ grad_bf16,
+                                                     int g_pitch, const float* __restrict__ gloss, float grad_scale) {
+  const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* row = h + b * D;
+  float inv_norm = 1.0f;
+  if (normalize) {
+    float ss = 0.0f;
+    for (int j = lane; j < D; j += 32) ss = fmaf(row[j], row[j], ss);
+    ss = warp_sum(ss);
+    inv_norm = rsqrtf(fmaxf(ss, 1e-12f));
+  }
+  const int label = y[b];
+  const float zy = row[label] * inv_norm;
+  const float theta_y = acosf(zy);
+  float l = 0.0f, dty = 0.0f, dot = 0.0f;     // dot = z . dz (for the normalisation backward)
+  for (int j0 = 0; j0 < D; j0 += 32) {
+    const int j = j0 + lane;
+    float dz = 0.0f, z = 0.0f;
+    if (j < D) {
+      z = row[j] * inv_norm;
+      if (z_out) z_out[b * D + j] = z;
+      if (j < N) {
+        const float th = acosf(z);
+        if (theta_out) theta_out[b * N + j] = th;
+        if (j != label) {
+          const float sg = 1.0f / (1.0f + expf(-w * (theta_y - th)));
+          l += sg;
+          const float dsg = w * sg * (1.0f - sg);          // d sigma / d delta * w
+          dty += dsg;                                       // dL/dtheta_y
+          dz = dsg * rsqrtf(fmaxf(1.0f - z * z, 0.0f));     // dL/dtheta_l = -dsg ; dtheta/dz = -1/sqrt(1-z^2)
+        }
+      }
+    }
+    dot += dz * z;
+  }
+  l = warp_sum(l);
+  dty = warp_sum(dty);
+  if (loss && lane == 0) loss[b] = l;
+  if (grad_f32 == nullptr && grad_bf16 == nullptr) return;
+  const float dzy = -dty * rsqrtf(fmaxf(1.0f - zy * zy, 0.0f));
+  dot = warp_sum(dot) + dzy * zy;
+  const float gl = (gloss ? gloss[b] : 1.0f) * grad_scale;
+  for (int j = lane; j < D; j += 32) {
+    const float z = row[j] * inv_norm;
+    float dz = 0.0f;
+    if (j < N) {
+      if (j == label) {
+        dz = dzy;
+      } else {
+        const float th = acosf(z);
+        const float sg = 1.0f / (1.0f + expf(-w * (theta_y - th)));
+        dz = w * sg * (1.0f - sg) * rsqrtf(fmaxf(1.0f - z * z, 0.0f));
+      }
+    }
+    const float g = (normalize ? (dz - z * dot) * inv_norm : dz) * gl;
+    if (grad_f32) grad_f32[b * g_pitch + j] = g;
+    if (grad_bf16) grad_bf16[b * g_pitch + j] = __float2bfloat16_rn(g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// bias gradients: out[n] += sum_m x[m, n]
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long rows, int n, int pitch,
+                                                    float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.0f;
+  if (c < n)
+    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8)
+      s += __bfloat162float(x[r * pitch + c]);
+  red[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && c < n) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += red[i][cl];
+    atomicAdd(out + c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// optimizer + weight refresh
+// ------------------------------------------------------------------------------------------------------------
+// step counter and bias-corrected learning rate live in device memory so that a captured CUDA graph of the whole
+// training step advances them on every replay
+__global__ void adam_tick_kernel(long long* step, float* lr_t, float lr, float beta1, float beta2) {
+  const long long t = *step + 1;
+  *step = t;
+  *lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t)));
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                  float* __restrict__ m, float* __restrict__ v, long long n,
+                                                  const float* __restrict__ lr_t_ptr, float beta1, float beta2,
+                                                  float eps, float grad_scale) {
+  const float lr_t = *lr_t_ptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// fp32 master W [K, N] (Keras layout) -> bf16 W [K, ldw] and bf16 W^T [N, ldt], hi (+ lo residual) planes
+__global__ void __launch_bounds__(256) refresh_weights_kernel(const float* __restrict__ w, int K, int N,
+                                                             bf16* __restrict__ w_hi, bf16* __restrict__ w_lo, int ldw,
+                                                             bf16* __restrict__ t_hi, bf16* __restrict__ t_lo, int ldt) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + tx;
+    float v = 0.0f;
+    if (k < K && n < N) {
+      v = w[(long long)k * N + n];
+      if (w_hi) {
+        const bf16 h = __float2bfloat16_rn(v);
+        w_hi[(long long)k * ldw + n] = h;
+        if (w_lo) w_lo[(long long)k * ldw + n] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  if (t_hi) {
+    for (int i = ty; i < 32; i += 8) {
+      const int n = n0 + i, k = k0 + tx;
+      if (n < N && k < K) {
+        const float v = tile[tx][i];
+        const bf16 h = __float2bfloat16_rn(v);
+        t_hi[(long long)n * ldt + k] = h;
+        if (t_lo) t_lo[(long long)n * ldt + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+  }
+}
+
+static inline int grid_for(long long n, int block, int cap = 148 * 16) {
+  long long g = ceil_div(n, block);
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace lbx
+
+using namespace lbx;
+
+extern "C" {
+
+int lbx_pack_rows_bf16(const float* x, long long B, int T, int F, void* hi, void* lo, int rows_per_utt, int row_off,
+                       int pitch, float drop_rate, unsigned long long seed, void* stream) {
+  LBX_CHECK_ARG(B >= 0 && T >= 0 && F >= 1 && pitch >= F, "bad shape B=%lld T=%d F=%d pitch=%d", B, T, F, pitch);
+  LBX_CHECK_ARG(row_off >= 0 && row_off + T <= rows_per_utt, "rows do not fit: off=%d T=%d rows_per_utt=%d", row_off, T,
+                rows_per_utt);
+  LBX_CHECK_ARG(drop_rate >= 0.0f && drop_rate < 1.0f, "drop_rate must be in [0, 1)");
+  if (B * T == 0) return LBX_OK;
+  LBX_CHECK_ARG(x && hi, "NULL pointer argument");
+  pack_rows_kernel<<<grid_for(B * T * (long long)pitch, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, B, T, F, (bf16*)hi, (bf16*)lo, rows_per_utt, row_off, pitch, drop_rate, seed);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_stats_pool_fwd(const void* y, int y_dtype, long long B, int rows_per_utt, int T, int C, int pitch,
+                       float clip_min, float* out, float* var_raw, void* out_hi, void* out_lo, void* stream) {
+  LBX_CHECK_ARG(B >= 0 && T >= 1 && C >= 1 && pitch >= C && rows_per_utt >= T, "bad pooling shape");
+  LBX_CHECK_ARG(B <= 65535, "batch too large for one pooling launch");
+  if (B == 0) return LBX_OK;
+  LBX_CHECK_ARG(y && out, "NULL pointer argument");
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)B);
+  if (y_dtype == LBX_F32)
+    stats_pool_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)y, rows_per_utt, T, C, pitch,
+                                                                         clip_min, out, var_raw, (bf16*)out_hi,
+                                                                         (bf16*)out_lo);
+  else if (y_dtype == LBX_BF16)
+    stats_pool_fwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, rows_per_utt, T, C, pitch,
+                                                                        clip_min, out, var_raw, (bf16*)out_hi,
+                                                                        (bf16*)out_lo);
+  else
+    return set_error(LBX_EINVAL, "bad y_dtype %d", y_dtype);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_stats_pool_bwd(const void* y_bf16, long long B, int rows_per_utt, int T, int C, int pitch, float clip_min,
+                       const float* pooled, const float* var_raw, const float* gpool, void* dz_bf16, void* stream) {
+  LBX_CHECK_ARG(B >= 0 && T >= 1 && C >= 1 && pitch >= C && rows_per_utt >= T && B <= 65535, "bad pooling shape");
+  if (B == 0) return LBX_OK;
+  LBX_CHECK_ARG(y_bf16 && pooled && var_raw && gpool && dz_bf16, "NULL pointer argument");
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)B);
+  stats_pool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y_bf16, rows_per_utt, T, C, pitch, clip_min,
+                                                                pooled, var_raw, gpool, (bf16*)dz_bf16);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_logsoftmax_xent(const float* logits, const int* labels, long long B, int n, float* logp, float* loss,
+                        void* dlogits_bf16, int dl_pitch, float grad_scale, void* stream) {
+  LBX_CHECK_ARG(B >= 0 && n >= 1, "bad shape");
+  if (B == 0) return LBX_OK;
+  LBX_CHECK_ARG(logits, "NULL logits");
+  LBX_CHECK_ARG(!(loss || dlogits_bf16) || labels, "labels are required for the loss / gradient");
+  LBX_CHECK_ARG(!dlogits_bf16 || dl_pitch >= n, "dl_pitch too small");
+  logsoftmax_xent_kernel<<<(unsigned)ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(
+      logits, labels, B, n, logp, loss, (bf16*)dlogits_bf16, dl_pitch, grad_scale);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_ap_loss(const float* h, const int* labels, long long B, int D, int N, float delta_weight, int normalize,
+                float* z_out, float* theta_out, float* loss, float* grad_f32, void* grad_bf16, int g_pitch,
+                const float* gloss, float grad_scale, void* stream) {
+  LBX_CHECK_ARG(N >= 1, "Must have at least 1 class");                                       /* losses.py:14 */
+  LBX_CHECK_ARG(D >= N, "Language vector dimension cannot be less than number of classes");  /* losses.py:15 */
+  LBX_CHECK_ARG(delta_weight > 0.0f, "delta_weight must be positive");                       /* losses.py:16 */
+  LBX_CHECK_ARG(B >= 0, "bad batch");
+  if (B == 0) return LBX_OK;
+  LBX_CHECK_ARG(h && labels, "NULL pointer argument");
+  LBX_CHECK_ARG(!(grad_f32 || grad_bf16) || g_pitch >= D, "g_pitch too small");
+  ap_loss_kernel<<<(unsigned)ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(h, labels, B, D, N, delta_weight, normalize,
+                                                                             z_out, theta_out, loss, grad_f32,
+                                                                             (bf16*)grad_bf16, g_pitch, gloss,
+                                                                             grad_scale);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_colsum_bf16(const void* x, long long rows, int n, int pitch, float* out, void* stream) {
+  LBX_CHECK_ARG(rows >= 0 && n >= 1 && pitch >= n, "bad shape");
+  if (rows == 0) return LBX_OK;
+  LBX_CHECK_ARG(x && out, "NULL pointer argument");
+  long long gy = ceil_div(rows, 256);
+  if (gy > 128) gy = 128;
+  dim3 grid((unsigned)ceil_div(n, 32), (unsigned)gy);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, rows, n, pitch, out);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* stream) {
+  LBX_CHECK_ARG(n >= 0, "bad arguments");
+  if (n == 0) return LBX_OK;
+  LBX_CHECK_ARG(params && grads && m && v && step_dev && lr_t_dev, "NULL pointer argument");
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, lr_t_dev, lr, beta1, beta2);
+  LBX_LAUNCH_CHECK();
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr_t_dev, beta1, beta2, eps,
+                                                                  grad_scale);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_refresh_weights(const float* w, int K, int N, void* w_hi, void* w_lo, int ldw, void* t_hi, void* t_lo, int ldt,
+                        void* stream) {
+  LBX_CHECK_ARG(K >= 1 && N >= 1, "bad shape");
+  LBX_CHECK_ARG(w, "NULL weights");
+  LBX_CHECK_ARG(!w_hi || ldw >= N, "ldw too small");
+  LBX_CHECK_ARG(!t_hi || ldt >= K, "ldt too small");
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(K, 32));
+  refresh_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, K, N, (bf16*)w_hi, (bf16*)w_lo, ldw, (bf16*)t_hi,
+                                                                 (bf16*)t_lo, ldt);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+"""Drop-in for the map stage lidbox/data/tf_utils.py:166-195 (`extract_features`), the call site
+`steps.extract_features` (lidbox/data/steps.py:708-736) invokes once per batch.
+
+Same positional signature and error convention (rank / sample-rate / finiteness checks raise).  The reference calls
+`audio_features.melspectrograms`, a name that does not exist at this commit; the intended chain
+spectrograms -> linear_to_mel -> log(x + 1e-6) is implemented, fused into one kernel for the (log-)mel feature types.
+Re-entrant: every call works on the calling thread's current CUDA stream and shares only read-only cached tables.
+"""
+import numpy as np
+import torch
+
+from ..features import audio as audio_features
+
+
+def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_kwargs=None, mfcc_kwargs=None,
+                     db_spec_kwargs=None, feat_scale_kwargs=None, window_norm_kwargs=None, check_finite=True):
+    spec_kwargs, melspec_kwargs = dict(spec_kwargs or {}), dict(melspec_kwargs or {})
+    sig = signals if isinstance(signals, torch.Tensor) else torch.as_tensor(np.asarray(signals))
+    if sig.dim() != 2:
+        raise ValueError("Input signals for feature extraction must be batches of mono signals without channels, "
+                         "i.e. of shape [B, N] where B is batch size and N number of samples.")
+    rates = np.asarray(sample_rates.cpu() if isinstance(sample_rates, torch.Tensor) else sample_rates).reshape(-1)
+    if rates.size == 0 or not (rates == rates[0]).all():
+        raise ValueError("Different sample rates in a single batch not supported, all signals in the same batch "
+                         "should have the same sample rate.")
+    sample_rate = int(rates[0])
+    if feattype in ("melspectrogram", "logmelspectrogram"):
+        X = audio_features.logmelspectrograms(sig, sample_rate, log=(feattype == "logmelspectrogram"), **spec_kwargs,
+                                              **melspec_kwargs)
+    elif feattype == "spectrogram":
+        X = audio_features.spectrograms(sig, sample_rate, **spec_kwargs)
+    elif feattype == "db_spectrogram":
+        X = audio_features.spectrograms(sig, sample_rate, **spec_kwargs)
+        if check_finite:
+            audio_features.assert_all_finite(X, "spectrogram failed")
+        X = audio_features.power_to_db(X, **(db_spec_kwargs or {}))
+    elif feattype == "mfcc":
+        raise NotImplementedError("mfcc (DCT-II epilogue) is a 'next' row of SURVEY.md §8(f), not built yet")
+    else:
+        raise ValueError("unknown feature type " + repr(feattype))
+    if check_finite:
+        audio_features.assert_all_finite(X, feattype + " failed")
+    if feat_scale_kwargs or window_norm_kwargs:
+        raise NotImplementedError("feature_scaling / window_normalization are 'next' rows of SURVEY.md §8(f)")
+    return X

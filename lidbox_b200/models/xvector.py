@@ -1,0 +1,505 @@
+"""Drop-in for lidbox/models/xvector.py on hand-written sm_100a kernels.
+
+    m = create(input_shape=(T or None, F), num_outputs)     # xvector.py:46-67
+    logp = m(x, training=False)                              # [B, T, F] -> [B, num_outputs] log-probabilities
+    emb = as_embedding_extractor(m)(x)                       # xvector.py:70-73: pre-ReLU segment1 output [B, 512]
+
+Layer names, Keras weight layouts (Conv1D kernel [k, C_in, C_out], Dense kernel [in, out]) and the causal/strided
+semantics follow the reference; the arithmetic runs through the C-ABI (include/lidbox_b200.h):
+
+  * every frame layer is ONE tcgen05 GEMM over an overlapping TMA view of the zero-left-padded NWC activations
+    (row pitch stride*C_in, width k*C_in: no im2col) with bias + ReLU fused in the epilogue, which writes straight
+    into the next layer's padded buffer;
+  * activation buffers of consecutive layers share one row geometry (rows per utterance R_L = padded length of
+    layer L+1), so every operand of forward, data-gradient and weight-gradient GEMMs is a flat 2-D matrix;
+  * precision "fp32" (default, inference parity): bf16x3 split accumulation, fp32 statistics;
+    precision "bf16" (training configs): bf16 operands, fp32 accumulation / statistics / loss / master weights.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+
+TIME_AXIS = 1                      # xvector.py:21
+STDDEV_SQRT_MIN_CLIP = 1e-10       # xvector.py:22
+_SLACK_ROWS = 8
+
+
+def _ceil8(n):
+    return (n + 7) // 8 * 8
+
+
+class _LayerSpec:
+    def __init__(self, kind, name, units, kernel_size=1, strides=1, activation="relu"):
+        self.kind, self.name, self.units = kind, name, units
+        self.kernel_size, self.strides, self.activation = kernel_size, strides, activation
+
+
+def frame_layer(filters, kernel_size, strides, padding="causal", activation="relu", name="frame"):
+    """xvector.py:38-39 — Conv1D(filters, kernel_size, strides, padding="causal", activation="relu")."""
+    if padding != "causal":
+        raise NotImplementedError("only padding='causal' is implemented (the only mode the reference uses)")
+    return _LayerSpec("frame", name, filters, kernel_size, strides, activation)
+
+
+def segment_layer(units, activation="relu", name="segment"):
+    """xvector.py:42-43 — Dense(units, activation="relu")."""
+    return _LayerSpec("segment", name, units, activation=activation)
+
+
+class GlobalMeanStddevPooling1D:
+    """xvector.py:25-35: mean and standard deviation over the time axis, concatenated -> [B, 2C]."""
+
+    def __init__(self, name="stats_pooling"):
+        self.name = name
+
+    def __call__(self, inputs):
+        x = inputs if isinstance(inputs, torch.Tensor) else torch.as_tensor(np.asarray(inputs))
+        if x.dim() != 3:
+            raise ValueError("expected [B, T, C], got %s" % (tuple(x.shape),))
+        x = x.to(_lib.require_cuda(), torch.float32).contiguous()
+        B, T, C = x.shape
+        out = torch.empty((B, 2 * C), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().lbx_stats_pool_fwd(_lib.ptr(x), ops.F32, B, T, T, C, C, STDDEV_SQRT_MIN_CLIP,
+                                                 _lib.ptr(out), None, None, None, _lib.stream_ptr(x.device)))
+        return out
+
+
+class _Geometry:
+    """Row geometry shared by all activation buffers for one (T) — see DESIGN.md §Data layout."""
+
+    def __init__(self, T, frames):
+        self.T = [T]
+        for f in frames:
+            self.T.append(-(-self.T[-1] // f.strides))
+        n = len(frames)
+        prod = [1] * (n + 1)                        # prod[L] = s_{L+1} * ... * s_n   (0-based layer index L)
+        for L in range(n - 1, -1, -1):
+            prod[L] = prod[L + 1] * frames[L].strides
+        P = self.T[n]
+        for L in range(n):
+            need = self.T[L] + frames[L].kernel_size - 1
+            P = max(P, -(-need // prod[L]))
+        self.P = P
+        self.Tpad = [P * prod[L] for L in range(n)]            # padded input length of layer L
+        self.R = [self.Tpad[L] // frames[L].strides for L in range(n)]   # GEMM rows per utterance of layer L
+        self.pad = [f.kernel_size - 1 for f in frames]         # data row offset inside layer L's input buffer
+        for L in range(n - 1):
+            assert self.R[L] == self.Tpad[L + 1]
+
+
+class XVector:
+    def __init__(self, input_shape, num_outputs, channel_dropout_rate=0, name="x-vector", frames=None, segments=None,
+                 precision="fp32", head="log_softmax", seed=None, device=None):
+        if len(input_shape) != 2:
+            raise ValueError("input_shape must be (T or None, F)")
+        self.name = name
+        self.input_shape = tuple(input_shape)
+        self.F = int(input_shape[1])
+        self.Fp = _ceil8(self.F)
+        self.num_outputs = int(num_outputs)
+        if self.F < 1 or self.num_outputs < 1:
+            raise ValueError("F and num_outputs must be >= 1")
+        self.channel_dropout_rate = float(channel_dropout_rate)
+        self.frames = frames or [frame_layer(512, 5, 1, name="frame1"), frame_layer(512, 3, 2, name="frame2"),
+                                 frame_layer(512, 3, 3, name="frame3"), frame_layer(512, 1, 1, name="frame4"),
+                                 frame_layer(1500, 1, 1, name="frame5")]
+        self.segments = segments or [segment_layer(512, name="segment1"), segment_layer(512, name="segment2")]
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if head not in ("log_softmax", "l2_normalize", "none"):
+            raise ValueError("unknown head " + head)
+        self.precision, self.head = precision, head
+        self.device = _lib.require_cuda(device)
+        self._dropout_seed = 0x5EED if seed is None else int(seed)
+        self._dropout_calls = 0
+        self._build_params(seed)
+        self._bufs = {}
+        self._adam = None
+
+    # ------------------------------------------------------------------ parameters
+    def _build_params(self, seed):
+        # (name, K, N, K_real) in execution order; weights are Keras kernels flattened to [K, N]
+        self.layers = []
+        c_in, c_in_real = self.Fp, self.F
+        for f in self.frames:
+            self.layers.append(dict(name=f.name, kind="frame", K=f.kernel_size * c_in, N=f.units, k=f.kernel_size,
+                                    s=f.strides, c_in=c_in, c_in_real=c_in_real, relu=f.activation == "relu"))
+            c_in = c_in_real = f.units
+        d_in = 2 * c_in
+        for sgm in self.segments:
+            self.layers.append(dict(name=sgm.name, kind="dense", K=d_in, N=sgm.units, relu=sgm.activation == "relu"))
+            d_in = sgm.units
+        self.layers.append(dict(name="outputs", kind="dense", K=d_in, N=self.num_outputs, relu=False))
+        off = 0
+        for ly in self.layers:
+            ly["w_off"], ly["b_off"] = off, off + ly["K"] * ly["N"]
+            off = ly["b_off"] + ly["N"]
+            ly["ldw"], ly["ldt"] = _ceil8(ly["N"]), ly["K"]
+            assert ly["K"] % 8 == 0
+        self.n_params_padded = off
+        dev = self.device
+        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        gen = torch.Generator().manual_seed(0 if seed is None else int(seed))
+        for ly in self.layers:           # Keras defaults: glorot-uniform kernels, zero biases
+            if ly["kind"] == "frame":
+                k, ci, co = ly["k"], ly["c_in_real"], ly["N"]
+                limit = math.sqrt(6.0 / (k * ci + k * co))
+                w = (torch.rand((k, ci, co), generator=gen) * 2 - 1) * limit
+                wp = torch.zeros((k, ly["c_in"], co))
+                wp[:, :ci] = w
+                self._w_view(ly).copy_(wp.reshape(ly["K"], co))
+            else:
+                limit = math.sqrt(6.0 / (ly["K"] + ly["N"]))
+                self._w_view(ly).copy_((torch.rand((ly["K"], ly["N"]), generator=gen) * 2 - 1) * limit)
+        for ly in self.layers:
+            ly["W"] = torch.zeros((ly["K"], ly["ldw"]), dtype=torch.bfloat16, device=dev)
+            ly["Wt"] = torch.zeros((ly["N"], ly["ldt"]), dtype=torch.bfloat16, device=dev)
+            ly["W_lo"] = ly["Wt_lo"] = None
+        self._weights_dirty, self._lo_dirty = True, True
+
+    def _w_view(self, ly):
+        return self.params[ly["w_off"]:ly["w_off"] + ly["K"] * ly["N"]].view(ly["K"], ly["N"])
+
+    def _b_view(self, ly):
+        return self.params[ly["b_off"]:ly["b_off"] + ly["N"]]
+
+    def count_params(self):
+        return sum((ly["k"] * ly["c_in_real"] if ly["kind"] == "frame" else ly["K"]) * ly["N"] + ly["N"]
+                   for ly in self.layers)
+
+    def get_weights(self):
+        """dict name/kernel|bias -> numpy array in Keras layouts."""
+        out = {}
+        for ly in self.layers:
+            w = self._w_view(ly).cpu()
+            if ly["kind"] == "frame":
+                w = w.view(ly["k"], ly["c_in"], ly["N"])[:, :ly["c_in_real"]]
+            out[ly["name"] + "/kernel"] = w.numpy().copy()
+            out[ly["name"] + "/bias"] = self._b_view(ly).cpu().numpy().copy()
+        return out
+
+    def set_weights(self, weights):
+        """Load reference-format weights (dict as returned by get_weights; Keras layouts)."""
+        for ly in self.layers:
+            w = torch.as_tensor(np.asarray(weights[ly["name"] + "/kernel"]), dtype=torch.float32)
+            if ly["kind"] == "frame":
+                if tuple(w.shape) != (ly["k"], ly["c_in_real"], ly["N"]):
+                    raise ValueError("bad kernel shape for %s: %s" % (ly["name"], tuple(w.shape)))
+                wp = torch.zeros((ly["k"], ly["c_in"], ly["N"]))
+                wp[:, :ly["c_in_real"]] = w
+                w = wp.reshape(ly["K"], ly["N"])
+            elif tuple(w.shape) != (ly["K"], ly["N"]):
+                raise ValueError("bad kernel shape for %s: %s" % (ly["name"], tuple(w.shape)))
+            self._w_view(ly).copy_(w)
+            self._b_view(ly).copy_(torch.as_tensor(np.asarray(weights[ly["name"] + "/bias"]), dtype=torch.float32))
+        self._weights_dirty = self._lo_dirty = True
+
+    def _refresh(self, need_lo):
+        lib, st = _lib.lib(), _lib.stream_ptr(self.device)
+        if need_lo and self.layers[0]["Wt_lo"] is None:
+            for ly in self.layers:
+                ly["Wt_lo"] = torch.zeros_like(ly["Wt"])
+            self._lo_dirty = True
+        if not (self._weights_dirty or (need_lo and self._lo_dirty)):
+            return
+        for ly in self.layers:
+            lo = ly["Wt_lo"] if need_lo else None
+            _lib.check(lib.lbx_refresh_weights(_lib.ptr(self._w_view(ly)), ly["K"], ly["N"], _lib.ptr(ly["W"]), None,
+                                               ly["ldw"], _lib.ptr(ly["Wt"]), _lib.ptr(lo), ly["ldt"], st))
+        self._weights_dirty = False
+        if need_lo:
+            self._lo_dirty = False
+        else:
+            self._lo_dirty = True
+
+    # ------------------------------------------------------------------ buffers
+    def _buffers(self, B, T, training):
+        key = (B, T, self.precision, bool(training))
+        bufs = self._bufs.get(key)
+        if bufs is not None:
+            return bufs
+        if len(self._bufs) > 4:
+            self._bufs.clear()
+        geo = _Geometry(T, self.frames)
+        dev, bf = self.device, torch.bfloat16
+        split = self.precision == "fp32"
+        n = len(self.frames)
+        X, X_lo = [], []
+        for L in range(n):
+            c = self.layers[L]["c_in"]
+            X.append(torch.zeros((B * geo.Tpad[L] + _SLACK_ROWS, c), dtype=bf, device=dev))
+            X_lo.append(torch.zeros_like(X[-1]) if split else None)
+        cn = self.layers[n - 1]["N"]
+        cnp = _ceil8(cn)
+        Y = torch.zeros((B * geo.R[n - 1] + _SLACK_ROWS, cnp), dtype=torch.float32 if split else bf, device=dev)
+        bufs = dict(geo=geo, X=X, X_lo=X_lo, Y=Y, cn=cn, cnp=cnp,
+                    pooled=torch.zeros((B, 2 * cn), dtype=torch.float32, device=dev),
+                    var_raw=torch.zeros((B, cn), dtype=torch.float32, device=dev),
+                    pooled_hi=torch.zeros((B, 2 * cn), dtype=bf, device=dev),
+                    pooled_lo=torch.zeros((B, 2 * cn), dtype=bf, device=dev) if split else None,
+                    H=[], H_lo=[], emb=torch.zeros((B, self.segments[0].units), dtype=torch.float32, device=dev),
+                    logits=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev),
+                    out=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev))
+        for sgm in self.segments:
+            bufs["H"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev))
+            bufs["H_lo"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev) if split else None)
+        if training:
+            # gradients w.r.t. each layer's (masked) pre-activation, in the geometry of that layer's output buffer
+            bufs["dZ"] = [torch.zeros_like(X[L + 1]) for L in range(n - 1)] + [torch.zeros_like(Y)]
+            bufs["gpool"] = torch.zeros((B, 2 * cn), dtype=torch.float32, device=dev)
+            bufs["dH"] = [torch.zeros_like(h) for h in bufs["H"]]
+            npad = _ceil8(self.num_outputs)
+            bufs["dlogits"] = torch.zeros((B, npad), dtype=bf, device=dev)
+            bufs["loss"] = torch.zeros((B,), dtype=torch.float32, device=dev)
+            bufs["z"] = torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev)
+        self._bufs[key] = bufs
+        return bufs
+
+    # ------------------------------------------------------------------ forward
+    def _prepare_input(self, x):
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(np.asarray(x))
+        if x.dim() != 3 or x.shape[2] != self.F:
+            raise ValueError("expected input of shape [B, T, %d], got %s" % (self.F, tuple(x.shape)))
+        if x.shape[1] < 1:
+            raise ValueError("empty time axis")
+        return x.to(self.device, torch.float32).contiguous()
+
+    def _forward(self, x, bufs, training, upto_embedding=False):
+        lib, st = _lib.lib(), _lib.stream_ptr(self.device)
+        geo = bufs["geo"]
+        B, T, _ = x.shape
+        split = self.precision == "fp32"
+        self._refresh(need_lo=split)
+        n = len(self.frames)
+        rate = self.channel_dropout_rate if training else 0.0
+        self._dropout_calls += 1
+        _lib.check(lib.lbx_pack_rows_bf16(_lib.ptr(x), B, T, self.F, _lib.ptr(bufs["X"][0]), _lib.ptr(bufs["X_lo"][0]),
+                                          geo.Tpad[0], geo.pad[0], self.Fp, rate,
+                                          self._dropout_seed + 7919 * self._dropout_calls, st))
+        for L in range(n):
+            ly = self.layers[L]
+            last = L == n - 1
+            out = bufs["Y"] if last else bufs["X"][L + 1]
+            out_lo = None if (last or not split) else bufs["X_lo"][L + 1]
+            ldo = bufs["cnp"] if last else ly["N"]
+            out_off = 0 if last else geo.pad[L + 1] * ly["N"]
+            ops.gemm(bufs["X"][L], B * geo.R[L], ly["K"], ly["s"] * ly["c_in"], ly["Wt"], ly["N"], ly["K"], ly["ldt"],
+                     out, ldo, a_lo=bufs["X_lo"][L], b_lo=ly["Wt_lo"] if split else None, out_lo=out_lo,
+                     out_off=out_off, bias=self._b_view(ly), relu=ly["relu"], rows_per_utt=geo.R[L],
+                     valid_rows=geo.T[L + 1])
+        _lib.check(lib.lbx_stats_pool_fwd(_lib.ptr(bufs["Y"]), ops.F32 if split else ops.BF16, B, geo.R[n - 1],
+                                          geo.T[n], bufs["cn"], bufs["cnp"], STDDEV_SQRT_MIN_CLIP,
+                                          _lib.ptr(bufs["pooled"]), _lib.ptr(bufs["var_raw"]),
+                                          _lib.ptr(bufs["pooled_hi"]), _lib.ptr(bufs["pooled_lo"]), st))
+        a, a_lo = bufs["pooled_hi"], bufs["pooled_lo"]
+        for i, sgm in enumerate(self.segments):
+            ly = self.layers[n + i]
+            if i == 0 and upto_embedding:
+                ops.gemm(a, B, ly["K"], ly["K"], ly["Wt"], ly["N"], ly["K"], ly["ldt"], bufs["emb"], ly["N"], a_lo=a_lo,
+                         b_lo=ly["Wt_lo"] if split else None, bias=self._b_view(ly), relu=False)
+                return bufs["emb"]
+            ops.gemm(a, B, ly["K"], ly["K"], ly["Wt"], ly["N"], ly["K"], ly["ldt"], bufs["H"][i], ly["N"], a_lo=a_lo,
+                     b_lo=ly["Wt_lo"] if split else None, out_lo=bufs["H_lo"][i], bias=self._b_view(ly),
+                     relu=ly["relu"])
+            a, a_lo = bufs["H"][i], bufs["H_lo"][i]
+        ly = self.layers[-1]
+        ops.gemm(a, B, ly["K"], ly["K"], ly["Wt"], ly["N"], ly["K"], ly["ldt"], bufs["logits"], ly["N"], a_lo=a_lo,
+                 b_lo=ly["Wt_lo"] if split else None, bias=self._b_view(ly), relu=False)
+        return bufs["logits"]
+
+    def __call__(self, x, training=False):
+        x = self._prepare_input(x)
+        B, T, _ = x.shape
+        bufs = self._buffers(B, T, False)
+        lib, st = _lib.lib(), _lib.stream_ptr(self.device)
+        logits = self._forward(x, bufs, training)
+        if self.head == "none":
+            return logits.clone()
+        if self.head == "l2_normalize":
+            dummy = torch.zeros(B, dtype=torch.int32, device=self.device)
+            z = torch.empty_like(logits)
+            _lib.check(lib.lbx_ap_loss(_lib.ptr(logits), _lib.ptr(dummy), B, self.num_outputs, 1, 1.0, 1, _lib.ptr(z),
+                                       None, None, None, None, 0, None, 1.0, st))
+            return z
+        _lib.check(lib.lbx_logsoftmax_xent(_lib.ptr(logits), None, B, self.num_outputs, _lib.ptr(bufs["out"]), None,
+                                           None, 0, 1.0, st))
+        return bufs["out"].clone()
+
+    predict = __call__
+
+    # ------------------------------------------------------------------ training
+    def configure_optimizer(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+        """Adam with the Keras defaults (eps = 1e-7), fp32 master weights and moments."""
+        self._adam = dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps, m=torch.zeros_like(self.params),
+                          v=torch.zeros_like(self.params),
+                          step=torch.zeros(1, dtype=torch.int64, device=self.device),
+                          lr_t=torch.zeros(1, dtype=torch.float32, device=self.device))
+
+    def loss_and_grads(self, x, y, loss="xent", ap_classes=None, delta_weight=1.0, global_batch=None):
+        """Forward + backward of one batch in bf16 (fp32 accumulation / statistics / loss).  Fills self.grads with
+        d(mean loss)/d(params) (mean over `global_batch`, default this batch) and returns the per-sample losses."""
+        if self.precision != "bf16":
+            raise ValueError("training runs in precision='bf16' (fp32 master weights); create the model with it")
+        x = self._prepare_input(x)
+        B, T, _ = x.shape
+        y = torch.as_tensor(y).to(self.device, torch.int32).reshape(-1).contiguous()   # [B,1] labels are squeezed
+        if y.numel() != B:
+            raise ValueError("labels must have one entry per sample")
+        bufs = self._buffers(B, T, True)
+        geo = bufs["geo"]
+        lib, st = _lib.lib(), _lib.stream_ptr(self.device)
+        n = len(self.frames)
+        logits = self._forward(x, bufs, True)
+        scale = 1.0 / float(global_batch or B)
+        npad = bufs["dlogits"].shape[1]
+        if loss == "xent":
+            _lib.check(lib.lbx_logsoftmax_xent(_lib.ptr(logits), _lib.ptr(y), B, self.num_outputs, None,
+                                               _lib.ptr(bufs["loss"]), _lib.ptr(bufs["dlogits"]), npad, scale, st))
+        elif loss == "ap":
+            N = int(ap_classes or self.num_outputs)
+            _lib.check(lib.lbx_ap_loss(_lib.ptr(logits), _lib.ptr(y), B, self.num_outputs, N, float(delta_weight), 1,
+                                       _lib.ptr(bufs["z"]), None, _lib.ptr(bufs["loss"]), None,
+                                       _lib.ptr(bufs["dlogits"]), npad, None, scale, st))
+        else:
+            raise ValueError("loss must be 'xent' or 'ap'")
+        self.grads.zero_()
+        g = self.grads
+
+        def wgrad(a, a_rows, a_cols, lda, dz, dz_cols, dz_pitch, ly, a_off=0, dz_off=0):
+            tiles = -(-a_cols // 128) * -(-dz_cols // 256)
+            ks = max(1, min(-(-a_rows // 64), 148 // tiles))
+            ops.gemm(a, a_rows, a_cols, lda, dz, a_rows, dz_cols, dz_pitch, g, ly["N"], layout=1, a_off=a_off,
+                     b_off=dz_off, out_off=ly["w_off"], k_splits=ks, epi_atomic=True)
+            _lib.check(lib.lbx_colsum_bf16(ops._addr(dz, dz_off), a_rows, dz_cols, dz_pitch,
+                                           ops._addr(g, ly["b_off"]), st))
+
+        # ---- dense head ----
+        dz, dz_cols, dz_pitch = bufs["dlogits"], self.num_outputs, npad
+        acts = [bufs["pooled_hi"]] + bufs["H"]
+        for i in range(len(self.segments), -1, -1):
+            ly = self.layers[n + i]
+            wgrad(acts[i], B, ly["K"], ly["K"], dz, dz_cols, dz_pitch, ly)
+            if i > 0:      # d hidden = dz . W^T, masked by the ReLU of the layer below
+                ops.gemm(dz, B, dz_cols, dz_pitch, ly["W"], ly["K"], ly["N"], ly["ldw"], bufs["dH"][i - 1], ly["K"],
+                         mask_src=bufs["H"][i - 1] if self.layers[n + i - 1]["relu"] else None)
+                dz, dz_cols, dz_pitch = bufs["dH"][i - 1], ly["K"], ly["K"]
+            else:          # d pooled (fp32, no mask)
+                ops.gemm(dz, B, dz_cols, dz_pitch, ly["W"], ly["K"], ly["N"], ly["ldw"], bufs["gpool"], ly["K"])
+        # ---- statistics pooling (+ ReLU mask of the last frame layer) ----
+        _lib.check(lib.lbx_stats_pool_bwd(_lib.ptr(bufs["Y"]), B, geo.R[n - 1], geo.T[n], bufs["cn"], bufs["cnp"],
+                                          STDDEV_SQRT_MIN_CLIP, _lib.ptr(bufs["pooled"]), _lib.ptr(bufs["var_raw"]),
+                                          _lib.ptr(bufs["gpool"]), _lib.ptr(bufs["dZ"][n - 1]), st))
+        # ---- frame layers, last to first ----
+        for L in range(n - 1, -1, -1):
+            ly = self.layers[L]
+            rows = B * geo.R[L]
+            dZ = bufs["dZ"][L]
+            dz_pitch = bufs["cnp"] if L == n - 1 else ly["N"]
+            dz_off = 0 if L == n - 1 else geo.pad[L + 1] * ly["N"]
+            wgrad(bufs["X"][L], rows, ly["K"], ly["s"] * ly["c_in"], dZ, ly["N"], dz_pitch, ly, dz_off=dz_off)
+            if L == 0:
+                break
+            # data gradient through the same overlapping view, masked by the ReLU of layer L-1 (= X[L] > 0; padding
+            # and junk rows of X[L] are zero, so they stay zero in dZ[L-1])
+            k, s, c = ly["k"], ly["s"], ly["c_in"]
+            if not self.layers[L - 1]["relu"]:
+                raise NotImplementedError("linear frame layers are not supported in the backward pass")
+            first = min(k, s)                        # taps [0, first) tile the time axis without overlap
+            ops.gemm(dZ, rows, ly["N"], dz_pitch, ly["W"], first * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
+                     a_off=dz_off, mask_src=bufs["X"][L])
+            j = first
+            while j < k:                             # remaining taps overlap the next row: accumulate pass(es)
+                cnt = min(s, k - j)
+                ops.gemm(dZ, rows, ly["N"], dz_pitch, ly["W"], cnt * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
+                         a_off=dz_off, b_off=j * c * ly["ldw"], out_off=j * c, mask_src=bufs["X"][L], mask_off=j * c,
+                         accumulate=True)
+                j += cnt
+        return bufs["loss"]
+
+    def apply_gradients(self, grad_scale=1.0):
+        if self._adam is None:
+            self.configure_optimizer()
+        a = self._adam
+        _lib.check(_lib.lib().lbx_adam_step(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(a["m"]),
+                                            _lib.ptr(a["v"]), self.params.numel(), a["lr"], a["beta1"], a["beta2"],
+                                            a["eps"], _lib.ptr(a["step"]), _lib.ptr(a["lr_t"]), float(grad_scale),
+                                            _lib.stream_ptr(self.device)))
+        self._weights_dirty = self._lo_dirty = True
+        self._refresh(need_lo=False)
+
+    def train_step(self, x, y, loss="xent", process_group=None, **kw):
+        """One optimisation step; with a process group the flat fp32 gradient is sum-all-reduced over NCCL first."""
+        world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(process_group)
+        B = x.shape[0]
+        losses = self.loss_and_grads(x, y, loss=loss, global_batch=B * world, **kw)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, group=process_group)
+        self.apply_gradients()
+        return losses
+
+
+class GraphedTrainStep:
+    """The whole optimisation step (optionally preceded by a caller-supplied feature stage) captured once into a
+    CUDA graph and replayed: the ~60 kernel launches of a step cost one host call.  Inputs are read from the static
+    tensors given at construction; copy new data into them before calling."""
+
+    def __init__(self, model, x_static, y_static, loss="xent", process_group=None, pre=None, warmup=3, **kw):
+        self.model, self.x, self.y = model, x_static, y_static
+        lib = _lib.lib()
+
+        def body():
+            feats = pre() if pre is not None else self.x
+            return model.train_step(feats, self.y, loss=loss, process_group=process_group, **kw)
+
+        side = torch.cuda.Stream(device=model.device)
+        side.wait_stream(torch.cuda.current_stream(model.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream(model.device).wait_stream(side)
+        torch.cuda.synchronize(model.device)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = lib.lbx_launch_count()
+        with torch.cuda.graph(self.graph):
+            self.losses = body()
+        self.kernels_per_step = int(lib.lbx_launch_count() - n0)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.losses
+
+
+def create(input_shape, num_outputs, channel_dropout_rate=0, name="x-vector", **kwargs):
+    """lidbox/models/xvector.py:46-67.  Extra keyword arguments (precision=, head=, seed=, device=) are extensions."""
+    return XVector(input_shape, num_outputs, channel_dropout_rate=channel_dropout_rate, name=name, **kwargs)
+
+
+def as_embedding_extractor(m):
+    """xvector.py:70-73: drops segment1's activation (MUTATES m, like the reference) and returns a callable
+    mapping [B, T, F] -> [B, 512] pre-ReLU segment1 outputs."""
+    n = len(m.frames)
+    m.segments[0].activation = None
+    m.layers[n]["relu"] = False
+    return _EmbeddingExtractor(m)
+
+
+class _EmbeddingExtractor:
+    def __init__(self, model):
+        self.model = model
+
+    def __call__(self, x, training=False):
+        m = self.model
+        x = m._prepare_input(x)
+        bufs = m._buffers(x.shape[0], x.shape[1], False)
+        return m._forward(x, bufs, training, upto_embedding=True).clone()
+
+    predict = __call__

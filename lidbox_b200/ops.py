@@ -8,6 +8,10 @@ from . import _lib
 
 F32, BF16 = 0, 1
 
+# bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream:
+# entries are (start_event, end_event, M, N, K, n_terms, layout)
+GEMM_TIMER = None
+
 
 def _addr(t, offset_elems=0):
     if t is None:
@@ -37,4 +41,14 @@ def gemm(a, a_rows, a_cols, lda, b, b_rows, b_cols, ldb, out, ldo, *, layout=0, 
     d.rows_per_utt, d.valid_rows = rows_per_utt, valid_rows
     d.mask_src = _addr(mask_src, mask_off)
     d.accumulate = int(accumulate)
+    if GEMM_TIMER is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().lbx_gemm_bf16(ctypes.byref(d), _lib.stream_ptr(a.device)))
+        e1.record()
+        if layout == 0:
+            GEMM_TIMER.append((e0, e1, a_rows, b_rows, a_cols, d.n_terms, 0))
+        else:
+            GEMM_TIMER.append((e0, e1, a_cols, b_cols, a_rows, d.n_terms, 1))
+        return
     _lib.check(_lib.lib().lbx_gemm_bf16(ctypes.byref(d), _lib.stream_ptr(a.device)))

@@ -331,25 +331,42 @@ def sparse_xent_on_logprobs(y, logp):
 # --------------------------------------------------------------------------- #
 
 
-def torch_xvector_forward(params, x, embedding=False, l2_normalize=False):
+def _bf16_ste(t, round_grad=False):
+    """Round to bfloat16 in the forward pass with a straight-through gradient; optionally also round the incoming
+    gradient to bfloat16 (mirrors where the bf16 training path stores activations / data gradients in bf16)."""
+    import torch
+    r = t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+    if round_grad and r.requires_grad:
+        r.register_hook(lambda g: g.to(torch.bfloat16).to(g.dtype))
+    return r
+
+
+def torch_xvector_forward(params, x, embedding=False, l2_normalize=False, emulate_bf16=False):
     """Same math as xvector_forward with torch ops so autograd provides the backward.
-    params: dict name -> torch tensor in Keras layouts; x: [B, T, F]."""
+    params: dict name -> torch tensor in Keras layouts; x: [B, T, F].
+    emulate_bf16=True restates the precision="bf16" training path: weights, stored activations and stored data
+    gradients are rounded to bfloat16 at the points where the CUDA path keeps them in bf16 (accumulation, biases,
+    pooling statistics, logits and the loss stay in high precision).  It exists so that the backward kernels can be
+    checked tightly; the plain fp64 path remains the reference semantics."""
     import torch
     import torch.nn.functional as F
-    h = x.transpose(1, 2)                                    # NCW for conv1d
+    q = (lambda t, g=False: _bf16_ste(t, g)) if emulate_bf16 else (lambda t, g=False: t)
+    h = q(x).transpose(1, 2)                                 # NCW for conv1d
     for name, _, k, stride in FRAME_LAYERS:
-        w = params[name + "/kernel"].permute(2, 1, 0)        # [k, Cin, Cout] -> [Cout, Cin, k] (cross-correlation)
-        h = F.relu(F.conv1d(F.pad(h, (k - 1, 0)), w, params[name + "/bias"], stride=stride))
+        w = q(params[name + "/kernel"]).permute(2, 1, 0)     # [k, Cin, Cout] -> [Cout, Cin, k] (cross-correlation)
+        h = q(F.relu(F.conv1d(F.pad(h, (k - 1, 0)), w, params[name + "/bias"], stride=stride)), True)
     mean = h.mean(dim=2)
     var = ((h - mean[:, :, None]) ** 2).mean(dim=2)
     std = torch.sqrt(torch.clamp(var, min=STDDEV_SQRT_MIN_CLIP))
-    h = torch.cat([mean, std], dim=1)
-    h = h @ params["segment1/kernel"] + params["segment1/bias"]
+    h = q(torch.cat([mean, std], dim=1))
+    h = h @ q(params["segment1/kernel"]) + params["segment1/bias"]
     if embedding:
         return h
-    h = F.relu(h)
-    h = F.relu(h @ params["segment2/kernel"] + params["segment2/bias"])
-    h = h @ params["outputs/kernel"] + params["outputs/bias"]
+    h = q(F.relu(h), True)
+    h = q(F.relu(h @ q(params["segment2/kernel"]) + params["segment2/bias"]), True)
+    h = h @ q(params["outputs/kernel"]) + params["outputs/bias"]
+    if emulate_bf16 and h.requires_grad:
+        h.register_hook(lambda g: g.to(torch.bfloat16).to(g.dtype))
     if l2_normalize:                                         # spherespeaker.py:28-31 style head for the AP config
         return h / torch.sqrt(torch.clamp((h * h).sum(dim=1, keepdim=True), min=1e-12))
     return torch.log_softmax(h, dim=-1)

@@ -114,7 +114,8 @@ int lbx_logmel_f32_host(const float* sig_host, long long B, long long N, int sam
  * a0.b0 + a0.b1 + a1.b0 for fp32-grade results (forward fp32 config).
  * Epilogue, per output element (m, n), in this order: + bias[n]; ReLU; zero unless mask_src[m*ldo+n] > 0;
  * then either atomicAdd into fp32 out (epi_atomic, required for k_splits > 1), or out (+)= x as fp32 / bf16
- * (plus out_lo = bf16 residual).  Rows with (m % rows_per_utt) >= valid_rows are not stored when rows_per_utt > 0. */
+ * (plus out_lo = bf16 residual).  Rows with (m % rows_per_utt) >= valid_rows are stored as ZERO when rows_per_utt > 0 (they land on
+ * destination rows that must stay zero: junk rows and the next utterance's causal padding). */
 typedef struct lbx_gemm_t {
   const void* a0; const void* a1;
   long long a_rows; int a_cols; long long lda;
@@ -131,6 +132,7 @@ typedef struct lbx_gemm_t {
   int rows_per_utt; int valid_rows;
   const void* mask_src;     /* bf16, indexed like out */
   int accumulate;
+  int tile_n;               /* 0 = automatic, or 128 / 256 */
 } lbx_gemm_t;
 int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream);
 

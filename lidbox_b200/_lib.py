@@ -21,6 +21,7 @@ class GemmDesc(ctypes.Structure):
         ("layout", c_int), ("n_terms", c_int), ("k_splits", c_int), ("epi_atomic", c_int), ("out_dtype", c_int),
         ("out", c_void_p), ("out_lo", c_void_p), ("ldo", c_ll), ("bias", c_void_p), ("relu", c_int),
         ("rows_per_utt", c_int), ("valid_rows", c_int), ("mask_src", c_void_p), ("accumulate", c_int),
+        ("tile_n", c_int),
     ]
 
 

@@ -19,13 +19,20 @@
 
 namespace lbx {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-constexpr int B_BYTES = BN * BK * 2;          // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_THREADS = 192;
-constexpr int TMEM_COLS = 512;                // 2 accumulator stages x 256 fp32 columns
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;                  // two warps per TMEM sub-partition, each takes half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+
+// tile-N variants: 256 (large problems) and 128 (problems with fewer than ~2 tiles per SM at N=256)
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;    // 2 accumulator stages x BN fp32 columns
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct GemmParams {
   int M, N, K;             // output rows, output cols, contraction length
@@ -123,7 +130,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M=128, N=256
+// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M=128, N=BN
+template <int BN>
 __host__ __device__ constexpr uint32_t make_idesc(int a_mn_major, int b_mn_major) {
   return (1u << 4)                       // c_format = F32
          | (1u << 7)                     // a_format = BF16
@@ -142,11 +150,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // ------------------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------------------
-template <int LAYOUT>
+// load 32 consecutive bf16 (16-byte vectors when possible) as floats
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, bool vec, int ncols, float (&f)[32]) {
+  if (vec) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 u = reinterpret_cast<const uint4*>(src)[q];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[8 * q + 2 * i] = __uint_as_float(w[i] << 16);
+        f[8 * q + 2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = j < ncols ? __bfloat162float(src[j]) : 0.0f;
+  }
+}
+
+template <int LAYOUT, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                      const GemmParams p) {
+  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
@@ -176,7 +204,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i, 1);
-      mbar_init(tempty_bar + i, 4);   // one arrival per epilogue warp
+      mbar_init(tempty_bar + i, EPI_WARPS);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -207,7 +235,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             mbar_wait(empty_bar + stage, phase ^ 1);
             unsigned char* sA = smem + (size_t)stage * STAGE_BYTES;
             unsigned char* sB = sA + A_BYTES;
-            mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+            mbar_expect_tx(full_bar + stage, (uint32_t)STAGE_BYTES);
             if (LAYOUT == 0) {
               tma_load_2d(mA, full_bar + stage, sA, kb * BK, m_blk * BM);
               tma_load_2d(mB, full_bar + stage, sB, kb * BK, n_blk * BN);
@@ -227,7 +255,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(LAYOUT, LAYOUT);
+      constexpr uint32_t idesc = make_idesc<BN>(LAYOUT, LAYOUT);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -266,108 +294,138 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   } else {
     // ===================================== epilogue =====================================
     const int sub = warp & 3;                    // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
+    const int chalf = (warp - 2) >> 2;           // which half of the tile's columns this warp drains
+    constexpr int CHUNKS = BN / 64;              // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int split = tile / mn_tiles, rem = tile - split * mn_tiles;
+      const int rem = tile % mn_tiles;
       const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
-      (void)split;
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const int m = m_blk * BM + sub * 32 + lane;
-      bool row_ok = m < p.M;
-      if (p.rows_per_utt > 0) row_ok = row_ok && ((m % p.rows_per_utt) < p.valid_rows);
+      const bool in_range = m < p.M;
+      // rows past the valid part of an utterance are stored as zeros: they land on rows of the destination that
+      // must stay zero anyway (junk rows / the next utterance's causal padding)
+      const bool row_zero = p.rows_per_utt > 0 && ((m % p.rows_per_utt) >= p.valid_rows);
       const long long row_off = (long long)m * p.ldo;
-      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)acc * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
+      const int col_base = n_blk * BN + chalf * (BN / 2);
+      constexpr int GROUP = 2, NGROUPS = CHUNKS / GROUP;     // 64 columns in flight per warp
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
+      for (int grp = 0; grp < NGROUPS; ++grp) {
+      uint32_t v[GROUP][32];
+#pragma unroll
+      for (int c = 0; c < GROUP; ++c)
+        if (col_base + (grp * GROUP + c) * 32 < p.N) tc_ld32(taddr + (grp * GROUP + c) * 32, v[c]);   // warp-uniform
+      tc_wait_ld();
+      if (grp == NGROUPS - 1) {
+        // all TMEM reads of this warp are done: release the accumulator stage before touching global memory
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (!in_range) continue;
+#pragma unroll
+      for (int c = 0; c < GROUP; ++c) {
+        const int n0 = col_base + (grp * GROUP + c) * 32;
         if (n0 >= p.N) break;
-        uint32_t v[32];
-        tc_ld32(taddr + c * 32, v);
-        tc_wait_ld();
-        if (row_ok) {
-          const int ncols = min(32, p.N - n0);
-          float x[32];
+        const int ncols = min(32, p.N - n0);
+        float x[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[c][j]);
+        if (p.bias != nullptr) {
+          const float* bp = p.bias + n0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) x[j] += __ldg(p.bias + n0 + j);
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
-          }
-          if (p.mask_src != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols && !(__bfloat162float(p.mask_src[row_off + n0 + j]) > 0.0f)) x[j] = 0.0f;
-          }
-          if (p.epi_atomic) {
-            float* o = reinterpret_cast<float*>(p.out) + row_off + n0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) atomicAdd(o + j, x[j]);
-          } else if (p.out_dtype == LBX_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + row_off + n0;
-            if (p.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) x[j] += o[j];
-            }
-            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                reinterpret_cast<float4*>(o)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) o[j] = x[j];
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + q);
+              x[4 * q] += b4.x; x[4 * q + 1] += b4.y; x[4 * q + 2] += b4.z; x[4 * q + 3] += b4.w;
             }
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n0;
-            if (p.accumulate) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) x[j] += __bfloat162float(o[j]);
-            }
-            const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-            if (vec) {
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) x[j] += __ldg(bp + j);
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+        }
+        if (row_zero) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+        }
+        if (p.mask_src != nullptr) {
+          const __nv_bfloat16* mp = p.mask_src + row_off + n0;
+          float mk[32];
+          load_bf16x32(mp, ncols == 32 && ((reinterpret_cast<uintptr_t>(mp) & 15) == 0), ncols, mk);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (!(mk[j] > 0.0f)) x[j] = 0.0f;
+        }
+        if (p.epi_atomic) {
+          float* o = reinterpret_cast<float*>(p.out) + row_off + n0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) atomicAdd(o + j, x[j]);
+        } else if (p.out_dtype == LBX_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + row_off + n0;
+          const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+          if (p.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) x[j] += o[j];
+          }
+          if (vec) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(o)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) o[j] = x[j];
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n0;
+          const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+          if (p.accumulate) {
+            float prev[32];
+            load_bf16x32(o, vec, ncols, prev);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += prev[j];
+          }
+          if (vec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              reinterpret_cast<uint4*>(o)[q] =
+                  make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
+                             pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) o[j] = __float2bfloat16_rn(x[j]);
+          }
+          if (p.out_lo != nullptr) {
+            __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + row_off + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] -= __bfloat162float(__float2bfloat16_rn(x[j]));
+            if (vec && ((reinterpret_cast<uintptr_t>(ol) & 15) == 0)) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                reinterpret_cast<uint4*>(o)[q] =
+                reinterpret_cast<uint4*>(ol)[q] =
                     make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
                                pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < ncols) o[j] = __float2bfloat16_rn(x[j]);
-            }
-            if (p.out_lo != nullptr) {
-              __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + row_off + n0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] -= __bfloat162float(__float2bfloat16_rn(x[j]));
-              if (vec && ((reinterpret_cast<uintptr_t>(ol) & 15) == 0)) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  reinterpret_cast<uint4*>(ol)[q] =
-                      make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
-                                 pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) ol[j] = __float2bfloat16_rn(x[j]);
-              }
+                if (j < ncols) ol[j] = __float2bfloat16_rn(x[j]);
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
   }
 
@@ -469,7 +527,10 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
 
   CUtensorMap mA0, mA1, mB0, mB1;
   int rc;
-  const int boxA_rows = g->layout == 0 ? BM : 64, boxB_rows = g->layout == 0 ? BN : 64;
+  // tile-N 128 when N=256 tiles would leave the machine under two tiles per SM (short single-wave launches)
+  const long long tiles256 = (long long)((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.k_splits;
+  const int bn = (g->tile_n == 128 || g->tile_n == 256) ? g->tile_n : ((tiles256 < 2 * 148 || p.N <= 128) ? 128 : 256);
+  const int boxA_rows = g->layout == 0 ? BM : 64, boxB_rows = g->layout == 0 ? bn : 64;
   if ((rc = make_map(&mA0, g->a0, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
   if ((rc = make_map(&mB0, g->b0, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
   if (g->n_terms == 3) {
@@ -482,17 +543,23 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
     int dev = 0, n = 0;
     LBX_CUDA(cudaGetDevice(&dev));
     LBX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::SMEM));
+    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::SMEM));
+    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM));
+    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM));
     g_num_sms = n;
-    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
   }
-  const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.k_splits;
+  const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.k_splits;
   const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
   cudaStream_t st = (cudaStream_t)stream;
-  if (g->layout == 0)
-    gemm_bf16_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(mA0, mA1, mB0, mB1, p);
+  if (g->layout == 0 && bn == 256)
+    gemm_bf16_kernel<0, 256><<<grid, GEMM_THREADS, Cfg<256>::SMEM, st>>>(mA0, mA1, mB0, mB1, p);
+  else if (g->layout == 0)
+    gemm_bf16_kernel<0, 128><<<grid, GEMM_THREADS, Cfg<128>::SMEM, st>>>(mA0, mA1, mB0, mB1, p);
+  else if (bn == 256)
+    gemm_bf16_kernel<1, 256><<<grid, GEMM_THREADS, Cfg<256>::SMEM, st>>>(mA0, mA1, mB0, mB1, p);
   else
-    gemm_bf16_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(mA0, mA1, mB0, mB1, p);
+    gemm_bf16_kernel<1, 128><<<grid, GEMM_THREADS, Cfg<128>::SMEM, st>>>(mA0, mA1, mB0, mB1, p);
   LBX_LAUNCH_CHECK();
   return LBX_OK;
 }

@@ -527,9 +527,8 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
 
   CUtensorMap mA0, mA1, mB0, mB1;
   int rc;
-  // tile-N 128 when N=256 tiles would leave the machine under two tiles per SM (short single-wave launches)
-  const long long tiles256 = (long long)((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.k_splits;
-  const int bn = (g->tile_n == 128 || g->tile_n == 256) ? g->tile_n : ((tiles256 < 2 * 148 || p.N <= 128) ? 128 : 256);
+  // tile-N 256 unless the problem is narrower than 128 columns (measured: 128 never wins on the TDNN shapes)
+  const int bn = (g->tile_n == 128 || g->tile_n == 256) ? g->tile_n : (p.N <= 128 ? 128 : 256);
   const int boxA_rows = g->layout == 0 ? BM : 64, boxB_rows = g->layout == 0 ? bn : 64;
   if ((rc = make_map(&mA0, g->a0, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
   if ((rc = make_map(&mB0, g->b0, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;

@@ -13,13 +13,14 @@ def t(fn, iters=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
 def nt(name, M, N, K, lda=None, mask=False, acc=False, ldo=None, bias=True, relu=True, tile_n=0, out_f32=False):
-    lda = lda or K; ldo = ldo or (N + 7) // 8 * 8
-    a = torch.randn((M * lda + 8 * K,), device=dev).to(bf)
-    b = torch.randn((N, K), device=dev).to(bf)
+    Kp = (K + 7) // 8 * 8
+    lda = lda or Kp; ldo = ldo or (N + 7) // 8 * 8
+    a = torch.randn((M * lda + 8 * Kp,), device=dev).to(bf)
+    b = torch.randn((N, Kp), device=dev).to(bf)
     out = torch.zeros((M * ldo + 8 * N,), device=dev, dtype=torch.float32 if out_f32 else bf)
     msk = torch.randn((M * ldo + 8 * N,), device=dev).to(bf) if mask else None
     bs = torch.randn((N,), device=dev) if bias else None
-    fn = lambda: ops.gemm(a, M, K, lda, b, N, K, K, out, ldo, bias=bs, relu=relu, mask_src=msk, accumulate=acc, tile_n=tile_n)
+    fn = lambda: ops.gemm(a, M, K, lda, b, N, K, Kp, out, ldo, bias=bs, relu=relu, mask_src=msk, accumulate=acc, tile_n=tile_n)
     us = t(fn)
     print("%-28s M=%6d N=%5d K=%5d tile_n=%3d  %8.1f us  %7.1f TFLOP/s" % (name, M, N, K, tile_n, us, 2.0 * M * N * K / us / 1e6))
 def tn(name, Kc, M, N, lda=None, splits=1, tile_n=0):
@@ -32,6 +33,11 @@ def tn(name, Kc, M, N, lda=None, splits=1, tile_n=0):
     us = t(fn)
     print("%-28s K=%6d M=%5d N=%5d splits=%2d tile_n=%3d %8.1f us  %7.1f TFLOP/s" % (name, Kc, M, N, splits, tile_n, us, 2.0 * M * N * Kc / us / 1e6))
 B, P = 256, 34
+only = sys.argv[1] if len(sys.argv) > 1 else None
+if only:
+    _nt, _tn = nt, tn
+    nt = lambda name, *a, **k: _nt(name, *a, **k) if only in name else None
+    tn = lambda name, *a, **k: _tn(name, *a, **k) if only in name else None
 for tile_n in (256, 128):
     nt("frame1 fwd", B * 6 * P, 512, 200, lda=40, tile_n=tile_n)
     nt("frame2 fwd", B * 3 * P, 512, 1536, lda=1024, tile_n=tile_n)

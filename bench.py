@@ -423,6 +423,12 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _log(msg):
+    if os.environ.get("LBX_BENCH_VERBOSE"):
+        sys.stderr.write("[bench rank %s] %s\n" % (os.environ.get("RANK", "0"), msg))
+        sys.stderr.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -459,7 +465,9 @@ def main():
     peaks = load_peaks()
     wl = WORKLOADS[args.workload](args, rank, world)
     wl.dist = dist
+    _log("setup")
     wl.setup(device)
+    _log("setup done")
 
     def barrier():
         if dist is not None:
@@ -469,6 +477,7 @@ def main():
     for _ in range(args.warmup):
         wl.step()
     barrier()
+    _log("warmup done")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -491,9 +500,11 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
 
+    _log("timed region done")
     # dominant-kernel timing for the roofline (CUDA events on the launching stream)
     roof = wl.roofline_measure(peaks) if hasattr(wl, "roofline_measure") else wl.roofline(ms_per_step, peaks)
 
+    _log("roofline done")
     # end-to-end through the public API with pinned host buffers
     for _ in range(2):
         wl.step_e2e()
@@ -512,6 +523,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_ms = float(t.item())
     h2d, d2h = wl.e2e_bytes()
+    _log("e2e done")
 
     if rank == 0:
         units = wl.units_per_step() * world
@@ -528,7 +540,13 @@ def main():
             line.update(wl.extra())
         print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.destroy_process_group()
+        # ranks > 0 wait here while rank 0 measures the secondary lines; then leave without tearing NCCL down
+        # (destroy_process_group can dead-lock while a captured CUDA graph still references the communicator)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

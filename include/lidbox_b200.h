@@ -133,6 +133,8 @@ typedef struct lbx_gemm_t {
   const void* mask_src;     /* bf16, indexed like out */
   int accumulate;
   int tile_n;               /* 0 = automatic, or 128 / 256 */
+  float* colsum;            /* optional: colsum[n % colsum_mod] += sum_m x[m,n] of the masked result (bias gradient) */
+  int colsum_mod;
 } lbx_gemm_t;
 int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream);
 
@@ -153,14 +155,18 @@ int lbx_pack_rows_bf16(const float* x, long long B, int T, int F, void* hi, void
 int lbx_stats_pool_fwd(const void* y, int y_dtype, long long B, int rows_per_utt, int T, int C, int pitch,
                        float clip_min, float* out, float* var_raw, void* out_hi, void* out_lo, void* stream);
 /* backward of the pooling fused with the ReLU mask of the producing layer: dz = (y > 0) * d pool / d y . gpool */
+/* dbias (optional): bias gradient of the producing layer, dbias[c] += sum_{b,t} dz[b,t,c]; zero_gpool: reset gpool
+ * after it has been consumed (it is accumulated atomically by the split-K GEMM of the next step). */
 int lbx_stats_pool_bwd(const void* y_bf16, long long B, int rows_per_utt, int T, int C, int pitch, float clip_min,
-                       const float* pooled, const float* var_raw, const float* gpool, void* dz_bf16, void* stream);
+                       const float* pooled, const float* var_raw, float* gpool, void* dz_bf16, float* dbias,
+                       int zero_gpool, void* stream);
 
 /* log_softmax (xvector.py:64-65) + sparse categorical cross-entropy on the log-probs, forward + gradient:
  * logp [B,n] (optional), loss [B] = -logp[b, y_b] (optional), dlogits bf16 [B, dl_pitch] =
  * (softmax - onehot) * grad_scale (optional). */
 int lbx_logsoftmax_xent(const float* logits, const int* labels, long long B, int n, float* logp, float* loss,
-                        void* dlogits_bf16, int dl_pitch, float grad_scale, void* stream);
+                        void* dlogits_bf16, int dl_pitch, float grad_scale, float* dbias /* optional: += column sums of
+                        the gradient = bias gradient of the output layer */, void* stream);
 
 /* lidbox/losses.py:12-52 SparseAngularProximity(N, D, delta_weight): theta = acos(z[:, :N]),
  * loss[b] = sum_{l != y_b} sigmoid(delta_weight * (theta[b,y_b] - theta[b,l])).  normalize = 1 first maps
@@ -169,7 +175,7 @@ int lbx_logsoftmax_xent(const float* logits, const int* labels, long long B, int
  * Constructor asserts of losses.py:14-16 are returned as LBX_EINVAL. */
 int lbx_ap_loss(const float* h, const int* labels, long long B, int D, int N, float delta_weight, int normalize,
                 float* z_out, float* theta_out, float* loss, float* grad_f32, void* grad_bf16, int g_pitch,
-                const float* gloss, float grad_scale, void* stream);
+                const float* gloss, float grad_scale, float* dbias, void* stream);
 
 /* bias gradient: out[n] += sum_m x[m, n], x bf16 [rows, pitch] */
 int lbx_colsum_bf16(const void* x, long long rows, int n, int pitch, float* out, void* stream);
@@ -179,6 +185,26 @@ int lbx_colsum_bf16(const void* x, long long rows, int n, int pitch, float* out,
  * call) and the bias-corrected rate (*lr_t_dev) live in device memory so the call can be replayed from a CUDA graph. */
 int lbx_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* stream);
+
+/* Finishing pass of a split-K Dense layer (lbx_gemm_bf16 with epi_atomic into the fp32 accumulator `acc`):
+ * x = acc + bias; ReLU; zero unless mask_src > 0; outputs as bf16 hi (+ lo residual) and/or fp32; colsum[n] += sum_m x;
+ * zero_acc resets acc for its next use. */
+int lbx_dense_finish(float* acc, long long M, int N, int ld_acc, const float* bias, int relu, const void* mask_src,
+                     int ld_mask, void* out_hi, void* out_lo, int ld_out, float* out_f32, int ld_f32, float* colsum,
+                     int zero_acc, void* stream);
+
+/* Fused optimizer step over all layers: Adam (as lbx_adam_step) on the flat fp32 buffers + refresh of the bf16
+ * operand copies W [K, ldw] and W^T [N, ldt] of every layer + optional reset of the gradient buffer. */
+#define LBX_MAX_LAYERS 16
+typedef struct lbx_adam_layers_t {
+  int n_layers;
+  long long w_off[LBX_MAX_LAYERS]; long long b_off[LBX_MAX_LAYERS];   /* element offsets into the flat buffers */
+  int K[LBX_MAX_LAYERS]; int N[LBX_MAX_LAYERS]; int ldw[LBX_MAX_LAYERS]; int ldt[LBX_MAX_LAYERS];
+  void* W[LBX_MAX_LAYERS]; void* Wt[LBX_MAX_LAYERS];                   /* bf16 device buffers */
+} lbx_adam_layers_t;
+int lbx_adam_refresh(const lbx_adam_layers_t* layers, float* params, float* grads, float* m, float* v, float lr,
+                     float beta1, float beta2, float eps, long long* step_dev, float* lr_t_dev, float grad_scale,
+                     int zero_grads, void* stream);
 
 /* fp32 master weight [K, N] (Keras kernel flattened) -> bf16 operand copies: W [K, ldw] (data-gradient operand) and
  * W^T [N, ldt] (forward operand), each as hi (+ lo residual) planes; any of w_hi / t_hi may be NULL. */

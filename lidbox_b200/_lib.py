@@ -21,8 +21,18 @@ class GemmDesc(ctypes.Structure):
         ("layout", c_int), ("n_terms", c_int), ("k_splits", c_int), ("epi_atomic", c_int), ("out_dtype", c_int),
         ("out", c_void_p), ("out_lo", c_void_p), ("ldo", c_ll), ("bias", c_void_p), ("relu", c_int),
         ("rows_per_utt", c_int), ("valid_rows", c_int), ("mask_src", c_void_p), ("accumulate", c_int),
-        ("tile_n", c_int),
+        ("tile_n", c_int), ("colsum", c_void_p), ("colsum_mod", c_int),
     ]
+
+
+MAX_LAYERS = 16
+
+
+class AdamLayers(ctypes.Structure):
+    """lbx_adam_layers_t (include/lidbox_b200.h)."""
+    _fields_ = [("n_layers", c_int), ("w_off", c_ll * MAX_LAYERS), ("b_off", c_ll * MAX_LAYERS),
+                ("K", c_int * MAX_LAYERS), ("N", c_int * MAX_LAYERS), ("ldw", c_int * MAX_LAYERS),
+                ("ldt", c_int * MAX_LAYERS), ("W", c_void_p * MAX_LAYERS), ("Wt", c_void_p * MAX_LAYERS)]
 
 
 # name -> (restype, argtypes); must list every symbol include/lidbox_b200.h declares (tests/test_abi.py checks this)
@@ -44,9 +54,12 @@ SIGNATURES = {
     "lbx_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), _P]),
     "lbx_pack_rows_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, _P]),
     "lbx_stats_pool_fwd": (c_int, [_P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
-    "lbx_stats_pool_bwd": (c_int, [_P, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
-    "lbx_logsoftmax_xent": (c_int, [_P, _P, c_ll, c_int, _P, _P, _P, c_int, c_float, _P]),
-    "lbx_ap_loss": (c_int, [_P, _P, c_ll, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_int, _P, c_float, _P]),
+    "lbx_stats_pool_bwd": (c_int, [_P, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_int, _P]),
+    "lbx_dense_finish": (c_int, [_P, c_ll, c_int, c_int, _P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, _P, c_int, _P]),
+    "lbx_adam_refresh": (c_int, [ctypes.POINTER(AdamLayers), _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P,
+                                 _P, c_float, c_int, _P]),
+    "lbx_logsoftmax_xent": (c_int, [_P, _P, c_ll, c_int, _P, _P, _P, c_int, c_float, _P, _P]),
+    "lbx_ap_loss": (c_int, [_P, _P, c_ll, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_int, _P, c_float, _P, _P]),
     "lbx_colsum_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P]),
     "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P]),
     "lbx_refresh_weights": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P]),

@@ -50,6 +50,8 @@ struct GemmParams {
   int valid_rows;
   const __nv_bfloat16* mask_src;   // optional: keep x only where mask_src[m*ldo + n] > 0 (ReLU backward)
   int accumulate;          // 1: out = out + x (read-modify-write, non-atomic)
+  float* colsum;           // optional: colsum[n % colsum_mod] += sum_m x[m, n] (bias gradient of the layer below)
+  int colsum_mod;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (lane == 0) mbar_arrive(tempty_bar + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (!in_range) continue;
+      if (!in_range && p.colsum == nullptr) continue;
 #pragma unroll
       for (int c = 0; c < GROUP; ++c) {
         const int n0 = col_base + (grp * GROUP + c) * 32;
@@ -353,11 +355,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
         }
-        if (row_zero) {
+        if (row_zero || !in_range) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = 0.0f;
         }
-        if (p.mask_src != nullptr) {
+        if (p.mask_src != nullptr && in_range) {
           const __nv_bfloat16* mp = p.mask_src + row_off + n0;
           float mk[32];
           load_bf16x32(mp, ncols == 32 && ((reinterpret_cast<uintptr_t>(mp) & 15) == 0), ncols, mk);
@@ -365,11 +367,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int j = 0; j < 32; ++j)
             if (!(mk[j] > 0.0f)) x[j] = 0.0f;
         }
-        if (p.epi_atomic) {
+        if (!in_range) {
+          // nothing to store; the lane only takes part in the column-sum reduction below
+        } else if (p.epi_atomic) {
           float* o = reinterpret_cast<float*>(p.out) + row_off + n0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) atomicAdd(o + j, x[j]);
+            for (int q = 0; q < 8; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * q), "f"(x[4 * q]),
+                           "f"(x[4 * q + 1]), "f"(x[4 * q + 2]), "f"(x[4 * q + 3])
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) atomicAdd(o + j, x[j]);
+          }
         } else if (p.out_dtype == LBX_F32) {
           float* o = reinterpret_cast<float*>(p.out) + row_off + n0;
           const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
@@ -390,22 +402,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         } else {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n0;
           const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+          float prev[32];
           if (p.accumulate) {
-            float prev[32];
             load_bf16x32(o, vec, ncols, prev);
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] += prev[j];
+            for (int j = 0; j < 32; ++j) prev[j] = 0.0f;
           }
           if (vec) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              reinterpret_cast<uint4*>(o)[q] =
-                  make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
-                             pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
+              reinterpret_cast<uint4*>(o)[q] = make_uint4(
+                  pack_bf16x2(x[8 * q] + prev[8 * q], x[8 * q + 1] + prev[8 * q + 1]),
+                  pack_bf16x2(x[8 * q + 2] + prev[8 * q + 2], x[8 * q + 3] + prev[8 * q + 3]),
+                  pack_bf16x2(x[8 * q + 4] + prev[8 * q + 4], x[8 * q + 5] + prev[8 * q + 5]),
+                  pack_bf16x2(x[8 * q + 6] + prev[8 * q + 6], x[8 * q + 7] + prev[8 * q + 7]));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < ncols) o[j] = __float2bfloat16_rn(x[j]);
+              if (j < ncols) o[j] = __float2bfloat16_rn(x[j] + prev[j]);
           }
           if (p.out_lo != nullptr) {
             __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + row_off + n0;
@@ -423,6 +438,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (j < ncols) ol[j] = __float2bfloat16_rn(x[j]);
             }
           }
+        }
+        if (p.colsum != nullptr) {
+          // transpose-reduce over the 32 rows of this warp: lane j ends up with the sum of column n0 + j
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send = up ? x[i] : x[i + off];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+              x[i] = (up ? x[i + off] : x[i]) + recv;
+            }
+          }
+          if (lane < ncols) atomicAdd(p.colsum + (n0 + lane) % p.colsum_mod, x[0]);
         }
       }
       }
@@ -524,6 +553,9 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   p.rows_per_utt = g->rows_per_utt; p.valid_rows = g->valid_rows;
   p.mask_src = reinterpret_cast<const __nv_bfloat16*>(g->mask_src);
   p.accumulate = g->accumulate;
+  p.colsum = g->colsum;
+  p.colsum_mod = g->colsum_mod > 0 ? g->colsum_mod : 1;
+  LBX_CHECK_ARG(!(g->colsum && (g->out_lo || g->epi_atomic)), "colsum cannot be combined with out_lo / atomic epilogues");
 
   CUtensorMap mA0, mA1, mB0, mB1;
   int rc;

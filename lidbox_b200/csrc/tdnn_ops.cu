@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) stats_pool_bwd_kernel(const bf16* __restr
 __global__ void __launch_bounds__(128) logsoftmax_xent_kernel(const float* __restrict__ logits, const int* __restrict__ y,
                                                              long long B, int n, float* __restrict__ logp,
                                                              float* __restrict__ loss, bf16* __restrict__ dlogits,
-                                                             int dl_pitch, float grad_scale) {
+                                                             int dl_pitch, float grad_scale, float* __restrict__ dbias) {
   const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -156,7 +156,11 @@ __global__ void __launch_bounds__(128) logsoftmax_xent_kernel(const float* __res
   for (int j = lane; j < n; j += 32) {
     const float lp = row[j] - lse;
     if (logp) logp[b * n + j] = lp;
-    if (dlogits) dlogits[b * dl_pitch + j] = __float2bfloat16_rn((expf(lp) - (j == label ? 1.0f : 0.0f)) * grad_scale);
+    if (dlogits) {
+      const bf16 gq = __float2bfloat16_rn((expf(lp) - (j == label ? 1.0f : 0.0f)) * grad_scale);
+      dlogits[b * dl_pitch + j] = gq;
+      if (dbias) atomicAdd(dbias + j, __bfloat162float(gq));
+    }
     if (loss && j == label) loss[b] = -lp;
   }
 }
@@ -169,7 +173,8 @@ __global__ void __launch_bounds__(128) ap_loss_kernel(const float* __restrict__ 
                                                      int D, int N, float w, int normalize, float* __restrict__ z_out,
                                                      float* __restrict__ theta_out, float* __restrict__ loss,
                                                      float* __restrict__ grad_f32, bf16* __restrict__ grad_bf16,
-                                                     int g_pitch, const float* __restrict__ gloss, float grad_scale) {
+                                                     int g_pitch, const float* __restrict__ gloss, float grad_scale,
+                                                     float* __restrict__ dbias) {
   const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -226,7 +231,11 @@ __global__ void __launch_bounds__(128) ap_loss_kernel(const float* __restrict__ 
     }
     const float g = (normalize ? (dz - z * dot) * inv_norm : dz) * gl;
     if (grad_f32) grad_f32[b * g_pitch + j] = g;
-    if (grad_bf16) grad_bf16[b * g_pitch + j] = __float2bfloat16_rn(g);
+    if (grad_bf16) {
+      const bf16 gq = __float2bfloat16_rn(g);
+      grad_bf16[b * g_pitch + j] = gq;
+      if (dbias) atomicAdd(dbias + j, __bfloat162float(gq));
+    }
   }
 }
 
@@ -311,6 +320,261 @@ __global__ void __launch_bounds__(256) refresh_weights_kernel(const float* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// vectorised bf16 pooling (training path): every thread owns 8 consecutive channels (one 16-byte load per row)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack_bf16x8(const uint4 u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256) stats_pool_fwd_bf16v_kernel(const bf16* __restrict__ y, int rows_per_utt, int T,
+                                                                  int C, int pitch, float clip_min,
+                                                                  float* __restrict__ out, float* __restrict__ var_raw,
+                                                                  bf16* __restrict__ out_hi) {
+  __shared__ float red[8][32][9];
+  const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int cv = blockIdx.x * 32 + lane;                    // 8-channel vector index
+  const int c0 = cv * 8;
+  const long long b = blockIdx.y;
+  const bool active = c0 < pitch;
+  const uint4* base = reinterpret_cast<const uint4*>(y + b * rows_per_utt * (long long)pitch) + cv;
+  const int p8 = pitch >> 3;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active)
+    for (int t = tl; t < T; t += 8) {
+      float f[8];
+      unpack_bf16x8(base[(long long)t * p8], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[tl][lane][i] = s[i];
+  __syncthreads();
+  float mean[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += red[j][lane][i];
+    mean[i] = a / (float)T;
+  }
+  __syncthreads();
+  float q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active)
+    for (int t = tl; t < T; t += 8) {
+      float f[8];
+      unpack_bf16x8(base[(long long)t * p8], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = f[i] - mean[i];
+        q[i] = fmaf(d, d, q[i]);
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[tl][lane][i] = q[i];
+  __syncthreads();
+  if (tl == 0 && active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      if (c >= C) break;
+      float var = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) var += red[j][lane][i];
+      var /= (float)T;
+      const float sd = sqrtf(fminf(fmaxf(var, clip_min), 3.402823466e+38f));
+      out[b * 2 * C + c] = mean[i];
+      out[b * 2 * C + C + c] = sd;
+      if (var_raw) var_raw[b * C + c] = var;
+      if (out_hi) {
+        out_hi[b * 2 * C + c] = __float2bfloat16_rn(mean[i]);
+        out_hi[b * 2 * C + C + c] = __float2bfloat16_rn(sd);
+      }
+    }
+  }
+}
+
+// backward (+ ReLU mask) with the bias gradient of the producing layer accumulated on the fly; consumes (zeroes) gpool
+__global__ void __launch_bounds__(256) stats_pool_bwd_bf16v_kernel(const bf16* __restrict__ y, int rows_per_utt, int T,
+                                                                  int C, int pitch, float clip_min,
+                                                                  const float* __restrict__ pooled,
+                                                                  const float* __restrict__ var_raw,
+                                                                  float* __restrict__ gpool, bf16* __restrict__ dz,
+                                                                  float* __restrict__ dbias, int zero_gpool) {
+  __shared__ float red[8][32][9];
+  const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int cv = blockIdx.x * 32 + lane;
+  const int c0 = cv * 8;
+  const long long b = blockIdx.y;
+  const bool active = c0 < pitch;
+  const int p8 = pitch >> 3;
+  float mean[8], gm[8], gs[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    acc[i] = 0.0f;
+    if (active && c < C) {
+      mean[i] = pooled[b * 2 * C + c];
+      const float sd = pooled[b * 2 * C + C + c];
+      gm[i] = gpool[b * 2 * C + c] / (float)T;
+      gs[i] = var_raw[b * C + c] > clip_min ? gpool[b * 2 * C + C + c] / ((float)T * sd) : 0.0f;
+    } else {
+      mean[i] = gm[i] = gs[i] = 0.0f;
+    }
+  }
+  if (active) {
+    const uint4* src = reinterpret_cast<const uint4*>(y + b * rows_per_utt * (long long)pitch) + cv;
+    uint4* dst = reinterpret_cast<uint4*>(dz + b * rows_per_utt * (long long)pitch) + cv;
+    for (int t = tl; t < T; t += 8) {
+      float f[8], g[8];
+      unpack_bf16x8(src[(long long)t * p8], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g[i] = f[i] > 0.0f ? fmaf(gs[i], f[i] - mean[i], gm[i]) : 0.0f;
+        acc[i] += g[i];
+      }
+      dst[(long long)t * p8] = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
+    }
+  }
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[tl][lane][i] = acc[i];
+  }
+  __syncthreads();
+  if (tl == 0 && active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      if (c >= C) break;
+      if (dbias != nullptr) {
+        float a = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += red[j][lane][i];
+        atomicAdd(dbias + c, a);
+      }
+      if (zero_gpool) {
+        gpool[b * 2 * C + c] = 0.0f;
+        gpool[b * 2 * C + C + c] = 0.0f;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// finishing pass of a split-K dense layer: acc (fp32, atomically accumulated by the GEMM) -> + bias, ReLU, ReLU-backward
+// mask, bf16 hi/lo and/or fp32 outputs, column sums (bias gradient of the layer below); re-zeroes acc for its next use
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dense_finish_kernel(float* __restrict__ acc, long long M, int N, int ld_acc,
+                                                          const float* __restrict__ bias, int relu,
+                                                          const bf16* __restrict__ mask_src, int ld_mask,
+                                                          bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int ld_out,
+                                                          float* __restrict__ out_f32, int ld_f32,
+                                                          float* __restrict__ colsum, int zero_acc) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + cl;
+  float cs = 0.0f;
+  if (n < N) {
+    const float bv = bias ? __ldg(bias + n) : 0.0f;
+    for (long long r = (long long)blockIdx.y * 64 + rl; r < M && r < (long long)(blockIdx.y + 1) * 64; r += 8) {
+      float x = acc[r * ld_acc + n] + bv;
+      if (zero_acc) acc[r * ld_acc + n] = 0.0f;
+      if (relu) x = fmaxf(x, 0.0f);
+      if (mask_src && !(__bfloat162float(mask_src[r * ld_mask + n]) > 0.0f)) x = 0.0f;
+      cs += x;
+      if (out_f32) out_f32[r * ld_f32 + n] = x;
+      if (out_hi) {
+        const bf16 h = __float2bfloat16_rn(x);
+        out_hi[r * ld_out + n] = h;
+        if (out_lo) out_lo[r * ld_out + n] = __float2bfloat16_rn(x - __bfloat162float(h));
+      }
+    }
+  }
+  if (colsum != nullptr) {
+    red[rl][cl] = cs;
+    __syncthreads();
+    if (rl == 0 && n < N) {
+#pragma unroll
+      for (int i = 1; i < 8; ++i) cs += red[i][cl];
+      atomicAdd(colsum + n, cs);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fused optimizer step: Adam on the fp32 master copy + refresh of both bf16 operand copies + gradient reset
+// ------------------------------------------------------------------------------------------------------------
+struct AdamLayersDev {
+  int n_layers;
+  int tile_start[LBX_MAX_LAYERS + 1];    // prefix sums of 32x32 weight tiles
+  int bias_start[LBX_MAX_LAYERS + 1];    // prefix sums of 256-wide bias blocks (offset by total weight tiles)
+  long long w_off[LBX_MAX_LAYERS], b_off[LBX_MAX_LAYERS];
+  int K[LBX_MAX_LAYERS], N[LBX_MAX_LAYERS], ldw[LBX_MAX_LAYERS], ldt[LBX_MAX_LAYERS];
+  bf16* W[LBX_MAX_LAYERS];
+  bf16* Wt[LBX_MAX_LAYERS];
+};
+
+__global__ void __launch_bounds__(256) adam_refresh_kernel(const AdamLayersDev L, float* __restrict__ p,
+                                                          float* __restrict__ g, float* __restrict__ m,
+                                                          float* __restrict__ v, const float* __restrict__ lr_t_ptr,
+                                                          float beta1, float beta2, float eps, float grad_scale,
+                                                          int zero_grads) {
+  __shared__ float tile[32][33];
+  const float lr_t = *lr_t_ptr;
+  const int blk = blockIdx.x;
+  const int total_w = L.tile_start[L.n_layers];
+  auto update = [&](long long i) -> float {
+    const float gi = g[i] * grad_scale;
+    if (zero_grads) g[i] = 0.0f;
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    p[i] = pi;
+    return pi;
+  };
+  if (blk < total_w) {
+    int l = 0;
+    while (blk >= L.tile_start[l + 1]) ++l;
+    const int K = L.K[l], N = L.N[l];
+    const int tiles_n = (N + 31) >> 5;
+    const int t = blk - L.tile_start[l];
+    const int k0 = (t / tiles_n) * 32, n0 = (t % tiles_n) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+      const int k = k0 + i, n = n0 + tx;
+      float val = 0.0f;
+      if (k < K && n < N) {
+        val = update(L.w_off[l] + (long long)k * N + n);
+        L.W[l][(long long)k * L.ldw[l] + n] = __float2bfloat16_rn(val);
+      }
+      tile[i][tx] = val;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int n = n0 + i, k = k0 + tx;
+      if (n < N && k < K) L.Wt[l][(long long)n * L.ldt[l] + k] = __float2bfloat16_rn(tile[tx][i]);
+    }
+  } else {
+    const int bb = blk - total_w;
+    int l = 0;
+    while (bb >= L.bias_start[l + 1]) ++l;
+    const int n = (bb - L.bias_start[l]) * 256 + threadIdx.x;
+    if (n < L.N[l]) update(L.b_off[l] + n);
+  }
+}
+
 static inline int grid_for(long long n, int block, int cap = 148 * 16) {
   long long g = ceil_div(n, block);
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
@@ -347,6 +611,9 @@ int lbx_stats_pool_fwd(const void* y, int y_dtype, long long B, int rows_per_utt
     stats_pool_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)y, rows_per_utt, T, C, pitch,
                                                                          clip_min, out, var_raw, (bf16*)out_hi,
                                                                          (bf16*)out_lo);
+  else if (y_dtype == LBX_BF16 && out_lo == nullptr && pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
+    stats_pool_fwd_bf16v_kernel<<<dim3((unsigned)ceil_div(pitch / 8, 32), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)y, rows_per_utt, T, C, pitch, clip_min, out, var_raw, (bf16*)out_hi);
   else if (y_dtype == LBX_BF16)
     stats_pool_fwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, rows_per_utt, T, C, pitch,
                                                                         clip_min, out, var_raw, (bf16*)out_hi,
@@ -358,33 +625,38 @@ int lbx_stats_pool_fwd(const void* y, int y_dtype, long long B, int rows_per_utt
 }
 
 int lbx_stats_pool_bwd(const void* y_bf16, long long B, int rows_per_utt, int T, int C, int pitch, float clip_min,
-                       const float* pooled, const float* var_raw, const float* gpool, void* dz_bf16, void* stream) {
+                       const float* pooled, const float* var_raw, float* gpool, void* dz_bf16, float* dbias,
+                       int zero_gpool, void* stream) {
   LBX_CHECK_ARG(B >= 0 && T >= 1 && C >= 1 && pitch >= C && rows_per_utt >= T && B <= 65535, "bad pooling shape");
+  LBX_CHECK_ARG(pitch % 8 == 0, "pitch must be a multiple of 8");
   if (B == 0) return LBX_OK;
   LBX_CHECK_ARG(y_bf16 && pooled && var_raw && gpool && dz_bf16, "NULL pointer argument");
-  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)B);
-  stats_pool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y_bf16, rows_per_utt, T, C, pitch, clip_min,
-                                                                pooled, var_raw, gpool, (bf16*)dz_bf16);
+  LBX_CHECK_ARG(((reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(dz_bf16)) & 15) == 0,
+                "activation buffers must be 16-byte aligned");
+  dim3 grid((unsigned)ceil_div(pitch / 8, 32), (unsigned)B);
+  stats_pool_bwd_bf16v_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y_bf16, rows_per_utt, T, C, pitch,
+                                                                      clip_min, pooled, var_raw, gpool, (bf16*)dz_bf16,
+                                                                      dbias, zero_gpool);
   LBX_LAUNCH_CHECK();
   return LBX_OK;
 }
 
 int lbx_logsoftmax_xent(const float* logits, const int* labels, long long B, int n, float* logp, float* loss,
-                        void* dlogits_bf16, int dl_pitch, float grad_scale, void* stream) {
+                        void* dlogits_bf16, int dl_pitch, float grad_scale, float* dbias, void* stream) {
   LBX_CHECK_ARG(B >= 0 && n >= 1, "bad shape");
   if (B == 0) return LBX_OK;
   LBX_CHECK_ARG(logits, "NULL logits");
   LBX_CHECK_ARG(!(loss || dlogits_bf16) || labels, "labels are required for the loss / gradient");
   LBX_CHECK_ARG(!dlogits_bf16 || dl_pitch >= n, "dl_pitch too small");
   logsoftmax_xent_kernel<<<(unsigned)ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(
-      logits, labels, B, n, logp, loss, (bf16*)dlogits_bf16, dl_pitch, grad_scale);
+      logits, labels, B, n, logp, loss, (bf16*)dlogits_bf16, dl_pitch, grad_scale, dbias);
   LBX_LAUNCH_CHECK();
   return LBX_OK;
 }
 
 int lbx_ap_loss(const float* h, const int* labels, long long B, int D, int N, float delta_weight, int normalize,
                 float* z_out, float* theta_out, float* loss, float* grad_f32, void* grad_bf16, int g_pitch,
-                const float* gloss, float grad_scale, void* stream) {
+                const float* gloss, float grad_scale, float* dbias, void* stream) {
   LBX_CHECK_ARG(N >= 1, "Must have at least 1 class");                                       /* losses.py:14 */
   LBX_CHECK_ARG(D >= N, "Language vector dimension cannot be less than number of classes");  /* losses.py:15 */
   LBX_CHECK_ARG(delta_weight > 0.0f, "delta_weight must be positive");                       /* losses.py:16 */
@@ -395,7 +667,7 @@ int lbx_ap_loss(const float* h, const int* labels, long long B, int D, int N, fl
   ap_loss_kernel<<<(unsigned)ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(h, labels, B, D, N, delta_weight, normalize,
                                                                              z_out, theta_out, loss, grad_f32,
                                                                              (bf16*)grad_bf16, g_pitch, gloss,
-                                                                             grad_scale);
+                                                                             grad_scale, dbias);
   LBX_LAUNCH_CHECK();
   return LBX_OK;
 }
@@ -421,6 +693,48 @@ int lbx_adam_step(float* params, const float* grads, float* m, float* v, long lo
   LBX_LAUNCH_CHECK();
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr_t_dev, beta1, beta2, eps,
                                                                   grad_scale);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_dense_finish(float* acc, long long M, int N, int ld_acc, const float* bias, int relu, const void* mask_src,
+                     int ld_mask, void* out_hi, void* out_lo, int ld_out, float* out_f32, int ld_f32, float* colsum,
+                     int zero_acc, void* stream) {
+  LBX_CHECK_ARG(M >= 0 && N >= 1 && ld_acc >= N, "bad shape");
+  if (M == 0) return LBX_OK;
+  LBX_CHECK_ARG(acc != nullptr, "NULL accumulator");
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 64));
+  dense_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc, M, N, ld_acc, bias, relu, (const bf16*)mask_src,
+                                                              ld_mask, (bf16*)out_hi, (bf16*)out_lo, ld_out, out_f32,
+                                                              ld_f32, colsum, zero_acc);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_adam_refresh(const lbx_adam_layers_t* layers, float* params, float* grads, float* m, float* v, float lr,
+                     float beta1, float beta2, float eps, long long* step_dev, float* lr_t_dev, float grad_scale,
+                     int zero_grads, void* stream) {
+  LBX_CHECK_ARG(layers && layers->n_layers >= 1 && layers->n_layers <= LBX_MAX_LAYERS, "bad layer table");
+  LBX_CHECK_ARG(params && grads && m && v && step_dev && lr_t_dev, "NULL pointer argument");
+  AdamLayersDev L{};
+  L.n_layers = layers->n_layers;
+  int tiles = 0, bias_blocks = 0;
+  for (int l = 0; l < L.n_layers; ++l) {
+    LBX_CHECK_ARG(layers->K[l] >= 1 && layers->N[l] >= 1 && layers->W[l] && layers->Wt[l], "bad layer %d", l);
+    L.tile_start[l] = tiles;
+    L.bias_start[l] = bias_blocks;
+    tiles += (int)(ceil_div(layers->K[l], 32) * ceil_div(layers->N[l], 32));
+    bias_blocks += (int)ceil_div(layers->N[l], 256);
+    L.w_off[l] = layers->w_off[l]; L.b_off[l] = layers->b_off[l];
+    L.K[l] = layers->K[l]; L.N[l] = layers->N[l]; L.ldw[l] = layers->ldw[l]; L.ldt[l] = layers->ldt[l];
+    L.W[l] = (bf16*)layers->W[l]; L.Wt[l] = (bf16*)layers->Wt[l];
+  }
+  L.tile_start[L.n_layers] = tiles;
+  L.bias_start[L.n_layers] = bias_blocks;
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, lr_t_dev, lr, beta1, beta2);
+  LBX_LAUNCH_CHECK();
+  adam_refresh_kernel<<<tiles + bias_blocks, 256, 0, (cudaStream_t)stream>>>(L, params, grads, m, v, lr_t_dev, beta1,
+                                                                            beta2, eps, grad_scale, zero_grads);
   LBX_LAUNCH_CHECK();
   return LBX_OK;
 }

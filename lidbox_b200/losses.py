@@ -23,7 +23,7 @@ def _ap_launch(z, y, N, w, want_theta, want_loss, gloss):
     loss = torch.empty((B,), dtype=torch.float32, device=z.device) if want_loss else None
     grad = torch.empty((B, D), dtype=torch.float32, device=z.device) if gloss is not None else None
     _lib.check(lib.lbx_ap_loss(_lib.ptr(z), _lib.ptr(y), B, D, N, float(w), 0, None, _lib.ptr(theta), _lib.ptr(loss),
-                               _lib.ptr(grad), None, D, _lib.ptr(gloss), 1.0, st))
+                               _lib.ptr(grad), None, D, _lib.ptr(gloss), 1.0, None, st))
     return theta, loss, grad
 
 

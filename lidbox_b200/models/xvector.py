@@ -118,6 +118,8 @@ class XVector:
         self._build_params(seed)
         self._bufs = {}
         self._adam = None
+        self._adam_layers = None
+        self._grads_clean = True
 
     # ------------------------------------------------------------------ parameters
     def _build_params(self, seed):
@@ -244,6 +246,8 @@ class XVector:
                     H=[], H_lo=[], emb=torch.zeros((B, self.segments[0].units), dtype=torch.float32, device=dev),
                     logits=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev),
                     out=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev))
+        widest = max([2 * cn, self.num_outputs] + [sgm.units for sgm in self.segments])
+        bufs["acc"] = torch.zeros((B, widest), dtype=torch.float32, device=dev)   # split-K accumulator (kept zeroed)
         for sgm in self.segments:
             bufs["H"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev))
             bufs["H_lo"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev) if split else None)
@@ -300,17 +304,27 @@ class XVector:
         for i, sgm in enumerate(self.segments):
             ly = self.layers[n + i]
             if i == 0 and upto_embedding:
-                ops.gemm(a, B, ly["K"], ly["K"], ly["Wt"], ly["N"], ly["K"], ly["ldt"], bufs["emb"], ly["N"], a_lo=a_lo,
-                         b_lo=ly["Wt_lo"] if split else None, bias=self._b_view(ly), relu=False)
+                self._dense(bufs, a, a_lo, B, ly, relu=False, out_f32=bufs["emb"])
                 return bufs["emb"]
-            ops.gemm(a, B, ly["K"], ly["K"], ly["Wt"], ly["N"], ly["K"], ly["ldt"], bufs["H"][i], ly["N"], a_lo=a_lo,
-                     b_lo=ly["Wt_lo"] if split else None, out_lo=bufs["H_lo"][i], bias=self._b_view(ly),
-                     relu=ly["relu"])
+            self._dense(bufs, a, a_lo, B, ly, relu=ly["relu"], out_hi=bufs["H"][i], out_lo=bufs["H_lo"][i])
             a, a_lo = bufs["H"][i], bufs["H_lo"][i]
         ly = self.layers[-1]
-        ops.gemm(a, B, ly["K"], ly["K"], ly["Wt"], ly["N"], ly["K"], ly["ldt"], bufs["logits"], ly["N"], a_lo=a_lo,
-                 b_lo=ly["Wt_lo"] if split else None, bias=self._b_view(ly), relu=False)
+        self._dense(bufs, a, a_lo, B, ly, relu=False, out_f32=bufs["logits"])
         return bufs["logits"]
+
+    def _dense(self, bufs, a, a_lo, B, ly, relu, out_hi=None, out_lo=None, out_f32=None):
+        """Dense layer for a small number of rows: split-K tcgen05 GEMM accumulating atomically into a zeroed fp32
+        buffer (so that more than a handful of SMs work on it), then one finishing pass (bias, ReLU, bf16 split)."""
+        split = self.precision == "fp32"
+        acc = bufs["acc"]
+        ld = acc.shape[1]
+        tiles = -(-B // 128) * -(-ly["N"] // 256)
+        ks = max(1, min(-(-ly["K"] // 64), 148 // tiles))
+        ops.gemm(a, B, ly["K"], ly["K"], ly["Wt"], ly["N"], ly["K"], ly["ldt"], acc, ld, a_lo=a_lo,
+                 b_lo=ly["Wt_lo"] if split else None, k_splits=ks, epi_atomic=True)
+        _lib.check(_lib.lib().lbx_dense_finish(_lib.ptr(acc), B, ly["N"], ld, _lib.ptr(self._b_view(ly)), int(relu), None,
+                                               0, _lib.ptr(out_hi), _lib.ptr(out_lo), ly["N"], _lib.ptr(out_f32),
+                                               ly["N"], None, 1, _lib.stream_ptr(self.device)))
 
     def __call__(self, x, training=False):
         x = self._prepare_input(x)
@@ -324,10 +338,10 @@ class XVector:
             dummy = torch.zeros(B, dtype=torch.int32, device=self.device)
             z = torch.empty_like(logits)
             _lib.check(lib.lbx_ap_loss(_lib.ptr(logits), _lib.ptr(dummy), B, self.num_outputs, 1, 1.0, 1, _lib.ptr(z),
-                                       None, None, None, None, 0, None, 1.0, st))
+                                       None, None, None, None, 0, None, 1.0, None, st))
             return z
         _lib.check(lib.lbx_logsoftmax_xent(_lib.ptr(logits), None, B, self.num_outputs, _lib.ptr(bufs["out"]), None,
-                                           None, 0, 1.0, st))
+                                           None, 0, 1.0, None, st))
         return bufs["out"].clone()
 
     predict = __call__
@@ -357,43 +371,58 @@ class XVector:
         logits = self._forward(x, bufs, True)
         scale = 1.0 / float(global_batch or B)
         npad = bufs["dlogits"].shape[1]
+        if not self._grads_clean:
+            self.grads.zero_()
+        self._grads_clean = False
+        g = self.grads
+        out_ly = self.layers[-1]
         if loss == "xent":
             _lib.check(lib.lbx_logsoftmax_xent(_lib.ptr(logits), _lib.ptr(y), B, self.num_outputs, None,
-                                               _lib.ptr(bufs["loss"]), _lib.ptr(bufs["dlogits"]), npad, scale, st))
+                                               _lib.ptr(bufs["loss"]), _lib.ptr(bufs["dlogits"]), npad, scale,
+                                               ops._addr(g, out_ly["b_off"]), st))
         elif loss == "ap":
             N = int(ap_classes or self.num_outputs)
             _lib.check(lib.lbx_ap_loss(_lib.ptr(logits), _lib.ptr(y), B, self.num_outputs, N, float(delta_weight), 1,
                                        _lib.ptr(bufs["z"]), None, _lib.ptr(bufs["loss"]), None,
-                                       _lib.ptr(bufs["dlogits"]), npad, None, scale, st))
+                                       _lib.ptr(bufs["dlogits"]), npad, None, scale, ops._addr(g, out_ly["b_off"]),
+                                       st))
         else:
             raise ValueError("loss must be 'xent' or 'ap'")
-        self.grads.zero_()
-        g = self.grads
 
         def wgrad(a, a_rows, a_cols, lda, dz, dz_cols, dz_pitch, ly, a_off=0, dz_off=0):
             tiles = -(-a_cols // 128) * -(-dz_cols // 256)
             ks = max(1, min(-(-a_rows // 64), 148 // tiles))
             ops.gemm(a, a_rows, a_cols, lda, dz, a_rows, dz_cols, dz_pitch, g, ly["N"], layout=1, a_off=a_off,
                      b_off=dz_off, out_off=ly["w_off"], k_splits=ks, epi_atomic=True)
-            _lib.check(lib.lbx_colsum_bf16(ops._addr(dz, dz_off), a_rows, dz_cols, dz_pitch,
-                                           ops._addr(g, ly["b_off"]), st))
 
-        # ---- dense head ----
+        # ---- dense head (bias gradients come fused out of the kernels that produce each dz) ----
         dz, dz_cols, dz_pitch = bufs["dlogits"], self.num_outputs, npad
         acts = [bufs["pooled_hi"]] + bufs["H"]
+        acc = bufs["acc"]
+        ld_acc = acc.shape[1]
         for i in range(len(self.segments), -1, -1):
             ly = self.layers[n + i]
             wgrad(acts[i], B, ly["K"], ly["K"], dz, dz_cols, dz_pitch, ly)
-            if i > 0:      # d hidden = dz . W^T, masked by the ReLU of the layer below
-                ops.gemm(dz, B, dz_cols, dz_pitch, ly["W"], ly["K"], ly["N"], ly["ldw"], bufs["dH"][i - 1], ly["K"],
-                         mask_src=bufs["H"][i - 1] if self.layers[n + i - 1]["relu"] else None)
+            tiles = -(-B // 128) * -(-ly["K"] // 256)
+            ks = max(1, min(-(-dz_cols // 64), 148 // tiles))
+            if i > 0:      # d hidden = (dz . W^T) masked by the ReLU of the layer below; split-K + finishing pass
+                below = self.layers[n + i - 1]
+                ops.gemm(dz, B, dz_cols, dz_pitch, ly["W"], ly["K"], ly["N"], ly["ldw"], acc, ld_acc, k_splits=ks,
+                         epi_atomic=True)
+                _lib.check(lib.lbx_dense_finish(_lib.ptr(acc), B, ly["K"], ld_acc, None, 0,
+                                                _lib.ptr(bufs["H"][i - 1]) if below["relu"] else None, ly["K"],
+                                                _lib.ptr(bufs["dH"][i - 1]), None, ly["K"], None, 0,
+                                                ops._addr(g, below["b_off"]), 1, st))
                 dz, dz_cols, dz_pitch = bufs["dH"][i - 1], ly["K"], ly["K"]
-            else:          # d pooled (fp32, no mask)
-                ops.gemm(dz, B, dz_cols, dz_pitch, ly["W"], ly["K"], ly["N"], ly["ldw"], bufs["gpool"], ly["K"])
-        # ---- statistics pooling (+ ReLU mask of the last frame layer) ----
+            else:          # d pooled (fp32, no mask): accumulated atomically into gpool, which pool_bwd re-zeroes
+                ops.gemm(dz, B, dz_cols, dz_pitch, ly["W"], ly["K"], ly["N"], ly["ldw"], bufs["gpool"], ly["K"],
+                         k_splits=ks, epi_atomic=True)
+        # ---- statistics pooling (+ ReLU mask and bias gradient of the last frame layer) ----
+        last = self.layers[n - 1]
         _lib.check(lib.lbx_stats_pool_bwd(_lib.ptr(bufs["Y"]), B, geo.R[n - 1], geo.T[n], bufs["cn"], bufs["cnp"],
                                           STDDEV_SQRT_MIN_CLIP, _lib.ptr(bufs["pooled"]), _lib.ptr(bufs["var_raw"]),
-                                          _lib.ptr(bufs["gpool"]), _lib.ptr(bufs["dZ"][n - 1]), st))
+                                          _lib.ptr(bufs["gpool"]), _lib.ptr(bufs["dZ"][n - 1]),
+                                          ops._addr(g, last["b_off"]), 1, st))
         # ---- frame layers, last to first ----
         for L in range(n - 1, -1, -1):
             ly = self.layers[L]
@@ -405,32 +434,46 @@ class XVector:
             if L == 0:
                 break
             # data gradient through the same overlapping view, masked by the ReLU of layer L-1 (= X[L] > 0; padding
-            # and junk rows of X[L] are zero, so they stay zero in dZ[L-1])
+            # and junk rows of X[L] are zero, so they stay zero in dZ[L-1]); the column sums of what is written are
+            # the bias gradient of layer L-1 (column n of the view is channel n mod C_in)
             k, s, c = ly["k"], ly["s"], ly["c_in"]
-            if not self.layers[L - 1]["relu"]:
+            below = self.layers[L - 1]
+            if not below["relu"]:
                 raise NotImplementedError("linear frame layers are not supported in the backward pass")
             first = min(k, s)                        # taps [0, first) tile the time axis without overlap
             ops.gemm(dZ, rows, ly["N"], dz_pitch, ly["W"], first * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
-                     a_off=dz_off, mask_src=bufs["X"][L])
+                     a_off=dz_off, mask_src=bufs["X"][L], colsum=g, colsum_off=below["b_off"], colsum_mod=c)
             j = first
             while j < k:                             # remaining taps overlap the next row: accumulate pass(es)
                 cnt = min(s, k - j)
                 ops.gemm(dZ, rows, ly["N"], dz_pitch, ly["W"], cnt * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
                          a_off=dz_off, b_off=j * c * ly["ldw"], out_off=j * c, mask_src=bufs["X"][L], mask_off=j * c,
-                         accumulate=True)
+                         accumulate=True, colsum=g, colsum_off=below["b_off"], colsum_mod=c)
                 j += cnt
         return bufs["loss"]
 
     def apply_gradients(self, grad_scale=1.0):
+        """Fused Adam + bf16 operand refresh + gradient reset (one kernel over all layers)."""
         if self._adam is None:
             self.configure_optimizer()
         a = self._adam
-        _lib.check(_lib.lib().lbx_adam_step(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(a["m"]),
-                                            _lib.ptr(a["v"]), self.params.numel(), a["lr"], a["beta1"], a["beta2"],
-                                            a["eps"], _lib.ptr(a["step"]), _lib.ptr(a["lr_t"]), float(grad_scale),
-                                            _lib.stream_ptr(self.device)))
-        self._weights_dirty = self._lo_dirty = True
-        self._refresh(need_lo=False)
+        if self._adam_layers is None:
+            t = _lib.AdamLayers()
+            t.n_layers = len(self.layers)
+            for i, ly in enumerate(self.layers):
+                t.w_off[i], t.b_off[i] = ly["w_off"], ly["b_off"]
+                t.K[i], t.N[i], t.ldw[i], t.ldt[i] = ly["K"], ly["N"], ly["ldw"], ly["ldt"]
+                t.W[i], t.Wt[i] = ly["W"].data_ptr(), ly["Wt"].data_ptr()
+            self._adam_layers = t
+        import ctypes
+        _lib.check(_lib.lib().lbx_adam_refresh(ctypes.byref(self._adam_layers), _lib.ptr(self.params),
+                                               _lib.ptr(self.grads), _lib.ptr(a["m"]), _lib.ptr(a["v"]), a["lr"],
+                                               a["beta1"], a["beta2"], a["eps"], _lib.ptr(a["step"]),
+                                               _lib.ptr(a["lr_t"]), float(grad_scale), 1,
+                                               _lib.stream_ptr(self.device)))
+        self._grads_clean = True
+        self._weights_dirty = False        # hi planes were refreshed by the fused kernel
+        self._lo_dirty = True
 
     def train_step(self, x, y, loss="xent", process_group=None, **kw):
         """One optimisation step; with a process group the flat fp32 gradient is sum-all-reduced over NCCL first."""

@@ -21,7 +21,7 @@ def _addr(t, offset_elems=0):
 
 def gemm(a, a_rows, a_cols, lda, b, b_rows, b_cols, ldb, out, ldo, *, layout=0, a_lo=None, b_lo=None, out_lo=None,
          a_off=0, b_off=0, out_off=0, k_splits=1, epi_atomic=False, bias=None, relu=False, rows_per_utt=0,
-         valid_rows=0, mask_src=None, mask_off=0, accumulate=False, tile_n=0):
+         valid_rows=0, mask_src=None, mask_off=0, accumulate=False, tile_n=0, colsum=None, colsum_off=0, colsum_mod=0):
     """lbx_gemm_bf16: see lbx_gemm_t.  `a`, `b` are bf16 buffers; offsets are in elements from their data_ptr."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     d = _lib.GemmDesc()
@@ -42,6 +42,7 @@ def gemm(a, a_rows, a_cols, lda, b, b_rows, b_cols, ldb, out, ldo, *, layout=0, 
     d.mask_src = _addr(mask_src, mask_off)
     d.accumulate = int(accumulate)
     d.tile_n = tile_n
+    d.colsum, d.colsum_mod = _addr(colsum, colsum_off), colsum_mod
     if GEMM_TIMER is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -107,6 +107,8 @@ int lbx_logmel_f32_host(const float* sig_host, long long B, long long N, int sam
 /* One bf16 tensor-core GEMM (tcgen05, fp32 accumulation in TMEM) with a fused epilogue.
  *   layout 0 (NT):  C[M,N] = A[M,K] . B[N,K]^T   M = a_rows, K = a_cols = b_cols, N = b_rows
  *   layout 1 (TN):  C[M,N] = A[K,M]^T . B[K,N]   K = a_rows = b_rows, M = a_cols, N = b_cols
+ *   layout 2 (NN):  C[M,N] = A[M,K] . B[K,N]     M = a_rows, K = a_cols = b_rows, N = b_cols (forward pass straight from
+ *                                                the Keras-layout weight [k*C_in, C_out]: no transposed copy is kept)
  * A/B are bf16 views: `rows` x `cols` with row pitch ld (elements, multiple of 8; may be SMALLER than cols: a causal
  * Conv1D with kernel k and stride s over NWC activations is the NT GEMM whose A view has cols = k*C_in and
  * lda = s*C_in on the zero-left-padded activation buffer — no im2col).
@@ -137,6 +139,8 @@ typedef struct lbx_gemm_t {
   int colsum_mod;
 } lbx_gemm_t;
 int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream);
+/* GEMMs are launched with programmatic dependent launch (prologue overlaps the previous kernel's tail); 0 disables. */
+int lbx_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------------------------------------------------
  * TDNN non-GEMM stages and losses
@@ -182,9 +186,12 @@ int lbx_colsum_bf16(const void* x, long long rows, int n, int pitch, float* out,
 
 /* Keras-compatible Adam on flat fp32 buffers: g' = g * grad_scale; m,v updates;
  * p -= lr * sqrt(1-beta2^t)/(1-beta1^t) * m / (sqrt(v) + eps).  The step counter t (*step_dev, incremented by the
- * call) and the bias-corrected rate (*lr_t_dev) live in device memory so the call can be replayed from a CUDA graph. */
-int lbx_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                  float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* stream);
+ * call) and the bias-corrected rate (*lr_t_dev) live in device memory so the call can be replayed from a CUDA graph.
+ * n must be a multiple of 4 and the buffers 16-byte aligned (vectorised). */
+int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, long long* step_dev, float* lr_t_dev, float grad_scale,
+                  void* params_bf16 /* optional: bf16 operand copy of the flat buffer, refreshed in the same pass */,
+                  int zero_grads /* reset the gradient buffer after it has been consumed */, void* stream);
 
 /* Finishing pass of a split-K Dense layer (lbx_gemm_bf16 with epi_atomic into the fp32 accumulator `acc`):
  * x = acc + bias; ReLU; zero unless mask_src > 0; outputs as bf16 hi (+ lo residual) and/or fp32; colsum[n] += sum_m x;
@@ -193,23 +200,9 @@ int lbx_dense_finish(float* acc, long long M, int N, int ld_acc, const float* bi
                      int ld_mask, void* out_hi, void* out_lo, int ld_out, float* out_f32, int ld_f32, float* colsum,
                      int zero_acc, void* stream);
 
-/* Fused optimizer step over all layers: Adam (as lbx_adam_step) on the flat fp32 buffers + refresh of the bf16
- * operand copies W [K, ldw] and W^T [N, ldt] of every layer + optional reset of the gradient buffer. */
-#define LBX_MAX_LAYERS 16
-typedef struct lbx_adam_layers_t {
-  int n_layers;
-  long long w_off[LBX_MAX_LAYERS]; long long b_off[LBX_MAX_LAYERS];   /* element offsets into the flat buffers */
-  int K[LBX_MAX_LAYERS]; int N[LBX_MAX_LAYERS]; int ldw[LBX_MAX_LAYERS]; int ldt[LBX_MAX_LAYERS];
-  void* W[LBX_MAX_LAYERS]; void* Wt[LBX_MAX_LAYERS];                   /* bf16 device buffers */
-} lbx_adam_layers_t;
-int lbx_adam_refresh(const lbx_adam_layers_t* layers, float* params, float* grads, float* m, float* v, float lr,
-                     float beta1, float beta2, float eps, long long* step_dev, float* lr_t_dev, float grad_scale,
-                     int zero_grads, void* stream);
-
-/* fp32 master weight [K, N] (Keras kernel flattened) -> bf16 operand copies: W [K, ldw] (data-gradient operand) and
- * W^T [N, ldt] (forward operand), each as hi (+ lo residual) planes; any of w_hi / t_hi may be NULL. */
-int lbx_refresh_weights(const float* w, int K, int N, void* w_hi, void* w_lo, int ldw, void* t_hi, void* t_lo, int ldt,
-                        void* stream);
+/* fp32 -> bf16 operand planes of the flat parameter buffer: hi = bf16(x), lo = bf16(x - hi) (lo optional; it feeds
+ * the bf16x3 forward mode).  The buffers keep the Keras layouts ([k*C_in, C_out] per kernel, pitch padded to 8). */
+int lbx_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream);
 
 #ifdef __cplusplus
 }

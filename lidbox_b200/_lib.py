@@ -25,16 +25,6 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
-MAX_LAYERS = 16
-
-
-class AdamLayers(ctypes.Structure):
-    """lbx_adam_layers_t (include/lidbox_b200.h)."""
-    _fields_ = [("n_layers", c_int), ("w_off", c_ll * MAX_LAYERS), ("b_off", c_ll * MAX_LAYERS),
-                ("K", c_int * MAX_LAYERS), ("N", c_int * MAX_LAYERS), ("ldw", c_int * MAX_LAYERS),
-                ("ldt", c_int * MAX_LAYERS), ("W", c_void_p * MAX_LAYERS), ("Wt", c_void_p * MAX_LAYERS)]
-
-
 # name -> (restype, argtypes); must list every symbol include/lidbox_b200.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
     "lbx_last_error": (ctypes.c_char_p, []),
@@ -52,17 +42,16 @@ SIGNATURES = {
     "lbx_power_to_db_f32": (c_int, [_P, c_ll, c_float, c_float, _P, _P, _P]),
     "lbx_check_finite_f32": (c_int, [_P, c_ll, _P, _P]),
     "lbx_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), _P]),
+    "lbx_set_pdl": (c_int, [c_int]),
     "lbx_pack_rows_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, _P]),
     "lbx_stats_pool_fwd": (c_int, [_P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
     "lbx_stats_pool_bwd": (c_int, [_P, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_int, _P]),
     "lbx_dense_finish": (c_int, [_P, c_ll, c_int, c_int, _P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, _P, c_int, _P]),
-    "lbx_adam_refresh": (c_int, [ctypes.POINTER(AdamLayers), _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P,
-                                 _P, c_float, c_int, _P]),
     "lbx_logsoftmax_xent": (c_int, [_P, _P, c_ll, c_int, _P, _P, _P, c_int, c_float, _P, _P]),
     "lbx_ap_loss": (c_int, [_P, _P, c_ll, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_int, _P, c_float, _P, _P]),
     "lbx_colsum_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P]),
-    "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P]),
-    "lbx_refresh_weights": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P]),
+    "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P, c_int, _P]),
+    "lbx_split_bf16": (c_int, [_P, c_ll, _P, _P, _P]),
     "lbx_logmel_f32_host": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_float,
                                     c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),
 }
@@ -87,6 +76,8 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = restype
             fn.argtypes = argtypes
+        if os.environ.get("LBX_PDL", "1") == "0":
+            handle.lbx_set_pdl(0)
         _lib = handle
     return _lib
 

@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                      const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                      const GemmParams p) {
   constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
+  constexpr bool A_MN = LAYOUT == 1;            // A stored [K, M] (contraction index is the slow one)
+  constexpr bool B_MN = LAYOUT != 0;            // B stored [K, N]
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
@@ -220,6 +222,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream;
+  // from here on global memory written by it is read (and memory it reads is overwritten)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -238,13 +244,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             unsigned char* sA = smem + (size_t)stage * STAGE_BYTES;
             unsigned char* sB = sA + A_BYTES;
             mbar_expect_tx(full_bar + stage, (uint32_t)STAGE_BYTES);
-            if (LAYOUT == 0) {
+            if (!A_MN) {
               tma_load_2d(mA, full_bar + stage, sA, kb * BK, m_blk * BM);
-              tma_load_2d(mB, full_bar + stage, sB, kb * BK, n_blk * BN);
             } else {
 #pragma unroll
               for (int i = 0; i < BM / 64; ++i)
                 tma_load_2d(mA, full_bar + stage, sA + i * 8192, m_blk * BM + i * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d(mB, full_bar + stage, sB, kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
               for (int i = 0; i < BN / 64; ++i)
                 tma_load_2d(mB, full_bar + stage, sB + i * 8192, n_blk * BN + i * 64, kb * BK);
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN>(LAYOUT, LAYOUT);
+      constexpr uint32_t idesc = make_idesc<BN>(A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -276,14 +285,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const uint32_t sB = sA + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            uint64_t da, db;
-            if (LAYOUT == 0) {   // K-major: 8-row groups are 1024 B apart; advance 32 B per UMMA_K inside the swizzle atom
-              da = make_smem_desc(sA + k * (UMMA_K * 2), 16, 1024);
-              db = make_smem_desc(sB + k * (UMMA_K * 2), 16, 1024);
-            } else {             // MN-major: 64-element blocks are 8192 B apart (LBO), 8 k-rows = 1024 B (SBO)
-              da = make_smem_desc(sA + k * (UMMA_K * 128), 8192, 1024);
-              db = make_smem_desc(sB + k * (UMMA_K * 128), 8192, 1024);
-            }
+            // K-major: 8-row groups are 1024 B apart; advance 32 B per UMMA_K inside the swizzle atom
+            // MN-major: 64-element blocks are 8192 B apart (LBO), 8 k-rows = 1024 B (SBO), 2048 B per UMMA_K
+            const uint64_t da = A_MN ? make_smem_desc(sA + k * (UMMA_K * 128), 8192, 1024)
+                                     : make_smem_desc(sA + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sB + k * (UMMA_K * 128), 8192, 1024)
+                                     : make_smem_desc(sB + k * (UMMA_K * 2), 16, 1024);
             tc_mma_bf16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit(empty_bar + stage);          // frees the smem stage when these MMAs retire
@@ -505,6 +512,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 }
 
 static int g_num_sms = 0;
+static int g_use_pdl = 1;
 
 }  // namespace lbx
 
@@ -512,7 +520,7 @@ using namespace lbx;
 
 extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   LBX_CHECK_ARG(g != nullptr, "NULL gemm descriptor");
-  LBX_CHECK_ARG(g->layout == 0 || g->layout == 1, "layout must be 0 (NT) or 1 (TN)");
+  LBX_CHECK_ARG(g->layout >= 0 && g->layout <= 2, "layout must be 0 (NT), 1 (TN) or 2 (NN)");
   LBX_CHECK_ARG(g->n_terms == 1 || g->n_terms == 3, "n_terms must be 1 or 3");
   LBX_CHECK_ARG(g->a_rows >= 0 && g->a_cols >= 0 && g->b_rows >= 0 && g->b_cols >= 0, "negative extent");
   GemmParams p{};
@@ -522,11 +530,16 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
                   g->b_cols);
     LBX_CHECK_ARG(g->a_rows <= 2147483647LL && g->b_rows <= 2147483647LL, "extent too large");
     p.M = (int)g->a_rows; p.N = (int)g->b_rows; p.K = g->a_cols;
-  } else {
+  } else if (g->layout == 1) {
     LBX_CHECK_ARG(g->a_rows == g->b_rows, "TN: A and B must share the contraction length (%lld vs %lld)", g->a_rows,
                   g->b_rows);
     LBX_CHECK_ARG(g->a_rows <= 2147483647LL, "extent too large");
     p.M = g->a_cols; p.N = g->b_cols; p.K = (int)g->a_rows;
+  } else {
+    LBX_CHECK_ARG((long long)g->a_cols == g->b_rows, "NN: A and B must share the contraction length (%d vs %lld)",
+                  g->a_cols, g->b_rows);
+    LBX_CHECK_ARG(g->a_rows <= 2147483647LL, "extent too large");
+    p.M = (int)g->a_rows; p.N = g->b_cols; p.K = g->a_cols;
   }
   if (p.M == 0 || p.N == 0) return LBX_OK;
   LBX_CHECK_ARG(p.K > 0, "empty contraction");
@@ -561,7 +574,7 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   int rc;
   // tile-N 256 unless the problem is narrower than 128 columns (measured: 128 never wins on the TDNN shapes)
   const int bn = (g->tile_n == 128 || g->tile_n == 256) ? g->tile_n : (p.N <= 128 ? 128 : 256);
-  const int boxA_rows = g->layout == 0 ? BM : 64, boxB_rows = g->layout == 0 ? bn : 64;
+  const int boxA_rows = g->layout == 1 ? 64 : BM, boxB_rows = g->layout == 0 ? bn : 64;
   if ((rc = make_map(&mA0, g->a0, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
   if ((rc = make_map(&mB0, g->b0, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
   if (g->n_terms == 3) {
@@ -574,23 +587,40 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
     int dev = 0, n = 0;
     LBX_CUDA(cudaGetDevice(&dev));
     LBX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::SMEM));
-    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::SMEM));
-    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM));
-    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM));
+#define LBX_SET_SMEM(L, N_) \
+  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<N_>::SMEM))
+    LBX_SET_SMEM(0, 256); LBX_SET_SMEM(1, 256); LBX_SET_SMEM(2, 256);
+    LBX_SET_SMEM(0, 128); LBX_SET_SMEM(1, 128); LBX_SET_SMEM(2, 128);
+#undef LBX_SET_SMEM
     g_num_sms = n;
   }
   const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.k_splits;
   const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (g->layout == 0 && bn == 256)
-    gemm_bf16_kernel<0, 256><<<grid, GEMM_THREADS, Cfg<256>::SMEM, st>>>(mA0, mA1, mB0, mB1, p);
-  else if (g->layout == 0)
-    gemm_bf16_kernel<0, 128><<<grid, GEMM_THREADS, Cfg<128>::SMEM, st>>>(mA0, mA1, mB0, mB1, p);
-  else if (bn == 256)
-    gemm_bf16_kernel<1, 256><<<grid, GEMM_THREADS, Cfg<256>::SMEM, st>>>(mA0, mA1, mB0, mB1, p);
-  else
-    gemm_bf16_kernel<1, 128><<<grid, GEMM_THREADS, Cfg<128>::SMEM, st>>>(mA0, mA1, mB0, mB1, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = bn == 256 ? Cfg<256>::SMEM : Cfg<128>::SMEM;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaError_t le;
+#define LBX_GEMM_LAUNCH(L, N_) le = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_>, mA0, mA1, mB0, mB1, p)
+  if (bn == 256) {
+    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 256); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 256); else LBX_GEMM_LAUNCH(2, 256);
+  } else {
+    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 128); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 128); else LBX_GEMM_LAUNCH(2, 128);
+  }
+#undef LBX_GEMM_LAUNCH
+  if (le != cudaSuccess) return set_error(LBX_ECUDA, "GEMM launch failed: %s", cudaGetErrorString(le));
   LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+// programmatic dependent launch for the GEMMs (on by default; LBX_PDL=0 in the environment disables it)
+extern "C" int lbx_set_pdl(int enabled) {
+  g_use_pdl = enabled ? 1 : 0;
   return LBX_OK;
 }

@@ -271,55 +271,46 @@ __global__ void adam_tick_kernel(long long* step, float* lr_t, float lr, float b
   *lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t)));
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                  float* __restrict__ m, float* __restrict__ v, long long n,
+// n4 = n / 4 float4 groups (the flat buffers are padded to a multiple of 4); optionally refreshes the bf16 operand
+// copy of the parameters (same flat layout) and resets the gradient for the next step
+__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                  float4* __restrict__ v, long long n4,
                                                   const float* __restrict__ lr_t_ptr, float beta1, float beta2,
-                                                  float eps, float grad_scale) {
+                                                  float eps, float grad_scale, uint2* __restrict__ p_bf16,
+                                                  int zero_grads) {
   const float lr_t = *lr_t_ptr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * grad_scale;
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
+    if (zero_grads) g[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#define LBX_ADAM1(c)                                        \
+    {                                                       \
+      const float gg = gi.c * grad_scale;                   \
+      mi.c = beta1 * mi.c + (1.0f - beta1) * gg;            \
+      vi.c = beta2 * vi.c + (1.0f - beta2) * gg * gg;       \
+      pi.c -= lr_t * mi.c / (sqrtf(vi.c) + eps);            \
+    }
+    LBX_ADAM1(x) LBX_ADAM1(y) LBX_ADAM1(z) LBX_ADAM1(w)
+#undef LBX_ADAM1
     m[i] = mi;
     v[i] = vi;
-    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
-  }
-}
-
-// fp32 master W [K, N] (Keras layout) -> bf16 W [K, ldw] and bf16 W^T [N, ldt], hi (+ lo residual) planes
-__global__ void __launch_bounds__(256) refresh_weights_kernel(const float* __restrict__ w, int K, int N,
-                                                             bf16* __restrict__ w_hi, bf16* __restrict__ w_lo, int ldw,
-                                                             bf16* __restrict__ t_hi, bf16* __restrict__ t_lo, int ldt) {
-  __shared__ float tile[32][33];
-  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
-    const int k = k0 + i, n = n0 + tx;
-    float v = 0.0f;
-    if (k < K && n < N) {
-      v = w[(long long)k * N + n];
-      if (w_hi) {
-        const bf16 h = __float2bfloat16_rn(v);
-        w_hi[(long long)k * ldw + n] = h;
-        if (w_lo) w_lo[(long long)k * ldw + n] = __float2bfloat16_rn(v - __bfloat162float(h));
-      }
-    }
-    tile[i][tx] = v;
-  }
-  __syncthreads();
-  if (t_hi) {
-    for (int i = ty; i < 32; i += 8) {
-      const int n = n0 + i, k = k0 + tx;
-      if (n < N && k < K) {
-        const float v = tile[tx][i];
-        const bf16 h = __float2bfloat16_rn(v);
-        t_hi[(long long)n * ldt + k] = h;
-        if (t_lo) t_lo[(long long)n * ldt + k] = __float2bfloat16_rn(v - __bfloat162float(h));
-      }
+    p[i] = pi;
+    if (p_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pi.x, pi.y), hi = __floats2bfloat162_rn(pi.z, pi.w);
+      p_bf16[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
     }
   }
 }
 
+// fp32 -> bf16 hi (+ lo residual) planes, elementwise (operand copies of the flat parameter buffer)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, long long n, bf16* __restrict__ hi,
+                                                        bf16* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const bf16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // vectorised bf16 pooling (training path): every thread owns 8 consecutive channels (one 16-byte load per row)
@@ -350,13 +341,15 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_bf16v_kernel(const bf16* _
   const uint4* base = reinterpret_cast<const uint4*>(y + b * rows_per_utt * (long long)pitch) + cv;
   const int p8 = pitch >> 3;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (active)
+  if (active) {
+#pragma unroll 4
     for (int t = tl; t < T; t += 8) {
       float f[8];
-      unpack_bf16x8(base[(long long)t * p8], f);
+      unpack_bf16x8(__ldg(base + (long long)t * p8), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] += f[i];
     }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[tl][lane][i] = s[i];
   __syncthreads();
@@ -370,16 +363,18 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_bf16v_kernel(const bf16* _
   }
   __syncthreads();
   float q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (active)
+  if (active) {
+#pragma unroll 4
     for (int t = tl; t < T; t += 8) {
       float f[8];
-      unpack_bf16x8(base[(long long)t * p8], f);
+      unpack_bf16x8(__ldg(base + (long long)t * p8), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float d = f[i] - mean[i];
         q[i] = fmaf(d, d, q[i]);
       }
     }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[tl][lane][i] = q[i];
   __syncthreads();
@@ -435,9 +430,10 @@ __global__ void __launch_bounds__(256) stats_pool_bwd_bf16v_kernel(const bf16* _
   if (active) {
     const uint4* src = reinterpret_cast<const uint4*>(y + b * rows_per_utt * (long long)pitch) + cv;
     uint4* dst = reinterpret_cast<uint4*>(dz + b * rows_per_utt * (long long)pitch) + cv;
+#pragma unroll 4
     for (int t = tl; t < T; t += 8) {
       float f[8], g[8];
-      unpack_bf16x8(src[(long long)t * p8], f);
+      unpack_bf16x8(__ldg(src + (long long)t * p8), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         g[i] = f[i] > 0.0f ? fmaf(gs[i], f[i] - mean[i], gm[i]) : 0.0f;
@@ -486,7 +482,7 @@ __global__ void __launch_bounds__(256) dense_finish_kernel(float* __restrict__ a
   float cs = 0.0f;
   if (n < N) {
     const float bv = bias ? __ldg(bias + n) : 0.0f;
-    for (long long r = (long long)blockIdx.y * 64 + rl; r < M && r < (long long)(blockIdx.y + 1) * 64; r += 8) {
+    for (long long r = (long long)blockIdx.y * 16 + rl; r < M && r < (long long)(blockIdx.y + 1) * 16; r += 8) {
       float x = acc[r * ld_acc + n] + bv;
       if (zero_acc) acc[r * ld_acc + n] = 0.0f;
       if (relu) x = fmaxf(x, 0.0f);
@@ -511,69 +507,6 @@ __global__ void __launch_bounds__(256) dense_finish_kernel(float* __restrict__ a
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// fused optimizer step: Adam on the fp32 master copy + refresh of both bf16 operand copies + gradient reset
-// ------------------------------------------------------------------------------------------------------------
-struct AdamLayersDev {
-  int n_layers;
-  int tile_start[LBX_MAX_LAYERS + 1];    // prefix sums of 32x32 weight tiles
-  int bias_start[LBX_MAX_LAYERS + 1];    // prefix sums of 256-wide bias blocks (offset by total weight tiles)
-  long long w_off[LBX_MAX_LAYERS], b_off[LBX_MAX_LAYERS];
-  int K[LBX_MAX_LAYERS], N[LBX_MAX_LAYERS], ldw[LBX_MAX_LAYERS], ldt[LBX_MAX_LAYERS];
-  bf16* W[LBX_MAX_LAYERS];
-  bf16* Wt[LBX_MAX_LAYERS];
-};
-
-__global__ void __launch_bounds__(256) adam_refresh_kernel(const AdamLayersDev L, float* __restrict__ p,
-                                                          float* __restrict__ g, float* __restrict__ m,
-                                                          float* __restrict__ v, const float* __restrict__ lr_t_ptr,
-                                                          float beta1, float beta2, float eps, float grad_scale,
-                                                          int zero_grads) {
-  __shared__ float tile[32][33];
-  const float lr_t = *lr_t_ptr;
-  const int blk = blockIdx.x;
-  const int total_w = L.tile_start[L.n_layers];
-  auto update = [&](long long i) -> float {
-    const float gi = g[i] * grad_scale;
-    if (zero_grads) g[i] = 0.0f;
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
-    p[i] = pi;
-    return pi;
-  };
-  if (blk < total_w) {
-    int l = 0;
-    while (blk >= L.tile_start[l + 1]) ++l;
-    const int K = L.K[l], N = L.N[l];
-    const int tiles_n = (N + 31) >> 5;
-    const int t = blk - L.tile_start[l];
-    const int k0 = (t / tiles_n) * 32, n0 = (t % tiles_n) * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8) {
-      const int k = k0 + i, n = n0 + tx;
-      float val = 0.0f;
-      if (k < K && n < N) {
-        val = update(L.w_off[l] + (long long)k * N + n);
-        L.W[l][(long long)k * L.ldw[l] + n] = __float2bfloat16_rn(val);
-      }
-      tile[i][tx] = val;
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-      const int n = n0 + i, k = k0 + tx;
-      if (n < N && k < K) L.Wt[l][(long long)n * L.ldt[l] + k] = __float2bfloat16_rn(tile[tx][i]);
-    }
-  } else {
-    const int bb = blk - total_w;
-    int l = 0;
-    while (bb >= L.bias_start[l + 1]) ++l;
-    const int n = (bb - L.bias_start[l]) * 256 + threadIdx.x;
-    if (n < L.N[l]) update(L.b_off[l] + n);
-  }
-}
 
 static inline int grid_for(long long n, int block, int cap = 148 * 16) {
   long long g = ceil_div(n, block);
@@ -684,15 +617,21 @@ int lbx_colsum_bf16(const void* x, long long rows, int n, int pitch, float* out,
   return LBX_OK;
 }
 
-int lbx_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                  float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* stream) {
-  LBX_CHECK_ARG(n >= 0, "bad arguments");
+int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* params_bf16, int zero_grads,
+                  void* stream) {
+  LBX_CHECK_ARG(n >= 0 && n % 4 == 0, "the flat parameter count must be a multiple of 4 (pad the buffers)");
   if (n == 0) return LBX_OK;
   LBX_CHECK_ARG(params && grads && m && v && step_dev && lr_t_dev, "NULL pointer argument");
+  LBX_CHECK_ARG(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                  reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(params_bf16) & 7) == 0,
+                "flat buffers must be 16-byte aligned");
   adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, lr_t_dev, lr, beta1, beta2);
   LBX_LAUNCH_CHECK();
-  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr_t_dev, beta1, beta2, eps,
-                                                                  grad_scale);
+  adam_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((float4*)params, (float4*)grads, (float4*)m,
+                                                                      (float4*)v, n / 4, lr_t_dev, beta1, beta2, eps,
+                                                                      grad_scale, (uint2*)params_bf16, zero_grads);
   LBX_LAUNCH_CHECK();
   return LBX_OK;
 }
@@ -703,7 +642,7 @@ int lbx_dense_finish(float* acc, long long M, int N, int ld_acc, const float* bi
   LBX_CHECK_ARG(M >= 0 && N >= 1 && ld_acc >= N, "bad shape");
   if (M == 0) return LBX_OK;
   LBX_CHECK_ARG(acc != nullptr, "NULL accumulator");
-  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 64));
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 16));
   dense_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc, M, N, ld_acc, bias, relu, (const bf16*)mask_src,
                                                               ld_mask, (bf16*)out_hi, (bf16*)out_lo, ld_out, out_f32,
                                                               ld_f32, colsum, zero_acc);
@@ -711,43 +650,11 @@ int lbx_dense_finish(float* acc, long long M, int N, int ld_acc, const float* bi
   return LBX_OK;
 }
 
-int lbx_adam_refresh(const lbx_adam_layers_t* layers, float* params, float* grads, float* m, float* v, float lr,
-                     float beta1, float beta2, float eps, long long* step_dev, float* lr_t_dev, float grad_scale,
-                     int zero_grads, void* stream) {
-  LBX_CHECK_ARG(layers && layers->n_layers >= 1 && layers->n_layers <= LBX_MAX_LAYERS, "bad layer table");
-  LBX_CHECK_ARG(params && grads && m && v && step_dev && lr_t_dev, "NULL pointer argument");
-  AdamLayersDev L{};
-  L.n_layers = layers->n_layers;
-  int tiles = 0, bias_blocks = 0;
-  for (int l = 0; l < L.n_layers; ++l) {
-    LBX_CHECK_ARG(layers->K[l] >= 1 && layers->N[l] >= 1 && layers->W[l] && layers->Wt[l], "bad layer %d", l);
-    L.tile_start[l] = tiles;
-    L.bias_start[l] = bias_blocks;
-    tiles += (int)(ceil_div(layers->K[l], 32) * ceil_div(layers->N[l], 32));
-    bias_blocks += (int)ceil_div(layers->N[l], 256);
-    L.w_off[l] = layers->w_off[l]; L.b_off[l] = layers->b_off[l];
-    L.K[l] = layers->K[l]; L.N[l] = layers->N[l]; L.ldw[l] = layers->ldw[l]; L.ldt[l] = layers->ldt[l];
-    L.W[l] = (bf16*)layers->W[l]; L.Wt[l] = (bf16*)layers->Wt[l];
-  }
-  L.tile_start[L.n_layers] = tiles;
-  L.bias_start[L.n_layers] = bias_blocks;
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, lr_t_dev, lr, beta1, beta2);
-  LBX_LAUNCH_CHECK();
-  adam_refresh_kernel<<<tiles + bias_blocks, 256, 0, (cudaStream_t)stream>>>(L, params, grads, m, v, lr_t_dev, beta1,
-                                                                            beta2, eps, grad_scale, zero_grads);
-  LBX_LAUNCH_CHECK();
-  return LBX_OK;
-}
-
-int lbx_refresh_weights(const float* w, int K, int N, void* w_hi, void* w_lo, int ldw, void* t_hi, void* t_lo, int ldt,
-                        void* stream) {
-  LBX_CHECK_ARG(K >= 1 && N >= 1, "bad shape");
-  LBX_CHECK_ARG(w, "NULL weights");
-  LBX_CHECK_ARG(!w_hi || ldw >= N, "ldw too small");
-  LBX_CHECK_ARG(!t_hi || ldt >= K, "ldt too small");
-  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(K, 32));
-  refresh_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, K, N, (bf16*)w_hi, (bf16*)w_lo, ldw, (bf16*)t_hi,
-                                                                 (bf16*)t_lo, ldt);
+int lbx_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream) {
+  LBX_CHECK_ARG(n >= 0, "bad length");
+  if (n == 0) return LBX_OK;
+  LBX_CHECK_ARG(x && hi, "NULL pointer argument");
+  split_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, (bf16*)hi, (bf16*)lo);
   LBX_LAUNCH_CHECK();
   return LBX_OK;
 }

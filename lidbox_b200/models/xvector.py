@@ -118,7 +118,6 @@ class XVector:
         self._build_params(seed)
         self._bufs = {}
         self._adam = None
-        self._adam_layers = None
         self._grads_clean = True
 
     # ------------------------------------------------------------------ parameters
@@ -135,16 +134,22 @@ class XVector:
             self.layers.append(dict(name=sgm.name, kind="dense", K=d_in, N=sgm.units, relu=sgm.activation == "relu"))
             d_in = sgm.units
         self.layers.append(dict(name="outputs", kind="dense", K=d_in, N=self.num_outputs, relu=False))
+        # one flat fp32 buffer holds every kernel as [K, ldw] (Keras layout, pitch padded to 8 columns) and every
+        # bias (padded to 8); padding stays zero.  Gradients, Adam moments and the bf16 operand copy mirror it, so the
+        # optimizer is one elementwise pass and the gradient is one all-reduce.
         off = 0
         for ly in self.layers:
-            ly["w_off"], ly["b_off"] = off, off + ly["K"] * ly["N"]
-            off = ly["b_off"] + ly["N"]
-            ly["ldw"], ly["ldt"] = _ceil8(ly["N"]), ly["K"]
-            assert ly["K"] % 8 == 0
+            ly["ldw"] = _ceil8(ly["N"])
+            ly["w_off"] = off
+            ly["b_off"] = off + ly["K"] * ly["ldw"]
+            off = ly["b_off"] + ly["ldw"]
+            assert ly["K"] % 8 == 0 and ly["w_off"] % 8 == 0
         self.n_params_padded = off
         dev = self.device
         self.params = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.w16 = torch.zeros(off, dtype=torch.bfloat16, device=dev)      # bf16 operand copy (hi plane)
+        self.w16_lo = None                                                 # residual plane, fp32 (bf16x3) mode only
         gen = torch.Generator().manual_seed(0 if seed is None else int(seed))
         for ly in self.layers:           # Keras defaults: glorot-uniform kernels, zero biases
             if ly["kind"] == "frame":
@@ -153,18 +158,15 @@ class XVector:
                 w = (torch.rand((k, ci, co), generator=gen) * 2 - 1) * limit
                 wp = torch.zeros((k, ly["c_in"], co))
                 wp[:, :ci] = w
-                self._w_view(ly).copy_(wp.reshape(ly["K"], co))
+                self._w_view(ly)[:, :co].copy_(wp.reshape(ly["K"], co))
             else:
                 limit = math.sqrt(6.0 / (ly["K"] + ly["N"]))
-                self._w_view(ly).copy_((torch.rand((ly["K"], ly["N"]), generator=gen) * 2 - 1) * limit)
-        for ly in self.layers:
-            ly["W"] = torch.zeros((ly["K"], ly["ldw"]), dtype=torch.bfloat16, device=dev)
-            ly["Wt"] = torch.zeros((ly["N"], ly["ldt"]), dtype=torch.bfloat16, device=dev)
-            ly["W_lo"] = ly["Wt_lo"] = None
+                self._w_view(ly)[:, :ly["N"]].copy_((torch.rand((ly["K"], ly["N"]), generator=gen) * 2 - 1) * limit)
         self._weights_dirty, self._lo_dirty = True, True
 
-    def _w_view(self, ly):
-        return self.params[ly["w_off"]:ly["w_off"] + ly["K"] * ly["N"]].view(ly["K"], ly["N"])
+    def _w_view(self, ly, buf=None):
+        buf = self.params if buf is None else buf
+        return buf[ly["w_off"]:ly["w_off"] + ly["K"] * ly["ldw"]].view(ly["K"], ly["ldw"])
 
     def _b_view(self, ly):
         return self.params[ly["b_off"]:ly["b_off"] + ly["N"]]
@@ -177,7 +179,7 @@ class XVector:
         """dict name/kernel|bias -> numpy array in Keras layouts."""
         out = {}
         for ly in self.layers:
-            w = self._w_view(ly).cpu()
+            w = self._w_view(ly)[:, :ly["N"]].cpu()
             if ly["kind"] == "frame":
                 w = w.view(ly["k"], ly["c_in"], ly["N"])[:, :ly["c_in_real"]]
             out[ly["name"] + "/kernel"] = w.numpy().copy()
@@ -196,27 +198,22 @@ class XVector:
                 w = wp.reshape(ly["K"], ly["N"])
             elif tuple(w.shape) != (ly["K"], ly["N"]):
                 raise ValueError("bad kernel shape for %s: %s" % (ly["name"], tuple(w.shape)))
-            self._w_view(ly).copy_(w)
+            self._w_view(ly)[:, :ly["N"]].copy_(w)
             self._b_view(ly).copy_(torch.as_tensor(np.asarray(weights[ly["name"] + "/bias"]), dtype=torch.float32))
         self._weights_dirty = self._lo_dirty = True
 
     def _refresh(self, need_lo):
-        lib, st = _lib.lib(), _lib.stream_ptr(self.device)
-        if need_lo and self.layers[0]["Wt_lo"] is None:
-            for ly in self.layers:
-                ly["Wt_lo"] = torch.zeros_like(ly["Wt"])
+        """(Re)build the bf16 operand copy of the parameters (and the residual plane for the bf16x3 mode)."""
+        if need_lo and self.w16_lo is None:
+            self.w16_lo = torch.zeros_like(self.w16)
             self._lo_dirty = True
         if not (self._weights_dirty or (need_lo and self._lo_dirty)):
             return
-        for ly in self.layers:
-            lo = ly["Wt_lo"] if need_lo else None
-            _lib.check(lib.lbx_refresh_weights(_lib.ptr(self._w_view(ly)), ly["K"], ly["N"], _lib.ptr(ly["W"]), None,
-                                               ly["ldw"], _lib.ptr(ly["Wt"]), _lib.ptr(lo), ly["ldt"], st))
+        _lib.check(_lib.lib().lbx_split_bf16(_lib.ptr(self.params), self.params.numel(), _lib.ptr(self.w16),
+                                             _lib.ptr(self.w16_lo) if need_lo else None,
+                                             _lib.stream_ptr(self.device)))
         self._weights_dirty = False
-        if need_lo:
-            self._lo_dirty = False
-        else:
-            self._lo_dirty = True
+        self._lo_dirty = not need_lo
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, B, T, training):
@@ -292,9 +289,9 @@ class XVector:
             out_lo = None if (last or not split) else bufs["X_lo"][L + 1]
             ldo = bufs["cnp"] if last else ly["N"]
             out_off = 0 if last else geo.pad[L + 1] * ly["N"]
-            ops.gemm(bufs["X"][L], B * geo.R[L], ly["K"], ly["s"] * ly["c_in"], ly["Wt"], ly["N"], ly["K"], ly["ldt"],
-                     out, ldo, a_lo=bufs["X_lo"][L], b_lo=ly["Wt_lo"] if split else None, out_lo=out_lo,
-                     out_off=out_off, bias=self._b_view(ly), relu=ly["relu"], rows_per_utt=geo.R[L],
+            ops.gemm(bufs["X"][L], B * geo.R[L], ly["K"], ly["s"] * ly["c_in"], self.w16, ly["K"], ly["N"], ly["ldw"],
+                     out, ldo, layout=2, a_lo=bufs["X_lo"][L], b_lo=self.w16_lo if split else None, b_off=ly["w_off"],
+                     out_lo=out_lo, out_off=out_off, bias=self._b_view(ly), relu=ly["relu"], rows_per_utt=geo.R[L],
                      valid_rows=geo.T[L + 1])
         _lib.check(lib.lbx_stats_pool_fwd(_lib.ptr(bufs["Y"]), ops.F32 if split else ops.BF16, B, geo.R[n - 1],
                                           geo.T[n], bufs["cn"], bufs["cnp"], STDDEV_SQRT_MIN_CLIP,
@@ -320,8 +317,8 @@ class XVector:
         ld = acc.shape[1]
         tiles = -(-B // 128) * -(-ly["N"] // 256)
         ks = max(1, min(-(-ly["K"] // 64), 148 // tiles))
-        ops.gemm(a, B, ly["K"], ly["K"], ly["Wt"], ly["N"], ly["K"], ly["ldt"], acc, ld, a_lo=a_lo,
-                 b_lo=ly["Wt_lo"] if split else None, k_splits=ks, epi_atomic=True)
+        ops.gemm(a, B, ly["K"], ly["K"], self.w16, ly["K"], ly["N"], ly["ldw"], acc, ld, layout=2, a_lo=a_lo,
+                 b_lo=self.w16_lo if split else None, b_off=ly["w_off"], k_splits=ks, epi_atomic=True)
         _lib.check(_lib.lib().lbx_dense_finish(_lib.ptr(acc), B, ly["N"], ld, _lib.ptr(self._b_view(ly)), int(relu), None,
                                                0, _lib.ptr(out_hi), _lib.ptr(out_lo), ly["N"], _lib.ptr(out_f32),
                                                ly["N"], None, 1, _lib.stream_ptr(self.device)))
@@ -392,7 +389,7 @@ class XVector:
         def wgrad(a, a_rows, a_cols, lda, dz, dz_cols, dz_pitch, ly, a_off=0, dz_off=0):
             tiles = -(-a_cols // 128) * -(-dz_cols // 256)
             ks = max(1, min(-(-a_rows // 64), 148 // tiles))
-            ops.gemm(a, a_rows, a_cols, lda, dz, a_rows, dz_cols, dz_pitch, g, ly["N"], layout=1, a_off=a_off,
+            ops.gemm(a, a_rows, a_cols, lda, dz, a_rows, dz_cols, dz_pitch, g, ly["ldw"], layout=1, a_off=a_off,
                      b_off=dz_off, out_off=ly["w_off"], k_splits=ks, epi_atomic=True)
 
         # ---- dense head (bias gradients come fused out of the kernels that produce each dz) ----
@@ -407,16 +404,16 @@ class XVector:
             ks = max(1, min(-(-dz_cols // 64), 148 // tiles))
             if i > 0:      # d hidden = (dz . W^T) masked by the ReLU of the layer below; split-K + finishing pass
                 below = self.layers[n + i - 1]
-                ops.gemm(dz, B, dz_cols, dz_pitch, ly["W"], ly["K"], ly["N"], ly["ldw"], acc, ld_acc, k_splits=ks,
-                         epi_atomic=True)
+                ops.gemm(dz, B, dz_cols, dz_pitch, self.w16, ly["K"], ly["N"], ly["ldw"], acc, ld_acc,
+                         b_off=ly["w_off"], k_splits=ks, epi_atomic=True)
                 _lib.check(lib.lbx_dense_finish(_lib.ptr(acc), B, ly["K"], ld_acc, None, 0,
                                                 _lib.ptr(bufs["H"][i - 1]) if below["relu"] else None, ly["K"],
                                                 _lib.ptr(bufs["dH"][i - 1]), None, ly["K"], None, 0,
                                                 ops._addr(g, below["b_off"]), 1, st))
                 dz, dz_cols, dz_pitch = bufs["dH"][i - 1], ly["K"], ly["K"]
             else:          # d pooled (fp32, no mask): accumulated atomically into gpool, which pool_bwd re-zeroes
-                ops.gemm(dz, B, dz_cols, dz_pitch, ly["W"], ly["K"], ly["N"], ly["ldw"], bufs["gpool"], ly["K"],
-                         k_splits=ks, epi_atomic=True)
+                ops.gemm(dz, B, dz_cols, dz_pitch, self.w16, ly["K"], ly["N"], ly["ldw"], bufs["gpool"], ly["K"],
+                         b_off=ly["w_off"], k_splits=ks, epi_atomic=True)
         # ---- statistics pooling (+ ReLU mask and bias gradient of the last frame layer) ----
         last = self.layers[n - 1]
         _lib.check(lib.lbx_stats_pool_bwd(_lib.ptr(bufs["Y"]), B, geo.R[n - 1], geo.T[n], bufs["cn"], bufs["cnp"],
@@ -441,38 +438,29 @@ class XVector:
             if not below["relu"]:
                 raise NotImplementedError("linear frame layers are not supported in the backward pass")
             first = min(k, s)                        # taps [0, first) tile the time axis without overlap
-            ops.gemm(dZ, rows, ly["N"], dz_pitch, ly["W"], first * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
-                     a_off=dz_off, mask_src=bufs["X"][L], colsum=g, colsum_off=below["b_off"], colsum_mod=c)
+            ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, first * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
+                     a_off=dz_off, b_off=ly["w_off"], mask_src=bufs["X"][L], colsum=g, colsum_off=below["b_off"],
+                     colsum_mod=c)
             j = first
             while j < k:                             # remaining taps overlap the next row: accumulate pass(es)
                 cnt = min(s, k - j)
-                ops.gemm(dZ, rows, ly["N"], dz_pitch, ly["W"], cnt * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
-                         a_off=dz_off, b_off=j * c * ly["ldw"], out_off=j * c, mask_src=bufs["X"][L], mask_off=j * c,
-                         accumulate=True, colsum=g, colsum_off=below["b_off"], colsum_mod=c)
+                ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, cnt * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
+                         a_off=dz_off, b_off=ly["w_off"] + j * c * ly["ldw"], out_off=j * c, mask_src=bufs["X"][L],
+                         mask_off=j * c, accumulate=True, colsum=g, colsum_off=below["b_off"], colsum_mod=c)
                 j += cnt
         return bufs["loss"]
 
     def apply_gradients(self, grad_scale=1.0):
-        """Fused Adam + bf16 operand refresh + gradient reset (one kernel over all layers)."""
+        """Adam on the flat fp32 buffers; the same pass refreshes the bf16 operand copy and resets the gradient."""
         if self._adam is None:
             self.configure_optimizer()
         a = self._adam
-        if self._adam_layers is None:
-            t = _lib.AdamLayers()
-            t.n_layers = len(self.layers)
-            for i, ly in enumerate(self.layers):
-                t.w_off[i], t.b_off[i] = ly["w_off"], ly["b_off"]
-                t.K[i], t.N[i], t.ldw[i], t.ldt[i] = ly["K"], ly["N"], ly["ldw"], ly["ldt"]
-                t.W[i], t.Wt[i] = ly["W"].data_ptr(), ly["Wt"].data_ptr()
-            self._adam_layers = t
-        import ctypes
-        _lib.check(_lib.lib().lbx_adam_refresh(ctypes.byref(self._adam_layers), _lib.ptr(self.params),
-                                               _lib.ptr(self.grads), _lib.ptr(a["m"]), _lib.ptr(a["v"]), a["lr"],
-                                               a["beta1"], a["beta2"], a["eps"], _lib.ptr(a["step"]),
-                                               _lib.ptr(a["lr_t"]), float(grad_scale), 1,
-                                               _lib.stream_ptr(self.device)))
+        _lib.check(_lib.lib().lbx_adam_step(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(a["m"]),
+                                            _lib.ptr(a["v"]), self.params.numel(), a["lr"], a["beta1"], a["beta2"],
+                                            a["eps"], _lib.ptr(a["step"]), _lib.ptr(a["lr_t"]), float(grad_scale),
+                                            _lib.ptr(self.w16), 1, _lib.stream_ptr(self.device)))
         self._grads_clean = True
-        self._weights_dirty = False        # hi planes were refreshed by the fused kernel
+        self._weights_dirty = False        # the hi plane was refreshed by the optimizer pass
         self._lo_dirty = True
 
     def train_step(self, x, y, loss="xent", process_group=None, **kw):

@@ -50,7 +50,9 @@ def gemm(a, a_rows, a_cols, lda, b, b_rows, b_cols, ldb, out, ldo, *, layout=0, 
         e1.record()
         if layout == 0:
             GEMM_TIMER.append((e0, e1, a_rows, b_rows, a_cols, d.n_terms, 0))
-        else:
+        elif layout == 1:
             GEMM_TIMER.append((e0, e1, a_cols, b_cols, a_rows, d.n_terms, 1))
+        else:
+            GEMM_TIMER.append((e0, e1, a_rows, b_cols, a_cols, d.n_terms, 2))
         return
     _lib.check(_lib.lib().lbx_gemm_bf16(ctypes.byref(d), _lib.stream_ptr(a.device)))

@@ -130,3 +130,31 @@ def test_dgrad_mask_and_accumulate(ops):
     ref = torch.where(y.double() > 0, dz.double() @ w.double().T, torch.zeros((), device="cuda", dtype=torch.double))
     ref = ref + prev.double()
     assert float((out.double() - ref).abs().max()) < 0.01 * float(ref.abs().max()) + 0.05
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 200), (1000, 1500, 512), (64, 4, 512), (5000, 512, 1536)])
+def test_nn_forward_from_keras_layout(ops, M, N, K):
+    # forward pass straight from the Keras-layout weight [K, N] (pitch padded to 8): B is an MN-major operand
+    ldw = (N + 7) // 8 * 8
+    a = _rand((M, K), 21).bfloat16()
+    w = torch.zeros((K, ldw), device="cuda", dtype=torch.bfloat16)
+    w[:, :N] = _rand((K, N), 22, 0.05).bfloat16()
+    bias = _rand((N,), 23)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(a, M, K, K, w, K, N, ldw, out, N, layout=2, bias=bias)
+    ref = a.double() @ w[:, :N].double() + bias.double()
+    _check(out, ref, a.double().abs() @ w[:, :N].double().abs() + bias.double().abs())
+
+
+def test_colsum_epilogue(ops):
+    # bias gradient fused into the data-gradient epilogue: colsum[n % mod] += sum_m masked result
+    M, N, K, C = 777, 1024, 512, 512
+    dz = _rand((M, K), 24).bfloat16()
+    w = _rand((N, K), 25, 0.05).bfloat16()
+    y = _rand((M, N), 26).bfloat16()
+    out = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
+    cs = torch.zeros((C,), device="cuda")
+    ops.gemm(dz, M, K, K, w, N, K, K, out, N, mask_src=y, colsum=cs, colsum_mod=C)
+    ref = torch.where(y.double() > 0, dz.double() @ w.double().T, torch.zeros((), device="cuda", dtype=torch.double))
+    ref_cs = ref.sum(dim=0).view(2, C).sum(dim=0)
+    assert float((cs.double() - ref_cs).abs().max()) < 1e-3 * float(ref.abs().sum(dim=0).max())

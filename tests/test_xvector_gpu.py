@@ -50,7 +50,9 @@ def _oracle_grads(params, x, y, loss="xent", N=None, w=1.0, emulate_bf16=False):
 def _check_grads(m, g_ref, min_cos, max_nw):
     grads = m.grads.cpu().numpy()
     for ly in m.layers:
-        gw = grads[ly["w_off"]:ly["w_off"] + ly["K"] * ly["N"]].reshape(ly["K"], ly["N"])
+        gw = grads[ly["w_off"]:ly["w_off"] + ly["K"] * ly["ldw"]].reshape(ly["K"], ly["ldw"])
+        assert not gw[:, ly["N"]:].any()                 # pitch padding never receives a gradient
+        gw = gw[:, :ly["N"]]
         gb = grads[ly["b_off"]:ly["b_off"] + ly["N"]]
         rw = g_ref[ly["name"] + "/kernel"].reshape(ly["K"], ly["N"])
         rb = g_ref[ly["name"] + "/bias"]
@@ -118,7 +120,7 @@ def test_channel_dropout_training_only(xv):
     x = np.random.default_rng(3).standard_normal((4, 50, 40)).astype(np.float32)
     m = xv.create((50, 40), 6, channel_dropout_rate=0.5)
     a, b = m(x, training=False), m(x, training=False)
-    assert torch.equal(a, b)
+    assert torch.allclose(a, b, rtol=0, atol=1e-5)      # split-K fp32 atomics: summation order is not fixed
     c = m(x, training=True)
     assert not torch.allclose(a, c) and torch.isfinite(c).all()
 

@@ -42,53 +42,49 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML every ~5 ms during the timed region (nvidia-smi's own
+    polling loop is too coarse for regions of a few tens of milliseconds)."""
 
     def __init__(self, gpu_index=0):
         self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            while not self._stop.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.005)
+        except Exception as e:          # never take the benchmark down
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def synth_signals(B, N, seed, device=None, pin=False):
@@ -247,6 +243,9 @@ class XVectorTrainWorkload:
         if self.use_graph:
             self.graphed = xvector.GraphedTrainStep(self.model, self.feats, self.y, loss=self.loss,
                                                     process_group=self.pg, pre=self._features, **self.kw)
+        # end-to-end path: two input buffers and two graphs, so the H2D copy of batch i+1 (copy stream) overlaps the
+        # training step of batch i (compute stream); every batch is still copied from pinned host memory
+        self.e2e = None
 
     def _features(self):
         return self.audio.logmelspectrograms(self.x, SR, out=self.feats)
@@ -263,36 +262,98 @@ class XVectorTrainWorkload:
     def launches_per_step(self):
         return self.graphed.kernels_per_step if self.graphed is not None else None
 
+    def _setup_e2e(self):
+        from lidbox_b200.models import xvector
+        dev = self.device
+        e = {"x": [self.x, torch.empty_like(self.x)], "graphs": [], "copy": torch.cuda.Stream(device=dev), "i": 0,
+             "h2d_done": [torch.cuda.Event(), torch.cuda.Event()], "step_done": [torch.cuda.Event(), torch.cuda.Event()],
+             "loss_host": [torch.empty((self.B,), dtype=torch.float32).pin_memory() for _ in range(2)]}
+        for k in range(2):
+            if k == 0 and self.graphed is not None:
+                e["graphs"].append(self.graphed)
+                continue
+            xk = e["x"][k]
+            pre = (lambda xk=xk: self.audio.logmelspectrograms(xk, SR, out=self.feats))
+            if self.use_graph:
+                e["graphs"].append(xvector.GraphedTrainStep(self.model, self.feats, self.y, loss=self.loss,
+                                                            process_group=self.pg, pre=pre, **self.kw))
+            else:
+                e["graphs"].append(lambda pre=pre: self.model.train_step(pre(), self.y, loss=self.loss,
+                                                                         process_group=self.pg, **self.kw))
+        cur = torch.cuda.current_stream(dev)
+        for k in range(2):
+            e["step_done"][k].record(cur)
+        # prime: the first batch is copied before the pipeline starts
+        with torch.cuda.stream(e["copy"]):
+            e["x"][0].copy_(self.x_host, non_blocking=True)
+            e["h2d_done"][0].record(e["copy"])
+        self.e2e = e
+
     def step_e2e(self):
-        self.x.copy_(self.x_host, non_blocking=True)
-        losses = self.step()
-        self.loss_host.copy_(losses, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        """One step of the public-API pipeline: batch i trains from device buffer i%2 while batch i+1 is copied from
+        pinned host memory into buffer (i+1)%2 on the copy stream; the per-sample losses of batch i are read back."""
+        if self.e2e is None:
+            self._setup_e2e()
+        e = self.e2e
+        k, nk = e["i"] % 2, (e["i"] + 1) % 2
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(e["copy"]):
+            e["copy"].wait_event(e["step_done"][nk])          # buffer nk is free once the step that read it is done
+            e["x"][nk].copy_(self.x_host, non_blocking=True)
+            e["h2d_done"][nk].record(e["copy"])
+        cur.wait_event(e["h2d_done"][k])
+        losses = e["graphs"][k]()
+        e["step_done"][k].record(cur)
+        e["loss_host"][k].copy_(losses, non_blocking=True)
+        e["i"] += 1
+        if e["i"] % 2 == 0:
+            cur.synchronize()                                  # host reads the losses of the last two steps
 
     def e2e_bytes(self):
         return self.B * self.N * 4, self.B * 4
 
     def roofline_measure(self, peaks):
-        """Times every GEMM launch of one eager step with CUDA events on the launching stream (3 repetitions, best)."""
+        """Dominant kernel = gemm_bf16_kernel.  Every GEMM descriptor of one training step is recorded, the launches
+        are replayed back-to-back from a CUDA graph (same operands, same order, nothing else in between) and timed
+        with CUDA events on the launching stream; achieved = algorithmic training FLOPs of the step / that time."""
         from lidbox_b200 import ops
         fwd, f1 = tdnn_forward_flops(self.T, self.n_out)
         alg = self.B * (3 * fwd - f1)
-        best, n_launch, issued = None, 0, 0
-        for _ in range(3):
-            ops.GEMM_TIMER = []
-            self._eager_step()
-            torch.cuda.synchronize()
-            rec, ops.GEMM_TIMER = ops.GEMM_TIMER, None
-            ms = sum(e0.elapsed_time(e1) for (e0, e1, *_r) in rec)
-            if best is None or ms < best:
-                best, n_launch = ms, len(rec)
-                issued = sum(2.0 * M * N * K * nt for (_a, _b, M, N, K, nt, _l) in rec)
-        ach = alg / (best * 1e-3) / 1e12
+        ops.GEMM_RECORD = []
+        self._eager_step()
+        torch.cuda.synchronize()
+        rec, ops.GEMM_RECORD = ops.GEMM_RECORD, None
+        issued = sum(2.0 * M * N * K * nt for (_d, _k, (M, N, K, nt, _l)) in rec)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            ops.replay(rec, self.device)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ops.replay(rec, self.device)
+        ms = _time_cuda(g.replay, 20)
+        self.model.grads.zero_()               # the replays accumulated into the gradient buffer
+        self.model._grads_clean = True
+        # per-launch durations (eager, CUDA events around each launch) for the largest single launch
+        ops.GEMM_TIMER = []
+        self._eager_step()
+        torch.cuda.synchronize()
+        tim, ops.GEMM_TIMER = ops.GEMM_TIMER, None
+        big = max(tim, key=lambda r: r[2] * r[3] * r[4])
+        big_ms = big[0].elapsed_time(big[1])
+        ach = alg / (ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        return {"bound": "tensor", "kernel": "gemm_bf16_kernel (all %d launches of one training step)" % n_launch,
+        return {"bound": "tensor", "kernel": "gemm_bf16_kernel (all %d launches of one training step, replayed "
+                                             "back-to-back from a CUDA graph)" % len(rec),
                 "achieved": ach, "peak": peak, "peak_source": peaks["source"] + " (sustained: timed inside a step)",
                 "unit": "TFLOP/s", "frac": ach / peak, "algorithmic_flops_per_step": alg,
-                "issued_flops_per_step": issued, "gemm_ms_per_step": best, "traffic": None}
+                "issued_flops_per_step": issued, "gemm_ms_per_step": ms, "launches": len(rec),
+                "avg_launch_us": ms * 1e3 / len(rec),
+                "largest_launch": {"M": big[2], "N": big[3], "K": big[4], "ms": big_ms,
+                                   "tflops": 2.0 * big[2] * big[3] * big[4] / (big_ms * 1e-3) / 1e12},
+                "traffic": None}
 
     def cpu_sample(self, budget_s=20.0):
         from oracle import lidbox_oracle as O
@@ -506,10 +567,10 @@ def main():
 
     _log("roofline done")
     # end-to-end through the public API with pinned host buffers
-    for _ in range(2):
+    for _ in range(4):
         wl.step_e2e()
     barrier()
-    e_steps = max(3, min(args.steps, 10))
+    e_steps = max(10, min(args.steps, 50))
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

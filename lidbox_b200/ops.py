@@ -11,6 +11,16 @@ F32, BF16 = 0, 1
 # bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream:
 # entries are (start_event, end_event, M, N, K, n_terms, layout)
 GEMM_TIMER = None
+# bench.py sets this to a list to record every GEMM descriptor of a step (replayed back-to-back for the roofline)
+GEMM_RECORD = None
+
+
+def replay(descs, device):
+    """Re-issue recorded GEMM descriptors on the current stream."""
+    st = _lib.stream_ptr(device)
+    fn = _lib.lib().lbx_gemm_bf16
+    for d, _keep, _shape in descs:
+        _lib.check(fn(ctypes.byref(d), st))
 
 
 def _addr(t, offset_elems=0):
@@ -43,6 +53,14 @@ def gemm(a, a_rows, a_cols, lda, b, b_rows, b_cols, ldb, out, ldo, *, layout=0, 
     d.accumulate = int(accumulate)
     d.tile_n = tile_n
     d.colsum, d.colsum_mod = _addr(colsum, colsum_off), colsum_mod
+    if GEMM_RECORD is not None:
+        if layout == 0:
+            shape = (a_rows, b_rows, a_cols)
+        elif layout == 1:
+            shape = (a_cols, b_cols, a_rows)
+        else:
+            shape = (a_rows, b_cols, a_cols)
+        GEMM_RECORD.append((d, (a, b, out, a_lo, b_lo, out_lo, bias, mask_src, colsum), shape + (d.n_terms, layout)))
     if GEMM_TIMER is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

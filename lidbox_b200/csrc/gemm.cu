@@ -23,6 +23,7 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int EPI_WARPS = 8;                  // two warps per TMEM sub-partition, each takes half of the tile's columns
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int BIAS_SMEM_FLOATS = 3072;         // the bias vector is staged in shared memory when N fits
 
 // tile-N variants: 256 (large problems) and 128 (problems with fewer than ~2 tiles per SM at N=256)
 template <int BN>
@@ -31,7 +32,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BN == 256 ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;    // 2 accumulator stages x BN fp32 columns
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_SMEM_FLOATS * 4;
 };
 
 struct GemmParams {
@@ -172,7 +173,7 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, bool vec,
 }
 
 template <int LAYOUT, int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __maxnreg__(200)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                      const GemmParams p) {
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -307,11 +309,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     constexpr int CHUNKS = BN / 64;              // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
+    // the bias vector is read by every tile: stage it once (global loads in the epilogue's critical path cost an L2
+    // round trip per 32-column chunk with only two warps per scheduler to hide it)
+    const bool bias_smem = p.bias != nullptr && p.N <= BIAS_SMEM_FLOATS;
+    if (bias_smem) {
+      for (int i = threadIdx.x - 64; i < p.N; i += 32 * EPI_WARPS) s_bias[i] = __ldg(p.bias + i);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int rem = tile % mn_tiles;
       const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
-      mbar_wait(tfull_bar + acc, acc_phase);
-      tc_fence_after();
       const int m = m_blk * BM + sub * 32 + lane;
       const bool in_range = m < p.M;
       // rows past the valid part of an utterance are stored as zeros: they land on rows of the destination that
@@ -320,6 +327,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const long long row_off = (long long)m * p.ldo;
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
       const int col_base = n_blk * BN + chalf * (BN / 2);
+      // ReLU-backward mask and read-modify-write operands are fetched one 32-column chunk ahead (the first one before
+      // the accumulator is even ready), as raw 16-byte vectors
+      const __nv_bfloat16* mrow = p.mask_src != nullptr ? p.mask_src + row_off : nullptr;
+      const __nv_bfloat16* prow = reinterpret_cast<const __nv_bfloat16*>(p.out) + row_off;
+      const bool mvec = mrow != nullptr && in_range && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
+      const bool pvec = p.accumulate && p.out_dtype == LBX_BF16 && !p.epi_atomic && in_range &&
+                        ((reinterpret_cast<uintptr_t>(prow) & 15) == 0);
+      uint4 mq[4];
+      auto prefetch = [&](int ci) {
+        const int n0 = col_base + ci * 32;
+        if (mvec && n0 + 32 <= p.N) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mq[q] = __ldg(reinterpret_cast<const uint4*>(mrow + n0) + q);
+        }
+      };
+      prefetch(0);
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
       constexpr int GROUP = 2, NGROUPS = CHUNKS / GROUP;     // 64 columns in flight per warp
 #pragma unroll 1
       for (int grp = 0; grp < NGROUPS; ++grp) {
@@ -338,13 +363,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (!in_range && p.colsum == nullptr) continue;
 #pragma unroll
       for (int c = 0; c < GROUP; ++c) {
-        const int n0 = col_base + (grp * GROUP + c) * 32;
+        const int ci = grp * GROUP + c;
+        const int n0 = col_base + ci * 32;
         if (n0 >= p.N) break;
         const int ncols = min(32, p.N - n0);
+        uint4 mc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mc[q] = mq[q];
+        if (ci + 1 < CHUNKS) prefetch(ci + 1);
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[c][j]);
-        if (p.bias != nullptr) {
+        if (bias_smem) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (4 * q < ncols) {                 // N is a multiple of 4 for every biased layer that takes this path
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + 4 * q);
+              x[4 * q] += b4.x; x[4 * q + 1] += b4.y; x[4 * q + 2] += b4.z; x[4 * q + 3] += b4.w;
+            }
+          }
+        } else if (p.bias != nullptr) {
           const float* bp = p.bias + n0;
           if (ncols == 32 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
@@ -366,10 +404,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = 0.0f;
         }
-        if (p.mask_src != nullptr && in_range) {
+        if (mvec && ncols == 32) {
+          // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w[4] = {mc[q].x, mc[q].y, mc[q].z, mc[q].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t lo16 = w[i] & 0xFFFFu, hi16 = w[i] >> 16;
+              if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) x[8 * q + 2 * i] = 0.0f;
+              if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) x[8 * q + 2 * i + 1] = 0.0f;
+            }
+          }
+        } else if (p.mask_src != nullptr && in_range) {
           const __nv_bfloat16* mp = p.mask_src + row_off + n0;
           float mk[32];
-          load_bf16x32(mp, ncols == 32 && ((reinterpret_cast<uintptr_t>(mp) & 15) == 0), ncols, mk);
+          load_bf16x32(mp, false, ncols, mk);
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (!(mk[j] > 0.0f)) x[j] = 0.0f;
@@ -411,7 +461,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
           float prev[32];
           if (p.accumulate) {
-            load_bf16x32(o, vec, ncols, prev);
+            load_bf16x32(o, pvec && ncols == 32, ncols, prev);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) prev[j] = 0.0f;

@@ -119,6 +119,8 @@ class XVector:
         self._bufs = {}
         self._adam = None
         self._grads_clean = True
+        self.overlap_wgrad = True
+        self._side_stream = torch.cuda.Stream(device=self.device)
 
     # ------------------------------------------------------------------ parameters
     def _build_params(self, seed):
@@ -386,9 +388,22 @@ class XVector:
         else:
             raise ValueError("loss must be 'xent' or 'ap'")
 
+        # weight gradients are leaves of the backward graph (only the optimizer reads them): they run on a side
+        # stream, concurrently with the latency-bound chain of data-gradient kernels, and are joined before Adam
+        cur = torch.cuda.current_stream(self.device)
+        side = self._side_stream if self.overlap_wgrad else None
+
         def wgrad(a, a_rows, a_cols, lda, dz, dz_cols, dz_pitch, ly, a_off=0, dz_off=0):
             tiles = -(-a_cols // 128) * -(-dz_cols // 256)
             ks = max(1, min(-(-a_rows // 64), 148 // tiles))
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    ops.gemm(a, a_rows, a_cols, lda, dz, a_rows, dz_cols, dz_pitch, g, ly["ldw"], layout=1,
+                             a_off=a_off, b_off=dz_off, out_off=ly["w_off"], k_splits=ks, epi_atomic=True)
+                return
             ops.gemm(a, a_rows, a_cols, lda, dz, a_rows, dz_cols, dz_pitch, g, ly["ldw"], layout=1, a_off=a_off,
                      b_off=dz_off, out_off=ly["w_off"], k_splits=ks, epi_atomic=True)
 
@@ -448,6 +463,10 @@ class XVector:
                          a_off=dz_off, b_off=ly["w_off"] + j * c * ly["ldw"], out_off=j * c, mask_src=bufs["X"][L],
                          mask_off=j * c, accumulate=True, colsum=g, colsum_off=below["b_off"], colsum_mod=c)
                 j += cnt
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            cur.wait_event(ev)
         return bufs["loss"]
 
     def apply_gradients(self, grad_scale=1.0):

@@ -173,7 +173,7 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, bool vec,
 }
 
 template <int LAYOUT, int BN>
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                      const GemmParams p) {

@@ -7,8 +7,8 @@
 // utterance, so row (b,t) of the implicit matrix is the k*C_in contiguous elements starting at padded time t*stride;
 // the A operand is a plain 2-D TMA view whose row pitch (stride*C_in) is smaller than its width (k*C_in).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/mask -> global).  Operands are bf16 in 128B-swizzled
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2-3 idle,
+// warps 4..11 = epilogue (TMEM -> registers -> bias/ReLU/mask -> global).  Operands are bf16 in 128B-swizzled
 // shared memory (4 stages x 48 KB), accumulators fp32 in TMEM, double-buffered (2 x 256 columns) so the epilogue
 // of tile i overlaps the main loop of tile i+1.  "bf16x3" mode runs three accumulating passes
 // (A_hi B_hi + A_hi B_lo + A_lo B_hi) for fp32-grade results from bf16 tensor cores.
@@ -19,10 +19,13 @@
 
 namespace lbx {
 
+#ifndef LBX_GEMM_SETMAXNREG
+#define LBX_GEMM_SETMAXNREG 0
+#endif
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int EPI_WARPS = 8;                  // two warps per TMEM sub-partition, each takes half of the tile's columns
-constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;   // warpgroup 0: TMA / MMA / 2 idle warps; warpgroups 1-2: epilogue
 constexpr int BIAS_SMEM_FLOATS = 3072;         // the bias vector is staged in shared memory when N fits
 
 // tile-N variants: 256 (large problems) and 128 (problems with fewer than ~2 tiles per SM at N=256)
@@ -173,7 +176,7 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, bool vec,
 }
 
 template <int LAYOUT, int BN>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                      const GemmParams p) {
@@ -229,6 +232,15 @@ __global__ void __maxnreg__(192)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+  // register budget: 384 threads start with 168 registers each; the control warpgroup gives most of its share to the
+  // two epilogue warpgroups (4*32*56 + 8*32*224 = 64512 <= 65536)
+#if LBX_GEMM_SETMAXNREG
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+  }
+#endif
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
@@ -302,10 +314,10 @@ __global__ void __maxnreg__(192)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ===================================== epilogue =====================================
     const int sub = warp & 3;                    // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
-    const int chalf = (warp - 2) >> 2;           // which half of the tile's columns this warp drains
+    const int chalf = (warp - 4) >> 2;           // which half of the tile's columns this warp drains
     constexpr int CHUNKS = BN / 64;              // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -313,7 +325,7 @@ __global__ void __maxnreg__(192)
     // round trip per 32-column chunk with only two warps per scheduler to hide it)
     const bool bias_smem = p.bias != nullptr && p.N <= BIAS_SMEM_FLOATS;
     if (bias_smem) {
-      for (int i = threadIdx.x - 64; i < p.N; i += 32 * EPI_WARPS) s_bias[i] = __ldg(p.bias + i);
+      for (int i = threadIdx.x - 128; i < p.N; i += 32 * EPI_WARPS) s_bias[i] = __ldg(p.bias + i);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {

@@ -6,7 +6,7 @@ import os
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "liblidbox_b200.so")
+LIB_PATH = os.environ.get("LBX_LIB") or os.path.join(_PKG_DIR, "liblidbox_b200.so")   # LBX_LIB: A/B builds
 
 c_int, c_ll, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 _P = c_void_p

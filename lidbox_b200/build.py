@@ -31,14 +31,20 @@ def is_stale():
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out=None):
     """Compile every CUDA translation unit into one shared library. Returns the library path."""
+    if out is not None:
+        return _compile(out, list(extra_flags), verbose)
     if not force and not is_stale():
         return LIB_PATH
+    return _compile(LIB_PATH, [], verbose)
+
+
+def _compile(LIB_PATH, extra, verbose):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: lidbox_b200 has no CPU fallback and cannot run without its CUDA library")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-o", LIB_PATH + ".tmp"] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-o", LIB_PATH + ".tmp"] + sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -19,13 +19,22 @@
 
 namespace lbx {
 
+#ifndef LBX_BIAS_SMEM
+#define LBX_BIAS_SMEM 1
+#endif
+#ifndef LBX_MASK_PREFETCH
+#define LBX_MASK_PREFETCH 1
+#endif
+#ifndef LBX_CTRL_WARPS
+#define LBX_CTRL_WARPS 4
+#endif
 #ifndef LBX_GEMM_SETMAXNREG
 #define LBX_GEMM_SETMAXNREG 0
 #endif
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int EPI_WARPS = 8;                  // two warps per TMEM sub-partition, each takes half of the tile's columns
-constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;   // warpgroup 0: TMA / MMA / 2 idle warps; warpgroups 1-2: epilogue
+constexpr int GEMM_THREADS = 32 * LBX_CTRL_WARPS + 32 * EPI_WARPS;   // warpgroup 0: TMA / MMA / 2 idle warps; warpgroups 1-2: epilogue
 constexpr int BIAS_SMEM_FLOATS = 3072;         // the bias vector is staged in shared memory when N fits
 
 // tile-N variants: 256 (large problems) and 128 (problems with fewer than ~2 tiles per SM at N=256)
@@ -175,7 +184,7 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, bool vec,
   }
 }
 
-template <int LAYOUT, int BN>
+template <int LAYOUT, int BN, bool HAS_MASK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -314,18 +323,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= LBX_CTRL_WARPS) {
     // ===================================== epilogue =====================================
     const int sub = warp & 3;                    // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
-    const int chalf = (warp - 4) >> 2;           // which half of the tile's columns this warp drains
+    const int chalf = (warp - LBX_CTRL_WARPS) >> 2;           // which half of the tile's columns this warp drains
     constexpr int CHUNKS = BN / 64;              // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     // the bias vector is read by every tile: stage it once (global loads in the epilogue's critical path cost an L2
     // round trip per 32-column chunk with only two warps per scheduler to hide it)
-    const bool bias_smem = p.bias != nullptr && p.N <= BIAS_SMEM_FLOATS;
+    const bool bias_smem = LBX_BIAS_SMEM && p.bias != nullptr && p.N <= BIAS_SMEM_FLOATS;
     if (bias_smem) {
-      for (int i = threadIdx.x - 128; i < p.N; i += 32 * EPI_WARPS) s_bias[i] = __ldg(p.bias + i);
+      for (int i = threadIdx.x - 32 * LBX_CTRL_WARPS; i < p.N; i += 32 * EPI_WARPS) s_bias[i] = __ldg(p.bias + i);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -339,22 +348,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const long long row_off = (long long)m * p.ldo;
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
       const int col_base = n_blk * BN + chalf * (BN / 2);
-      // ReLU-backward mask and read-modify-write operands are fetched one 32-column chunk ahead (the first one before
-      // the accumulator is even ready), as raw 16-byte vectors
-      const __nv_bfloat16* mrow = p.mask_src != nullptr ? p.mask_src + row_off : nullptr;
+      const __nv_bfloat16* mrow = HAS_MASK ? p.mask_src + row_off : nullptr;
       const __nv_bfloat16* prow = reinterpret_cast<const __nv_bfloat16*>(p.out) + row_off;
-      const bool mvec = mrow != nullptr && in_range && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
+      const bool mvec = HAS_MASK && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
       const bool pvec = p.accumulate && p.out_dtype == LBX_BF16 && !p.epi_atomic && in_range &&
                         ((reinterpret_cast<uintptr_t>(prow) & 15) == 0);
-      uint4 mq[4];
-      auto prefetch = [&](int ci) {
-        const int n0 = col_base + ci * 32;
-        if (mvec && n0 + 32 <= p.N) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) mq[q] = __ldg(reinterpret_cast<const uint4*>(mrow + n0) + q);
-        }
-      };
-      prefetch(0);
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       constexpr int GROUP = 2, NGROUPS = CHUNKS / GROUP;     // 64 columns in flight per warp
@@ -379,10 +377,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int n0 = col_base + ci * 32;
         if (n0 >= p.N) break;
         const int ncols = min(32, p.N - n0);
-        uint4 mc[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) mc[q] = mq[q];
-        if (ci + 1 < CHUNKS) prefetch(ci + 1);
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[c][j]);
@@ -416,22 +410,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = 0.0f;
         }
-        if (mvec && ncols == 32) {
-          // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t w[4] = {mc[q].x, mc[q].y, mc[q].z, mc[q].w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t lo16 = w[i] & 0xFFFFu, hi16 = w[i] >> 16;
-              if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) x[8 * q + 2 * i] = 0.0f;
-              if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) x[8 * q + 2 * i + 1] = 0.0f;
-            }
-          }
-        } else if (p.mask_src != nullptr && in_range) {
-          const __nv_bfloat16* mp = p.mask_src + row_off + n0;
+        if (HAS_MASK && in_range) {
           float mk[32];
-          load_bf16x32(mp, false, ncols, mk);
+          load_bf16x32(mrow + n0, mvec && ncols == 32, ncols, mk);
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (!(mk[j] > 0.0f)) x[j] = 0.0f;
@@ -649,8 +630,11 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
     int dev = 0, n = 0;
     LBX_CUDA(cudaGetDevice(&dev));
     LBX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-#define LBX_SET_SMEM(L, N_) \
-  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<N_>::SMEM))
+#define LBX_SET_SMEM(L, N_)                                                                                       \
+  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                (int)Cfg<N_>::SMEM));                                                             \
+  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                (int)Cfg<N_>::SMEM))
     LBX_SET_SMEM(0, 256); LBX_SET_SMEM(1, 256); LBX_SET_SMEM(2, 256);
     LBX_SET_SMEM(0, 128); LBX_SET_SMEM(1, 128); LBX_SET_SMEM(2, 128);
 #undef LBX_SET_SMEM
@@ -669,7 +653,9 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   cfg.attrs = attr;
   cfg.numAttrs = g_use_pdl ? 1 : 0;
   cudaError_t le;
-#define LBX_GEMM_LAUNCH(L, N_) le = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_>, mA0, mA1, mB0, mB1, p)
+#define LBX_GEMM_LAUNCH(L, N_)                                                                         \
+  le = p.mask_src ? cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, true>, mA0, mA1, mB0, mB1, p)    \
+                  : cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, false>, mA0, mA1, mB0, mB1, p)
   if (bn == 256) {
     if (g->layout == 0) LBX_GEMM_LAUNCH(0, 256); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 256); else LBX_GEMM_LAUNCH(2, 256);
   } else {

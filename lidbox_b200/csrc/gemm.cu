@@ -36,6 +36,8 @@ constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int EPI_WARPS = 8;                  // two warps per TMEM sub-partition, each takes half of the tile's columns
 constexpr int GEMM_THREADS = 32 * LBX_CTRL_WARPS + 32 * EPI_WARPS;   // warpgroup 0: TMA / MMA / 2 idle warps; warpgroups 1-2: epilogue
 constexpr int BIAS_SMEM_FLOATS = 3072;         // the bias vector is staged in shared memory when N fits
+constexpr int STAGE_PITCH = 80;                // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16-byte accesses)
+constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH;
 
 // tile-N variants: 256 (large problems) and 128 (problems with fewer than ~2 tiles per SM at N=256)
 template <int BN>
@@ -44,7 +46,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BN == 256 ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;    // 2 accumulator stages x BN fp32 columns
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_SMEM_FLOATS * 4;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_SMEM_FLOATS * 4 +
+                                 EPI_WARPS * STAGE_BYTES_PER_WARP;
 };
 
 struct GemmParams {
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES + 256);
+  unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_bias + BIAS_SMEM_FLOATS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -348,6 +352,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const long long row_off = (long long)m * p.ldo;
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
       const int col_base = n_blk * BN + chalf * (BN / 2);
+      // coalescing through a per-warp staging tile: a thread owns one accumulator ROW, so direct 16-byte accesses touch
+      // 32 different lines per instruction (half sectors); staged, 4 lanes cover 64 contiguous bytes of one row
+      unsigned char* st = s_stage + (warp - LBX_CTRL_WARPS) * STAGE_BYTES_PER_WARP;
+      const int warp_row0 = m_blk * BM + sub * 32;
+      const int sr = lane >> 2, sseg = lane & 3;           // staged access: rows sr + 8j, 16-byte segment sseg
+      const bool ld_al = (p.ldo & 7) == 0;
+      const bool stage_out = p.out_dtype == LBX_BF16 && !p.epi_atomic && !p.accumulate && ld_al &&
+                             ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                             (p.out_lo == nullptr || (reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0);
+      const bool stage_mask = HAS_MASK && ld_al && ((reinterpret_cast<uintptr_t>(p.mask_src) & 15) == 0);
       const __nv_bfloat16* mrow = HAS_MASK ? p.mask_src + row_off : nullptr;
       const __nv_bfloat16* prow = reinterpret_cast<const __nv_bfloat16*>(p.out) + row_off;
       const bool mvec = HAS_MASK && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
@@ -355,7 +369,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         ((reinterpret_cast<uintptr_t>(prow) & 15) == 0);
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
-      constexpr int GROUP = 2, NGROUPS = CHUNKS / GROUP;     // 64 columns in flight per warp
+#ifndef LBX_EPI_GROUP
+#define LBX_EPI_GROUP 1
+#endif
+      constexpr int GROUP = LBX_EPI_GROUP, NGROUPS = CHUNKS / GROUP;     // 32*GROUP columns in flight per warp
 #pragma unroll 1
       for (int grp = 0; grp < NGROUPS; ++grp) {
       uint32_t v[GROUP][32];
@@ -370,7 +387,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (lane == 0) mbar_arrive(tempty_bar + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (!in_range && p.colsum == nullptr) continue;
+      if (m_blk * BM + sub * 32 >= p.M && p.colsum == nullptr) continue;   // whole warp past the last row
 #pragma unroll
       for (int c = 0; c < GROUP; ++c) {
         const int ci = grp * GROUP + c;
@@ -410,14 +427,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = 0.0f;
         }
-        if (HAS_MASK && in_range) {
+        if (HAS_MASK && stage_mask && ncols == 32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = sr + 8 * j;
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if (warp_row0 + r < p.M)
+              val = __ldg(reinterpret_cast<const uint4*>(p.mask_src + (long long)(warp_row0 + r) * p.ldo + n0) + sseg);
+            *reinterpret_cast<uint4*>(st + r * STAGE_PITCH + sseg * 16) = val;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(st + lane * STAGE_PITCH + q * 16);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {       // bf16 > 0  <=>  sign clear and magnitude non-zero
+              const uint32_t lo16 = w[i] & 0xFFFFu, hi16 = w[i] >> 16;
+              if (lo16 == 0u || lo16 >= 0x8000u) x[8 * q + 2 * i] = 0.0f;
+              if (hi16 == 0u || hi16 >= 0x8000u) x[8 * q + 2 * i + 1] = 0.0f;
+            }
+          }
+          __syncwarp();
+        } else if (HAS_MASK && in_range) {
           float mk[32];
           load_bf16x32(mrow + n0, mvec && ncols == 32, ncols, mk);
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (!(mk[j] > 0.0f)) x[j] = 0.0f;
         }
-        if (!in_range) {
+        if (stage_out && ncols == 32) {
+#pragma unroll
+          for (int plane = 0; plane < 2; ++plane) {
+            if (plane == 1 && p.out_lo == nullptr) break;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(plane == 0 ? p.out : p.out_lo);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float y[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                y[i] = plane == 0 ? x[8 * q + i] : x[8 * q + i] - __bfloat162float(__float2bfloat16_rn(x[8 * q + i]));
+              *reinterpret_cast<uint4*>(st + lane * STAGE_PITCH + q * 16) =
+                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                             pack_bf16x2(y[6], y[7]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = sr + 8 * j;
+              if (warp_row0 + r < p.M)
+                *(reinterpret_cast<uint4*>(dst + (long long)(warp_row0 + r) * p.ldo + n0) + sseg) =
+                    *reinterpret_cast<const uint4*>(st + r * STAGE_PITCH + sseg * 16);
+            }
+            __syncwarp();
+          }
+        } else if (!in_range) {
           // nothing to store; the lane only takes part in the column-sum reduction below
         } else if (p.epi_atomic) {
           float* o = reinterpret_cast<float*>(p.out) + row_off + n0;

@@ -112,8 +112,12 @@ int lbx_logmel_f32_host(const float* sig_host, long long B, long long N, int sam
  * A/B are bf16 views: `rows` x `cols` with row pitch ld (elements, multiple of 8; may be SMALLER than cols: a causal
  * Conv1D with kernel k and stride s over NWC activations is the NT GEMM whose A view has cols = k*C_in and
  * lda = s*C_in on the zero-left-padded activation buffer — no im2col).
- * n_terms = 3 ("bf16x3"): a1/b1 hold the bf16 residual planes (x - bf16(x)); the kernel accumulates
- * a0.b0 + a0.b1 + a1.b0 for fp32-grade results (forward fp32 config).
+ * n_terms (1..3) accumulating passes over the contraction; pass t reads A plane term_a[t] (0: a0, 1: a1) shifted by
+ * term_a_row[t] rows, and B plane term_b[t] (0: b0, 1: b1).  Two uses:
+ *   "bf16x3": a1/b1 = bf16 residual planes (x - bf16(x)), passes (a0,b0) (a0,b1) (a1,b0): fp32-grade forward results;
+ *   gather-form data gradient of a strided conv (k > stride): output time tau = t*stride + j receives tap j of row t,
+ *   so every residue class of tau is ONE GEMM whose passes read dZ shifted by -i rows against the weights of tap
+ *   rho + i*stride (no read-modify-write pass).
  * Epilogue, per output element (m, n), in this order: + bias[n]; ReLU; zero unless mask_src[m*ldo+n] > 0;
  * then either atomicAdd into fp32 out (epi_atomic, required for k_splits > 1), or out (+)= x as fp32 / bf16
  * (plus out_lo = bf16 residual).  Rows with (m % rows_per_utt) >= valid_rows are stored as ZERO when rows_per_utt > 0 (they land on
@@ -125,6 +129,7 @@ typedef struct lbx_gemm_t {
   long long b_rows; int b_cols; long long ldb;
   int layout;
   int n_terms;
+  int term_a[3]; int term_b[3]; int term_a_row[3];
   int k_splits;
   int epi_atomic;
   int out_dtype;            /* LBX_F32 | LBX_BF16 */

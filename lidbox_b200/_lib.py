@@ -18,7 +18,8 @@ class GemmDesc(ctypes.Structure):
     _fields_ = [
         ("a0", c_void_p), ("a1", c_void_p), ("a_rows", c_ll), ("a_cols", c_int), ("lda", c_ll),
         ("b0", c_void_p), ("b1", c_void_p), ("b_rows", c_ll), ("b_cols", c_int), ("ldb", c_ll),
-        ("layout", c_int), ("n_terms", c_int), ("k_splits", c_int), ("epi_atomic", c_int), ("out_dtype", c_int),
+        ("layout", c_int), ("n_terms", c_int), ("term_a", c_int * 3), ("term_b", c_int * 3), ("term_a_row", c_int * 3),
+        ("k_splits", c_int), ("epi_atomic", c_int), ("out_dtype", c_int),
         ("out", c_void_p), ("out_lo", c_void_p), ("ldo", c_ll), ("bias", c_void_p), ("relu", c_int),
         ("rows_per_utt", c_int), ("valid_rows", c_int), ("mask_src", c_void_p), ("accumulate", c_int),
         ("tile_n", c_int), ("colsum", c_void_p), ("colsum_mod", c_int),

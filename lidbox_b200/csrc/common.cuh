@@ -39,6 +39,40 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
     lbx::count_launch();                                                                        \
   } while (0)
 
+// Programmatic dependent launch: every kernel of the library starts with LBX_PDL_SYNC() (wait for the previous
+// kernel's memory, then let the next kernel start its own launch/prologue) and is launched through launch_pdl().
+extern int g_use_pdl;
+#define LBX_PDL_SYNC()                                             \
+  do {                                                             \
+    asm volatile("griddepcontrol.wait;" ::: "memory");             \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#define LBX_LAUNCH_PDL(...)                                                                          \
+  do {                                                                                               \
+    cudaError_t _le = lbx::launch_pdl(__VA_ARGS__);                                                  \
+    if (_le != cudaSuccess)                                                                          \
+      return lbx::set_error(LBX_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_le),  \
+                            __FILE__, __LINE__);                                                     \
+    lbx::count_launch();                                                                             \
+  } while (0)
+
 static inline bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 static inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 

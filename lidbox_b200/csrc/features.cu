@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) logmel512_kernel(const Fused
   int* s_blen = s_bstart + p.n_mel;
   int* s_boff = s_blen + p.n_mel;
 
+  LBX_PDL_SYNC();
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, half = lane >> 4, l16 = lane & 15;
   const int L = p.frame_length, step = p.frame_step;
@@ -429,8 +430,7 @@ template <int MODE>
 static int launch_fused(const FusedParams& p, long long B, size_t smem, cudaStream_t st) {
   LBX_CUDA(cudaFuncSetAttribute(logmel512_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(p.T, FR), (unsigned)B);
-  logmel512_kernel<MODE><<<grid, FUSED_THREADS, smem, st>>>(p);
-  LBX_LAUNCH_CHECK();
+  LBX_LAUNCH_PDL(logmel512_kernel<MODE>, grid, dim3(FUSED_THREADS), smem, st, p);
   return LBX_OK;
 }
 

@@ -53,7 +53,9 @@ struct Cfg {
 struct GemmParams {
   int M, N, K;             // output rows, output cols, contraction length
   int layout;              // 0 NT, 1 TN
-  int n_terms;             // 1 or 3 (bf16x3)
+  int n_terms;             // accumulating passes over the contraction (1..3)
+  int term_a[3], term_b[3];   // which A / B tensor map each pass reads (0 or 1)
+  int term_arow[3];        // row offset added to the A coordinate of each pass (NT / NN layouts)
   int k_splits;            // split-K partitions (>= 1)
   int epi_atomic;          // 1: atomicAdd fp32 into out (split-K / gradient accumulation)
   int out_dtype;           // LBX_F32 / LBX_BF16
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapB0);
-    if (p.n_terms == 3) {
+    if (p.n_terms > 1) {
       tma_prefetch_desc(&mapA1);
       tma_prefetch_desc(&mapB1);
     }
@@ -264,15 +266,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
         const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int term = 0; term < p.n_terms; ++term) {
-          const CUtensorMap* mA = (term == 2) ? &mapA1 : &mapA0;
-          const CUtensorMap* mB = (term == 1) ? &mapB1 : &mapB0;
+          const CUtensorMap* mA = p.term_a[term] ? &mapA1 : &mapA0;
+          const CUtensorMap* mB = p.term_b[term] ? &mapB1 : &mapB0;
+          const int arow = p.term_arow[term];
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             unsigned char* sA = smem + (size_t)stage * STAGE_BYTES;
             unsigned char* sB = sA + A_BYTES;
             mbar_expect_tx(full_bar + stage, (uint32_t)STAGE_BYTES);
             if (!A_MN) {
-              tma_load_2d(mA, full_bar + stage, sA, kb * BK, m_blk * BM);
+              tma_load_2d(mA, full_bar + stage, sA, kb * BK, m_blk * BM + arow);
             } else {
 #pragma unroll
               for (int i = 0; i < BM / 64; ++i)
@@ -619,7 +622,6 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 }
 
 static int g_num_sms = 0;
-static int g_use_pdl = 1;
 
 }  // namespace lbx
 
@@ -628,7 +630,7 @@ using namespace lbx;
 extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   LBX_CHECK_ARG(g != nullptr, "NULL gemm descriptor");
   LBX_CHECK_ARG(g->layout >= 0 && g->layout <= 2, "layout must be 0 (NT), 1 (TN) or 2 (NN)");
-  LBX_CHECK_ARG(g->n_terms == 1 || g->n_terms == 3, "n_terms must be 1 or 3");
+  LBX_CHECK_ARG(g->n_terms >= 1 && g->n_terms <= 3, "n_terms must be 1, 2 or 3");
   LBX_CHECK_ARG(g->a_rows >= 0 && g->a_cols >= 0 && g->b_rows >= 0 && g->b_cols >= 0, "negative extent");
   GemmParams p{};
   p.layout = g->layout;
@@ -651,7 +653,12 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   if (p.M == 0 || p.N == 0) return LBX_OK;
   LBX_CHECK_ARG(p.K > 0, "empty contraction");
   LBX_CHECK_ARG(g->a0 && g->b0 && g->out, "NULL operand");
-  LBX_CHECK_ARG(g->n_terms == 1 || (g->a1 && g->b1), "bf16x3 needs the lo planes a1/b1");
+  for (int t = 0; t < g->n_terms; ++t) {
+    LBX_CHECK_ARG((g->term_a[t] == 0 || (g->term_a[t] == 1 && g->a1)) && (g->term_b[t] == 0 || (g->term_b[t] == 1 && g->b1)),
+                  "term %d selects an operand plane that was not given", t);
+    LBX_CHECK_ARG(g->term_a_row[t] == 0 || g->layout != 1, "row offsets are not available in the TN layout");
+    p.term_a[t] = g->term_a[t]; p.term_b[t] = g->term_b[t]; p.term_arow[t] = g->term_a_row[t];
+  }
   LBX_CHECK_ARG(g->lda % 8 == 0 && g->ldb % 8 == 0, "operand pitches must be multiples of 8 elements (16 bytes)");
   LBX_CHECK_ARG((reinterpret_cast<uintptr_t>(g->a0) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->b0) & 15) == 0,
                 "operands must be 16-byte aligned");
@@ -684,12 +691,9 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   const int boxA_rows = g->layout == 1 ? 64 : BM, boxB_rows = g->layout == 0 ? bn : 64;
   if ((rc = make_map(&mA0, g->a0, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
   if ((rc = make_map(&mB0, g->b0, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
-  if (g->n_terms == 3) {
-    if ((rc = make_map(&mA1, g->a1, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
-    if ((rc = make_map(&mB1, g->b1, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
-  } else {
-    mA1 = mA0; mB1 = mB0;
-  }
+  mA1 = mA0; mB1 = mB0;
+  if (g->a1 && (rc = make_map(&mA1, g->a1, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
+  if (g->b1 && (rc = make_map(&mB1, g->b1, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
   if (g_num_sms == 0) {
     int dev = 0, n = 0;
     LBX_CUDA(cudaGetDevice(&dev));
@@ -728,11 +732,5 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
 #undef LBX_GEMM_LAUNCH
   if (le != cudaSuccess) return set_error(LBX_ECUDA, "GEMM launch failed: %s", cudaGetErrorString(le));
   LBX_LAUNCH_CHECK();
-  return LBX_OK;
-}
-
-// programmatic dependent launch for the GEMMs (on by default; LBX_PDL=0 in the environment disables it)
-extern "C" int lbx_set_pdl(int enabled) {
-  g_use_pdl = enabled ? 1 : 0;
   return LBX_OK;
 }

@@ -7,6 +7,7 @@
 namespace lbx {
 
 std::atomic<long long> g_launch_count{0};
+int g_use_pdl = 1;
 
 char* error_buffer() {
   static thread_local char buf[512] = {0};
@@ -28,6 +29,12 @@ extern "C" {
 const char* lbx_last_error(void) { return lbx::error_buffer(); }
 int lbx_version(void) { return 100; }
 long long lbx_launch_count(void) { return lbx::g_launch_count.load(); }
+
+// programmatic dependent launch (on by default; LBX_PDL=0 in the environment of the Python host disables it)
+int lbx_set_pdl(int enabled) {
+  lbx::g_use_pdl = enabled ? 1 : 0;
+  return LBX_OK;
+}
 
 // lidbox/features/audio.py:185-189: tf.cast(tf.cast(sr, f32) * 1e-3 * tf.cast(ms, f32), i32); left-to-right fp32
 int lbx_ms_to_frames(int sample_rate, int ms) {

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
                                                        bf16* __restrict__ hi, bf16* __restrict__ lo, int rows_per_utt,
                                                        int row_off, int pitch, float drop_rate,
                                                        unsigned long long seed) {
+  LBX_PDL_SYNC();
   const long long total = B * T * (long long)pitch;
   const float keep_scale = drop_rate > 0.0f ? 1.0f / (1.0f - drop_rate) : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(128) logsoftmax_xent_kernel(const float* __res
                                                              long long B, int n, float* __restrict__ logp,
                                                              float* __restrict__ loss, bf16* __restrict__ dlogits,
                                                              int dl_pitch, float grad_scale, float* __restrict__ dbias) {
+  LBX_PDL_SYNC();
   const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(128) ap_loss_kernel(const float* __restrict__ 
                                                      float* __restrict__ grad_f32, bf16* __restrict__ grad_bf16,
                                                      int g_pitch, const float* __restrict__ gloss, float grad_scale,
                                                      float* __restrict__ dbias) {
+  LBX_PDL_SYNC();
   const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 // step counter and bias-corrected learning rate live in device memory so that a captured CUDA graph of the whole
 // training step advances them on every replay
 __global__ void adam_tick_kernel(long long* step, float* lr_t, float lr, float beta1, float beta2) {
+  LBX_PDL_SYNC();
   const long long t = *step + 1;
   *step = t;
   *lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t)));
@@ -278,6 +282,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float
                                                   const float* __restrict__ lr_t_ptr, float beta1, float beta2,
                                                   float eps, float grad_scale, uint2* __restrict__ p_bf16,
                                                   int zero_grads) {
+  LBX_PDL_SYNC();
   const float lr_t = *lr_t_ptr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
@@ -332,6 +337,7 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_bf16v_kernel(const bf16* _
                                                                   int C, int pitch, float clip_min,
                                                                   float* __restrict__ out, float* __restrict__ var_raw,
                                                                   bf16* __restrict__ out_hi) {
+  LBX_PDL_SYNC();
   __shared__ float red[8][32][9];
   const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
   const int cv = blockIdx.x * 32 + lane;                    // 8-channel vector index
@@ -406,6 +412,7 @@ __global__ void __launch_bounds__(256) stats_pool_bwd_bf16v_kernel(const bf16* _
                                                                   const float* __restrict__ var_raw,
                                                                   float* __restrict__ gpool, bf16* __restrict__ dz,
                                                                   float* __restrict__ dbias, int zero_gpool) {
+  LBX_PDL_SYNC();
   __shared__ float red[8][32][9];
   const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
   const int cv = blockIdx.x * 32 + lane;
@@ -466,6 +473,161 @@ __global__ void __launch_bounds__(256) stats_pool_bwd_bf16v_kernel(const bf16* _
   }
 }
 
+
+// Register-cached variants for short time axes (T <= 8 * MAXR): every thread issues all of its row loads up front
+// (memory-level parallelism instead of a dependent load->add loop) and the forward pass reads the activations once.
+template <int MAXR>
+__global__ void __launch_bounds__(256) stats_pool_fwd_bf16r_kernel(const bf16* __restrict__ y, int rows_per_utt, int T,
+                                                                  int C, int pitch, float clip_min,
+                                                                  float* __restrict__ out, float* __restrict__ var_raw,
+                                                                  bf16* __restrict__ out_hi) {
+  LBX_PDL_SYNC();
+  __shared__ float red[8][32][9];
+  const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int cv = blockIdx.x * 32 + lane;
+  const int c0 = cv * 8;
+  const long long b = blockIdx.y;
+  const bool active = c0 < pitch;
+  const uint4* base = reinterpret_cast<const uint4*>(y + b * rows_per_utt * (long long)pitch) + cv;
+  const int p8 = pitch >> 3;
+  uint4 raw[MAXR];
+#pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    const int t = tl + 8 * r;
+    raw[r] = (active && t < T) ? __ldg(base + (long long)t * p8) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    float f[8];
+    unpack_bf16x8(raw[r], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[tl][lane][i] = s[i];
+  __syncthreads();
+  float mean[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += red[j][lane][i];
+    mean[i] = a / (float)T;
+  }
+  __syncthreads();
+  float q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    if (tl + 8 * r < T) {
+      float f[8];
+      unpack_bf16x8(raw[r], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = f[i] - mean[i];
+        q[i] = fmaf(d, d, q[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[tl][lane][i] = q[i];
+  __syncthreads();
+  if (tl == 0 && active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      if (c >= C) break;
+      float var = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) var += red[j][lane][i];
+      var /= (float)T;
+      const float sd = sqrtf(fminf(fmaxf(var, clip_min), 3.402823466e+38f));
+      out[b * 2 * C + c] = mean[i];
+      out[b * 2 * C + C + c] = sd;
+      if (var_raw) var_raw[b * C + c] = var;
+      if (out_hi) {
+        out_hi[b * 2 * C + c] = __float2bfloat16_rn(mean[i]);
+        out_hi[b * 2 * C + C + c] = __float2bfloat16_rn(sd);
+      }
+    }
+  }
+}
+
+template <int MAXR>
+__global__ void __launch_bounds__(256) stats_pool_bwd_bf16r_kernel(const bf16* __restrict__ y, int rows_per_utt, int T,
+                                                                  int C, int pitch, float clip_min,
+                                                                  const float* __restrict__ pooled,
+                                                                  const float* __restrict__ var_raw,
+                                                                  float* __restrict__ gpool, bf16* __restrict__ dz,
+                                                                  float* __restrict__ dbias, int zero_gpool) {
+  LBX_PDL_SYNC();
+  __shared__ float red[8][32][9];
+  const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int cv = blockIdx.x * 32 + lane;
+  const int c0 = cv * 8;
+  const long long b = blockIdx.y;
+  const bool active = c0 < pitch;
+  const int p8 = pitch >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(y + b * rows_per_utt * (long long)pitch) + cv;
+  uint4* dst = reinterpret_cast<uint4*>(dz + b * rows_per_utt * (long long)pitch) + cv;
+  uint4 raw[MAXR];
+#pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    const int t = tl + 8 * r;
+    raw[r] = (active && t < T) ? __ldg(src + (long long)t * p8) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float mean[8], gm[8], gs[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    acc[i] = 0.0f;
+    if (active && c < C) {
+      mean[i] = pooled[b * 2 * C + c];
+      const float sd = pooled[b * 2 * C + C + c];
+      gm[i] = gpool[b * 2 * C + c] / (float)T;
+      gs[i] = var_raw[b * C + c] > clip_min ? gpool[b * 2 * C + C + c] / ((float)T * sd) : 0.0f;
+    } else {
+      mean[i] = gm[i] = gs[i] = 0.0f;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    const int t = tl + 8 * r;
+    if (active && t < T) {
+      float f[8], g[8];
+      unpack_bf16x8(raw[r], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g[i] = f[i] > 0.0f ? fmaf(gs[i], f[i] - mean[i], gm[i]) : 0.0f;
+        acc[i] += g[i];
+      }
+      dst[(long long)t * p8] = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
+    }
+  }
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[tl][lane][i] = acc[i];
+  }
+  __syncthreads();
+  if (tl == 0 && active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      if (c >= C) break;
+      if (dbias != nullptr) {
+        float a = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += red[j][lane][i];
+        atomicAdd(dbias + c, a);
+      }
+      if (zero_gpool) {
+        gpool[b * 2 * C + c] = 0.0f;
+        gpool[b * 2 * C + C + c] = 0.0f;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // finishing pass of a split-K dense layer: acc (fp32, atomically accumulated by the GEMM) -> + bias, ReLU, ReLU-backward
 // mask, bf16 hi/lo and/or fp32 outputs, column sums (bias gradient of the layer below); re-zeroes acc for its next use
@@ -476,6 +638,7 @@ __global__ void __launch_bounds__(256) dense_finish_kernel(float* __restrict__ a
                                                           bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int ld_out,
                                                           float* __restrict__ out_f32, int ld_f32,
                                                           float* __restrict__ colsum, int zero_acc) {
+  LBX_PDL_SYNC();
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + cl;
@@ -527,9 +690,8 @@ int lbx_pack_rows_bf16(const float* x, long long B, int T, int F, void* hi, void
   LBX_CHECK_ARG(drop_rate >= 0.0f && drop_rate < 1.0f, "drop_rate must be in [0, 1)");
   if (B * T == 0) return LBX_OK;
   LBX_CHECK_ARG(x && hi, "NULL pointer argument");
-  pack_rows_kernel<<<grid_for(B * T * (long long)pitch, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, B, T, F, (bf16*)hi, (bf16*)lo, rows_per_utt, row_off, pitch, drop_rate, seed);
-  LBX_LAUNCH_CHECK();
+  LBX_LAUNCH_PDL(pack_rows_kernel, dim3(grid_for(B * T * (long long)pitch, 256)), dim3(256), 0, (cudaStream_t)stream, x, B,
+                 T, F, (bf16*)hi, (bf16*)lo, rows_per_utt, row_off, pitch, drop_rate, seed);
   return LBX_OK;
 }
 
@@ -545,8 +707,18 @@ int lbx_stats_pool_fwd(const void* y, int y_dtype, long long B, int rows_per_utt
                                                                          clip_min, out, var_raw, (bf16*)out_hi,
                                                                          (bf16*)out_lo);
   else if (y_dtype == LBX_BF16 && out_lo == nullptr && pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
-    stats_pool_fwd_bf16v_kernel<<<dim3((unsigned)ceil_div(pitch / 8, 32), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)y, rows_per_utt, T, C, pitch, clip_min, out, var_raw, (bf16*)out_hi);
+  {
+    if (T <= 48) {
+      LBX_LAUNCH_PDL(stats_pool_fwd_bf16r_kernel<6>, dim3((unsigned)ceil_div(pitch / 8, 32), (unsigned)B), dim3(256), 0,
+                     (cudaStream_t)stream, (const bf16*)y, rows_per_utt, T, C, pitch, clip_min, out, var_raw,
+                     (bf16*)out_hi);
+      return LBX_OK;
+    }
+    LBX_LAUNCH_PDL(stats_pool_fwd_bf16v_kernel, dim3((unsigned)ceil_div(pitch / 8, 32), (unsigned)B), dim3(256), 0,
+                   (cudaStream_t)stream, (const bf16*)y, rows_per_utt, T, C, pitch, clip_min, out, var_raw,
+                   (bf16*)out_hi);
+    return LBX_OK;
+  }
   else if (y_dtype == LBX_BF16)
     stats_pool_fwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, rows_per_utt, T, C, pitch,
                                                                         clip_min, out, var_raw, (bf16*)out_hi,
@@ -567,10 +739,13 @@ int lbx_stats_pool_bwd(const void* y_bf16, long long B, int rows_per_utt, int T,
   LBX_CHECK_ARG(((reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(dz_bf16)) & 15) == 0,
                 "activation buffers must be 16-byte aligned");
   dim3 grid((unsigned)ceil_div(pitch / 8, 32), (unsigned)B);
-  stats_pool_bwd_bf16v_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y_bf16, rows_per_utt, T, C, pitch,
-                                                                      clip_min, pooled, var_raw, gpool, (bf16*)dz_bf16,
-                                                                      dbias, zero_gpool);
-  LBX_LAUNCH_CHECK();
+  if (T <= 48) {
+    LBX_LAUNCH_PDL(stats_pool_bwd_bf16r_kernel<6>, grid, dim3(256), 0, (cudaStream_t)stream, (const bf16*)y_bf16,
+                   rows_per_utt, T, C, pitch, clip_min, pooled, var_raw, gpool, (bf16*)dz_bf16, dbias, zero_gpool);
+    return LBX_OK;
+  }
+  LBX_LAUNCH_PDL(stats_pool_bwd_bf16v_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const bf16*)y_bf16, rows_per_utt, T,
+                 C, pitch, clip_min, pooled, var_raw, gpool, (bf16*)dz_bf16, dbias, zero_gpool);
   return LBX_OK;
 }
 
@@ -581,9 +756,8 @@ int lbx_logsoftmax_xent(const float* logits, const int* labels, long long B, int
   LBX_CHECK_ARG(logits, "NULL logits");
   LBX_CHECK_ARG(!(loss || dlogits_bf16) || labels, "labels are required for the loss / gradient");
   LBX_CHECK_ARG(!dlogits_bf16 || dl_pitch >= n, "dl_pitch too small");
-  logsoftmax_xent_kernel<<<(unsigned)ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(
-      logits, labels, B, n, logp, loss, (bf16*)dlogits_bf16, dl_pitch, grad_scale, dbias);
-  LBX_LAUNCH_CHECK();
+  LBX_LAUNCH_PDL(logsoftmax_xent_kernel, dim3((unsigned)ceil_div(B, 4)), dim3(128), 0, (cudaStream_t)stream, logits, labels,
+                 B, n, logp, loss, (bf16*)dlogits_bf16, dl_pitch, grad_scale, dbias);
   return LBX_OK;
 }
 
@@ -597,11 +771,9 @@ int lbx_ap_loss(const float* h, const int* labels, long long B, int D, int N, fl
   if (B == 0) return LBX_OK;
   LBX_CHECK_ARG(h && labels, "NULL pointer argument");
   LBX_CHECK_ARG(!(grad_f32 || grad_bf16) || g_pitch >= D, "g_pitch too small");
-  ap_loss_kernel<<<(unsigned)ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(h, labels, B, D, N, delta_weight, normalize,
-                                                                             z_out, theta_out, loss, grad_f32,
-                                                                             (bf16*)grad_bf16, g_pitch, gloss,
-                                                                             grad_scale, dbias);
-  LBX_LAUNCH_CHECK();
+  LBX_LAUNCH_PDL(ap_loss_kernel, dim3((unsigned)ceil_div(B, 4)), dim3(128), 0, (cudaStream_t)stream, h, labels, B, D, N,
+                 delta_weight, normalize, z_out, theta_out, loss, grad_f32, (bf16*)grad_bf16, g_pitch, gloss,
+                 grad_scale, dbias);
   return LBX_OK;
 }
 
@@ -627,12 +799,10 @@ int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, 
                   reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(params_bf16) & 7) == 0,
                 "flat buffers must be 16-byte aligned");
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, lr_t_dev, lr, beta1, beta2);
-  LBX_LAUNCH_CHECK();
-  adam_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((float4*)params, (float4*)grads, (float4*)m,
-                                                                      (float4*)v, n / 4, lr_t_dev, beta1, beta2, eps,
-                                                                      grad_scale, (uint2*)params_bf16, zero_grads);
-  LBX_LAUNCH_CHECK();
+  LBX_LAUNCH_PDL(adam_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev, lr_t_dev, lr, beta1, beta2);
+  LBX_LAUNCH_PDL(adam_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, (float4*)params,
+                 (float4*)grads, (float4*)m, (float4*)v, n / 4, (const float*)lr_t_dev, beta1, beta2, eps, grad_scale,
+                 (uint2*)params_bf16, zero_grads);
   return LBX_OK;
 }
 
@@ -643,10 +813,8 @@ int lbx_dense_finish(float* acc, long long M, int N, int ld_acc, const float* bi
   if (M == 0) return LBX_OK;
   LBX_CHECK_ARG(acc != nullptr, "NULL accumulator");
   dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 16));
-  dense_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc, M, N, ld_acc, bias, relu, (const bf16*)mask_src,
-                                                              ld_mask, (bf16*)out_hi, (bf16*)out_lo, ld_out, out_f32,
-                                                              ld_f32, colsum, zero_acc);
-  LBX_LAUNCH_CHECK();
+  LBX_LAUNCH_PDL(dense_finish_kernel, grid, dim3(256), 0, (cudaStream_t)stream, acc, M, N, ld_acc, bias, relu,
+                 (const bf16*)mask_src, ld_mask, (bf16*)out_hi, (bf16*)out_lo, ld_out, out_f32, ld_f32, colsum, zero_acc);
   return LBX_OK;
 }
 

@@ -452,17 +452,29 @@ class XVector:
             below = self.layers[L - 1]
             if not below["relu"]:
                 raise NotImplementedError("linear frame layers are not supported in the backward pass")
-            first = min(k, s)                        # taps [0, first) tile the time axis without overlap
-            ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, first * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
-                     a_off=dz_off, b_off=ly["w_off"], mask_src=bufs["X"][L], colsum=g, colsum_off=below["b_off"],
-                     colsum_mod=c)
-            j = first
-            while j < k:                             # remaining taps overlap the next row: accumulate pass(es)
-                cnt = min(s, k - j)
-                ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, cnt * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
-                         a_off=dz_off, b_off=ly["w_off"] + j * c * ly["ldw"], out_off=j * c, mask_src=bufs["X"][L],
-                         mask_off=j * c, accumulate=True, colsum=g, colsum_off=below["b_off"], colsum_mod=c)
-                j += cnt
+            if k <= s:
+                # taps tile the time axis without overlap: one GEMM writes all k*C_in columns of every view row
+                ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, k * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
+                         a_off=dz_off, b_off=ly["w_off"], mask_src=bufs["X"][L], colsum=g, colsum_off=below["b_off"],
+                         colsum_mod=c)
+            else:
+                # gather form: padded output time tau = t*s + j.  For every residue rho = tau mod s one GEMM whose
+                # accumulating passes read dZ shifted by -i rows against the weights of tap rho + i*s
+                if -(-k // s) > 3:
+                    raise NotImplementedError("kernel_size > 3 * strides in the backward pass")
+                for rho in range(s):
+                    taps = list(range(rho, k, s))
+                    if not taps:
+                        continue
+                    terms = [(0, min(i, 1), -i) for i in range(len(taps))]
+                    if len(taps) == 3:
+                        raise NotImplementedError("three overlapping taps per residue class")
+                    b1 = self.w16 if len(taps) > 1 else None
+                    ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
+                             a_off=dz_off, b_off=ly["w_off"] + taps[0] * c * ly["ldw"], b1=b1,
+                             b1_off=ly["w_off"] + taps[-1] * c * ly["ldw"], terms=terms, out_off=rho * c,
+                             mask_src=bufs["X"][L], mask_off=rho * c, colsum=g, colsum_off=below["b_off"],
+                             colsum_mod=c)
         if side is not None:
             ev = torch.cuda.Event()
             ev.record(side)

@@ -221,6 +221,8 @@ class XVectorTrainWorkload:
                             % (self.label, self.B, self.sec, self.n_classes, self.loss, self._act_mb()),
                 "batch_per_gpu": self.B, "global_batch": self.B * self.world, "seconds": self.sec,
                 "frames_per_utt": self.T, "cuda_graph": self.use_graph,
+                "feature_prefetch": "log-mel of batch i+1 runs on a second stream during step i (one log-mel + one "
+                                    "training step per replay)" if self.pipelined else "inline",
                 "parallelism": "dp%d (NCCL all-reduce of the 18 MB fp32 gradient)" % self.world}
 
     def _act_mb(self):
@@ -231,20 +233,33 @@ class XVectorTrainWorkload:
         from lidbox_b200.models import xvector
         self.audio, self.device = audio, device
         self.x_host, y = class_signals(self.B, self.N, self.n_classes, 1234 + self.rank, pin=True)
-        self.x = self.x_host.to(device)
+        # two signal buffers and two feature buffers: while the model trains on the features of batch i, the log-mel
+        # of batch i+1 runs on a second stream (the prefetch a tf.data input pipeline does), and in the end-to-end
+        # path the H2D copy of batch i+2 runs on a copy stream.  Every replay = one log-mel + one training step.
+        self.xs = [self.x_host.to(device), self.x_host.to(device)]
+        self.x = self.xs[0]
         self.y = y.to(device)
-        self.feats = torch.empty((self.B, self.T, 40), dtype=torch.float32, device=device)
+        self.fbuf = [torch.empty((self.B, self.T, 40), dtype=torch.float32, device=device) for _ in range(2)]
+        self.feats = self.fbuf[0]
         self.model = xvector.create((self.T, 40), self.n_out, precision="bf16", head=self.head, seed=0)
         self.model.configure_optimizer(lr=1e-3)
-        self.loss_host = torch.empty((self.B,), dtype=torch.float32).pin_memory()
         self.pg = self.dist.group.WORLD if self.dist is not None else None
         self.kw = dict(ap_classes=self.n_classes) if self.loss == "ap" else {}
-        self.graphed = None
-        if self.use_graph:
-            self.graphed = xvector.GraphedTrainStep(self.model, self.feats, self.y, loss=self.loss,
-                                                    process_group=self.pg, pre=self._features, **self.kw)
-        # end-to-end path: two input buffers and two graphs, so the H2D copy of batch i+1 (copy stream) overlaps the
-        # training step of batch i (compute stream); every batch is still copied from pinned host memory
+        self.pipelined = os.environ.get("LBX_BENCH_PIPELINE", "1") != "0"
+        self.i = 0
+        self.steps = []
+        self.audio.logmelspectrograms(self.xs[0], SR, out=self.fbuf[0])          # prime the pipeline
+        for k in range(2):
+            nxt = (lambda k=k: self.audio.logmelspectrograms(self.xs[1 - k], SR, out=self.fbuf[1 - k]))
+            inline = (lambda k=k: self.audio.logmelspectrograms(self.xs[k], SR, out=self.fbuf[k]))
+            if self.use_graph:
+                self.steps.append(xvector.GraphedTrainStep(
+                    self.model, self.fbuf[k], self.y, loss=self.loss, process_group=self.pg,
+                    pre=None if self.pipelined else inline, concurrent=nxt if self.pipelined else None, **self.kw))
+            else:
+                self.steps.append(lambda inline=inline: self.model.train_step(inline(), self.y, loss=self.loss,
+                                                                              process_group=self.pg, **self.kw))
+        self.graphed = self.steps[0] if self.use_graph else None
         self.e2e = None
 
     def _features(self):
@@ -257,56 +272,51 @@ class XVectorTrainWorkload:
         return self.B * self.sec
 
     def step(self):
-        return self.graphed() if self.graphed is not None else self._eager_step()
+        out = self.steps[self.i % 2]()
+        self.i += 1
+        return out
 
     def launches_per_step(self):
         return self.graphed.kernels_per_step if self.graphed is not None else None
 
     def _setup_e2e(self):
-        from lidbox_b200.models import xvector
         dev = self.device
-        e = {"x": [self.x, torch.empty_like(self.x)], "graphs": [], "copy": torch.cuda.Stream(device=dev), "i": 0,
-             "h2d_done": [torch.cuda.Event(), torch.cuda.Event()], "step_done": [torch.cuda.Event(), torch.cuda.Event()],
+        e = {"copy": torch.cuda.Stream(device=dev),
+             "h2d_done": [torch.cuda.Event(), torch.cuda.Event()], "step_done": torch.cuda.Event(),
              "loss_host": [torch.empty((self.B,), dtype=torch.float32).pin_memory() for _ in range(2)]}
-        for k in range(2):
-            if k == 0 and self.graphed is not None:
-                e["graphs"].append(self.graphed)
-                continue
-            xk = e["x"][k]
-            pre = (lambda xk=xk: self.audio.logmelspectrograms(xk, SR, out=self.feats))
-            if self.use_graph:
-                e["graphs"].append(xvector.GraphedTrainStep(self.model, self.feats, self.y, loss=self.loss,
-                                                            process_group=self.pg, pre=pre, **self.kw))
-            else:
-                e["graphs"].append(lambda pre=pre: self.model.train_step(pre(), self.y, loss=self.loss,
-                                                                         process_group=self.pg, **self.kw))
         cur = torch.cuda.current_stream(dev)
-        for k in range(2):
-            e["step_done"][k].record(cur)
-        # prime: the first batch is copied before the pipeline starts
+        torch.cuda.synchronize(dev)
+        # prime: batch 0 -> xs[k0] + its features, batch 1 -> xs[1-k0]
+        k0 = self.i % 2
+        self.xs[k0].copy_(self.x_host, non_blocking=True)
+        self.audio.logmelspectrograms(self.xs[k0], SR, out=self.fbuf[k0])
         with torch.cuda.stream(e["copy"]):
-            e["x"][0].copy_(self.x_host, non_blocking=True)
-            e["h2d_done"][0].record(e["copy"])
+            e["copy"].wait_stream(cur)
+            self.xs[1 - k0].copy_(self.x_host, non_blocking=True)
+            e["h2d_done"][1 - k0].record(e["copy"])
+        e["step_done"].record(cur)
         self.e2e = e
 
     def step_e2e(self):
-        """One step of the public-API pipeline: batch i trains from device buffer i%2 while batch i+1 is copied from
-        pinned host memory into buffer (i+1)%2 on the copy stream; the per-sample losses of batch i are read back."""
+        """One step of the public-API pipeline with the batch in pinned HOST memory: replay k trains on the features
+        of batch i (buffer k) and extracts the features of batch i+1 from device buffer 1-k, while batch i+2 is copied
+        host->device into buffer k on the copy stream; the per-sample losses of batch i are copied back."""
         if self.e2e is None:
             self._setup_e2e()
         e = self.e2e
-        k, nk = e["i"] % 2, (e["i"] + 1) % 2
+        k = self.i % 2
         cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(e["h2d_done"][1 - k])                  # signals of batch i+1 are on the device
+        prev_done = e["step_done"]
+        losses = self.step()
+        e["step_done"] = torch.cuda.Event()
+        e["step_done"].record(cur)
         with torch.cuda.stream(e["copy"]):
-            e["copy"].wait_event(e["step_done"][nk])          # buffer nk is free once the step that read it is done
-            e["x"][nk].copy_(self.x_host, non_blocking=True)
-            e["h2d_done"][nk].record(e["copy"])
-        cur.wait_event(e["h2d_done"][k])
-        losses = e["graphs"][k]()
-        e["step_done"][k].record(cur)
+            e["copy"].wait_event(prev_done)                    # buffer k was last read by the previous replay
+            self.xs[k].copy_(self.x_host, non_blocking=True)
+            e["h2d_done"][k].record(e["copy"])
         e["loss_host"][k].copy_(losses, non_blocking=True)
-        e["i"] += 1
-        if e["i"] % 2 == 0:
+        if k == 1:
             cur.synchronize()                                  # host reads the losses of the last two steps
 
     def e2e_bytes(self):

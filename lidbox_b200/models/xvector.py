@@ -514,13 +514,30 @@ class GraphedTrainStep:
     CUDA graph and replayed: the ~60 kernel launches of a step cost one host call.  Inputs are read from the static
     tensors given at construction; copy new data into them before calling."""
 
-    def __init__(self, model, x_static, y_static, loss="xent", process_group=None, pre=None, warmup=3, **kw):
+    def __init__(self, model, x_static, y_static, loss="xent", process_group=None, pre=None, concurrent=None,
+                 warmup=3, **kw):
+        """pre: optional callable producing the features inline (same stream, before the step).
+        concurrent: optional callable enqueued on a second stream alongside the step and joined at its end — e.g. the
+        feature extraction of the NEXT batch (input-pipeline prefetch), which is independent of this step."""
         self.model, self.x, self.y = model, x_static, y_static
         lib = _lib.lib()
+        aux = torch.cuda.Stream(device=model.device) if concurrent is not None else None
 
         def body():
+            if aux is not None:
+                cur = torch.cuda.current_stream(model.device)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                aux.wait_event(ev)
+                with torch.cuda.stream(aux):
+                    concurrent()
             feats = pre() if pre is not None else self.x
-            return model.train_step(feats, self.y, loss=loss, process_group=process_group, **kw)
+            out = model.train_step(feats, self.y, loss=loss, process_group=process_group, **kw)
+            if aux is not None:
+                ev2 = torch.cuda.Event()
+                ev2.record(aux)
+                torch.cuda.current_stream(model.device).wait_event(ev2)
+            return out
 
         side = torch.cuda.Stream(device=model.device)
         side.wait_stream(torch.cuda.current_stream(model.device))

@@ -91,11 +91,12 @@ __device__ __forceinline__ float hann_value(int i, int L) {
 // ------------------------------------------------------------------------------------------------------------
 // fused 512-point kernel
 // ------------------------------------------------------------------------------------------------------------
-constexpr int FR = 32;           // frames per CTA (= lanes of the mel phase)
+constexpr int FR = 16;           // frames per CTA: 8 warps x 2 half-warps, one frame per half-warp, a single pass
 constexpr int FUSED_THREADS = 256;
-constexpr int P_STRIDE = 257;    // odd: lanes=frames reads are conflict-free; 16*257 % 32 == 16: half-warp writes too
+constexpr int P_STRIDE = 257;    // odd: the lanes = frames reads of the mel phase are conflict-free
 constexpr int SCR_ROW = 17;      // float2 per transpose row (16 + 1 pad)
 constexpr int SCR_FLOATS = 8 * 2 * 16 * SCR_ROW * 2;
+constexpr int P_FLOATS = (FR * P_STRIDE + 3) & ~3;
 
 struct FusedParams {
   const float* sig;
@@ -104,8 +105,7 @@ struct FusedParams {
   long long T;
   int frame_length;
   int frame_step;
-  int sig_smem;        // floats reserved for the staged signal run (multiple of 4, >= (FR-1)*step + L + 34)
-  int pw_mode;
+  int sig_smem;        // floats reserved for the staged signal run (multiple of 4, >= (FR-1)*step + 512 + 2)
   float power;
   // mel (MODE 1)
   int n_mel;
@@ -118,21 +118,29 @@ struct FusedParams {
   float eps;
 };
 
-template <int MODE>  // 0: power spectrogram [B,T,257]; 1: (log-)mel [B,T,n_mel]
-__global__ void __launch_bounds__(FUSED_THREADS, 2) logmel512_kernel(const FusedParams p) {
+template <int PW>
+__device__ __forceinline__ float power_of(float mag2, float power) {
+  if (PW == 2) return mag2;                      // |X|^2
+  if (PW == 1) return sqrtf(mag2);               // |X|
+  return powf(sqrtf(mag2), power);               // pow(abs(S), power), audio.py:230
+}
+
+// MODE 0: power spectrogram [B,T,257]; MODE 1: (log-)mel [B,T,n_mel].  PW: 2 -> |X|^2, 1 -> |X|, 0 -> generic power.
+template <int MODE, int PW>
+__global__ void __launch_bounds__(FUSED_THREADS, 3) logmel512_kernel(const FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_sig = reinterpret_cast<float*>(smem_raw);
-  float* s_win = s_sig + p.sig_smem;                       // 512
-  float2* s_tw = reinterpret_cast<float2*>(s_win + 512);   // 256 entries of W256^e
-  float* s_P = reinterpret_cast<float*>(s_tw + 256);       // FR * P_STRIDE
-  float2* s_scr = reinterpret_cast<float2*>(s_P + FR * P_STRIDE);
-  float* s_out = reinterpret_cast<float*>(s_scr);          // aliases the transpose scratch (dead by then)
+  float* s_win = s_sig + p.sig_smem;                         // 512 (zero beyond frame_length)
+  float2* s_twA = reinterpret_cast<float2*>(s_win + 512);    // [q][l]: W256^{l * KIDX(q)}, 256 entries
+  float2* s_w512 = s_twA + 256;                              // W512^k, k = 0..255
+  float* s_P = reinterpret_cast<float*>(s_w512 + 256);       // FR * P_STRIDE
+  float2* s_scr = reinterpret_cast<float2*>(s_P + P_FLOATS);
+  float* s_out = reinterpret_cast<float*>(s_scr);            // aliases the transpose scratch (dead by then)
   float* s_bw = reinterpret_cast<float*>(s_scr) + SCR_FLOATS;
   int* s_bstart = reinterpret_cast<int*>(s_bw + ((p.n_packed + 3) & ~3));
   int* s_blen = s_bstart + p.n_mel;
   int* s_boff = s_blen + p.n_mel;
 
-  LBX_PDL_SYNC();
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, half = lane >> 4, l16 = lane & 15;
   const int L = p.frame_length, step = p.frame_step;
@@ -140,10 +148,26 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) logmel512_kernel(const Fused
   const int b = blockIdx.y;
   const int nf = (int)min((long long)FR, p.T - t0);
 
-  // ---- stage the sample run, window, twiddles and mel tables ----
+  // ---- tables that do not depend on earlier kernels: window and twiddles ----
+  for (int i = tid; i < 512; i += FUSED_THREADS) {
+    float w = 0.0f;
+    if (i < L) {
+      // periodic Hann, tf.signal.hann_window(L, periodic=True): n = L + (1 - L%2) - 1; cos(2 pi i / n) via cospi
+      const float n = (float)(L + (1 - (L & 1)) - 1);
+      w = L == 1 ? 1.0f : 0.5f - 0.5f * cospif(2.0f * (float)i / n);
+    }
+    s_win[i] = w;
+  }
+  {
+    float sn, cs;
+    sincospif((float)tid * (1.0f / 256.0f), &sn, &cs);       // W512^tid = exp(-2 pi i tid / 512)
+    s_w512[tid] = make_float2(cs, -sn);
+  }
+  LBX_PDL_SYNC();
+  // ---- stage the sample run and the mel tables ----
   {
     const long long s0 = t0 * step;
-    const int n_valid = (nf - 1) * step + L;                // samples this CTA actually needs (all in range)
+    const int n_valid = (nf - 1) * step + L;                  // samples this CTA actually needs (all in range)
     const float* g = p.sig + (long long)b * p.N + s0;
     if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
       const int n4 = n_valid >> 2;
@@ -155,12 +179,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) logmel512_kernel(const Fused
       for (int i = tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = __ldg(g + i);
     }
     for (int i = n_valid + tid; i < p.sig_smem; i += FUSED_THREADS) s_sig[i] = 0.0f;
-    for (int i = tid; i < 512; i += FUSED_THREADS) s_win[i] = (i < L) ? hann_value(i, L) : 0.0f;
-    {
-      float s, c;
-      sincospif((float)tid * (1.0f / 128.0f), &s, &c);     // W256^tid = exp(-2 pi i tid / 256)
-      s_tw[tid] = make_float2(c, -s);
-    }
     if (MODE == 1) {
       for (int i = tid; i < p.n_packed; i += FUSED_THREADS) s_bw[i] = __ldg(p.band_w + i);
       for (int i = tid; i < p.n_mel; i += FUSED_THREADS) {
@@ -171,103 +189,87 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) logmel512_kernel(const Fused
     }
   }
   __syncthreads();
-
-  // per-lane twiddles: twA[p] = W256^{l16 * KIDX(p)} (between the two radix-16 steps), wk1 = W512^{l16}
-  float2 twA[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) twA[q] = s_tw[(l16 * KIDX(q)) & 255];
-  float2 wk1;
   {
-    float s, c;
-    sincospif((float)l16 * (1.0f / 256.0f), &s, &c);
-    wk1 = make_float2(c, -s);
+    // twiddles between the two radix-16 steps, stored so that a half-warp reads 16 consecutive entries:
+    // s_twA[q*16 + l] = W256^{l * KIDX(q)};  W256^e = W512^{2e} (e < 128) = -W512^{2e-256} (e >= 128)
+    const int q = tid >> 4, l = tid & 15;
+    const int e = (l * KIDX(q)) & 255;
+    const float2 w = e < 128 ? s_w512[2 * e] : s_w512[2 * e - 256];
+    s_twA[tid] = e < 128 ? w : make_float2(-w.x, -w.y);
   }
+  __syncthreads();
 
+  const int f = half * 8 + warp;                              // frame within the CTA's run
+  const float* fs = s_sig + f * step;
   float2* my_scr = s_scr + (warp * 2 + half) * 16 * SCR_ROW;
-  const int nrows = (L + 31) >> 5;                          // rows of 32 samples that hold non-zero window
-  const bool even_step = (step & 1) == 0;
-
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int f = half * 16 + pass * 8 + warp;             // frame within the CTA's run
-    const float* fs = s_sig + f * step;
-    float2 v[16];
-    // z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1],  n = 16 n1 + l16
-    if (even_step) {
+  float2 v[16];
+  // z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1],  n = 16 n1 + l16 (rows beyond the window multiply by zero)
+  if ((step & 1) == 0) {
 #pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) {
-        if (n1 < nrows) {
-          const float2 x = *reinterpret_cast<const float2*>(fs + 32 * n1 + 2 * l16);
-          const float2 w = *reinterpret_cast<const float2*>(s_win + 32 * n1 + 2 * l16);
-          v[n1] = make_float2(x.x * w.x, x.y * w.y);
-        } else {
-          v[n1] = make_float2(0.0f, 0.0f);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) {
-        if (n1 < nrows) {
-          const int i = 32 * n1 + 2 * l16;
-          v[n1] = make_float2(fs[i] * s_win[i], fs[i + 1] * s_win[i + 1]);
-        } else {
-          v[n1] = make_float2(0.0f, 0.0f);
-        }
-      }
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const float2 x = *reinterpret_cast<const float2*>(fs + 32 * n1 + 2 * l16);
+      const float2 w = *reinterpret_cast<const float2*>(s_win + 32 * n1 + 2 * l16);
+      v[n1] = make_float2(x.x * w.x, x.y * w.y);
     }
-    fft16(v);
+  } else {
 #pragma unroll
-    for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], twA[q]);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) my_scr[KIDX(q) * SCR_ROW + l16] = v[q];
-    __syncwarp();
-#pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) v[n2] = my_scr[l16 * SCR_ROW + n2];
-    __syncwarp();
-    fft16(v);                                              // v[q] = Z[l16 + 16 KIDX(q)]
-
-    // split step: X[k] = E[k] + W512^k O[k], partner Z[(256-k) & 255] comes from lane (16 - l16) & 15, reg 15-q
-    float* Prow = s_P + f * P_STRIDE;
-    const int src_lane = (half << 4) | ((16 - l16) & 15);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int k2 = KIDX(q);
-      float cx = __shfl_sync(0xffffffffu, v[15 - q].x, src_lane);
-      float cy = __shfl_sync(0xffffffffu, v[15 - q].y, src_lane);
-      if (l16 == 0) {                                      // k1 == 0: partner index 16*((16-k2)&15) is in this lane
-        cx = v[PIDX((16 - k2) & 15)].x;
-        cy = v[PIDX((16 - k2) & 15)].y;
-      }
-      const float a = v[q].x, bb = v[q].y;
-      const float2 E2 = make_float2(a + cx, bb - cy);       // 2 E
-      const float2 O2 = make_float2(bb + cy, cx - a);       // 2 O
-      const float2 wk = cmul(wk1, w32(k2));                 // W512^{l16 + 16 k2}
-      const float2 t = cmul(wk, O2);
-      const float xr = 0.5f * (E2.x + t.x), xi = 0.5f * (E2.y + t.y);
-      Prow[l16 + 16 * k2] = apply_power(fmaf(xr, xr, xi * xi), p.pw_mode, p.power);
-      if (q == 0 && l16 == 0) {                            // Nyquist bin: X[256] = Re Z0 - Im Z0
-        const float xn = a - bb;
-        Prow[256] = apply_power(xn * xn, p.pw_mode, p.power);
-      }
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const int i = 32 * n1 + 2 * l16;
+      v[n1] = make_float2(fs[i] * s_win[i], fs[i + 1] * s_win[i + 1]);
     }
   }
+  fft16(v);
+#pragma unroll
+  for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], s_twA[q * 16 + l16]);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) my_scr[KIDX(q) * SCR_ROW + l16] = v[q];
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) v[n2] = my_scr[l16 * SCR_ROW + n2];
+  fft16(v);                                                   // v[q] = Z[l16 + 16 KIDX(q)]
+
+  // split step.  With E = (Z[k] + conj Z[256-k]) / 2, O = (Z[k] - conj Z[256-k]) / 2i and t = W512^k O:
+  //   X[k] = E + t,  X[256-k] = conj(E - t)  ->  both power bins from one evaluation; only k2 = KIDX(q) < 8 is walked.
+  // The partner Z[256-k] lives in lane (16 - l16) & 15, register 15 - q (lane 0 pairs with itself).
+  float* Prow = s_P + f * P_STRIDE;
+  const int src_lane = (half << 4) | ((16 - l16) & 15);
+#pragma unroll
+  for (int qi = 0; qi < 8; ++qi) {
+    const int q = (qi >> 1) * 4 + (qi & 1);                   // 0,1,4,5,8,9,12,13
+    const int k2 = KIDX(q);
+    float cx = __shfl_sync(0xffffffffu, v[15 - q].x, src_lane);
+    float cy = __shfl_sync(0xffffffffu, v[15 - q].y, src_lane);
+    if (l16 == 0) {                                           // k1 == 0: partner 16*((16-k2)&15) is in this lane
+      cx = v[PIDX((16 - k2) & 15)].x;
+      cy = v[PIDX((16 - k2) & 15)].y;
+    }
+    const float a = v[q].x, bb = v[q].y;
+    const float ex = a + cx, ey = bb - cy;                    // 2 E
+    const float2 t = cmul(s_w512[l16 + 16 * k2], make_float2(bb + cy, cx - a));   // W512^k * 2 O
+    const float x1 = ex + t.x, y1 = ey + t.y, x2 = ex - t.x, y2 = ey - t.y;
+    const int k = l16 + 16 * k2;
+    Prow[k] = power_of<PW>(0.25f * fmaf(x1, x1, y1 * y1), p.power);
+    Prow[256 - k] = power_of<PW>(0.25f * fmaf(x2, x2, y2 * y2), p.power);
+  }
+  if (l16 == 0) Prow[128] = power_of<PW>(fmaf(v[PIDX(8)].x, v[PIDX(8)].x, v[PIDX(8)].y * v[PIDX(8)].y), p.power);
   __syncthreads();
 
   if (MODE == 0) {
     float* dst = p.out + ((long long)b * p.T + t0) * 257;
-    const int total = nf * 257;                            // s_P rows are contiguous (stride 257)
+    const int total = nf * 257;                               // s_P rows are contiguous (stride 257)
     for (int i = tid; i < total; i += FUSED_THREADS) dst[i] = s_P[i];
   } else {
     const int n_mel = p.n_mel;
-    const float* Pf = s_P + lane * P_STRIDE;                // lane = frame
-    for (int m = warp; m < n_mel; m += 8) {
+    const int mf = tid & 15;                                  // frame
+    const float* Pf = s_P + mf * P_STRIDE;
+    for (int m = tid >> 4; m < n_mel; m += 16) {
       const int start = s_bstart[m], len = s_blen[m];
       const float* w = s_bw + s_boff[m];
       const float* Pk = Pf + start;
       float acc = 0.0f;
       for (int j = 0; j < len; ++j) acc = fmaf(Pk[j], w[j], acc);
       if (p.log_mode == 1) acc = logf(acc + p.eps);
-      s_out[lane * n_mel + m] = acc;
+      s_out[mf * n_mel + m] = acc;
     }
     __syncthreads();
     float* dst = p.out + ((long long)b * p.T + t0) * n_mel;
@@ -398,20 +400,21 @@ __global__ void __launch_bounds__(256) check_finite_kernel(const float* __restri
 static int pw_mode_of(float power) { return power == 2.0f ? 2 : (power == 1.0f ? 1 : 0); }
 
 static int fused_sig_smem(int L, int step) {
-  long long n = (long long)(FR - 1) * step + L + 34;        // +34: the last row of 32 may read past L (window 0)
+  (void)L;
+  long long n = (long long)(FR - 1) * step + 512 + 2;       // every frame reads all 512 points (window is 0 past L)
   return (int)((n + 3) & ~3LL);
 }
 
 static size_t fused_smem_bytes(int L, int step, int n_mel, int n_packed) {
-  size_t floats = (size_t)fused_sig_smem(L, step) + 512 + 512 /* s_tw */ + (size_t)FR * P_STRIDE + SCR_FLOATS +
-                  (size_t)((n_packed + 3) & ~3) + 3 * (size_t)n_mel;
+  size_t floats = (size_t)fused_sig_smem(L, step) + 512 + 512 /* s_twA */ + 512 /* s_w512 */ + (size_t)P_FLOATS +
+                  SCR_FLOATS + (size_t)((n_packed + 3) & ~3) + 3 * (size_t)n_mel;
   return floats * 4;
 }
 
 static bool fused_ok(int L, int step, int nfft, int n_mel, int n_packed) {
   if (nfft != 512 || L > 512 || L < 1 || step < 1) return false;
   if (n_mel > 256 || FR * n_mel > SCR_FLOATS) return false;
-  return fused_smem_bytes(L, step, n_mel, n_packed) <= 110 * 1024;   // two CTAs per SM
+  return fused_smem_bytes(L, step, n_mel, n_packed) <= 110 * 1024;
 }
 
 static int check_stft_args(const float* sig, long long B, long long N, int L, int step, int nfft) {
@@ -426,12 +429,20 @@ static int check_stft_args(const float* sig, long long B, long long N, int L, in
   return LBX_OK;
 }
 
+template <int MODE, int PW>
+static int launch_fused_pw(const FusedParams& p, long long B, size_t smem, cudaStream_t st) {
+  LBX_CUDA(cudaFuncSetAttribute(logmel512_kernel<MODE, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div(p.T, FR), (unsigned)B);
+  LBX_LAUNCH_PDL((logmel512_kernel<MODE, PW>), grid, dim3(FUSED_THREADS), smem, st, p);
+  return LBX_OK;
+}
+
 template <int MODE>
 static int launch_fused(const FusedParams& p, long long B, size_t smem, cudaStream_t st) {
-  LBX_CUDA(cudaFuncSetAttribute(logmel512_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(p.T, FR), (unsigned)B);
-  LBX_LAUNCH_PDL(logmel512_kernel<MODE>, grid, dim3(FUSED_THREADS), smem, st, p);
-  return LBX_OK;
+  const int pw = pw_mode_of(p.power);
+  if (pw == 2) return launch_fused_pw<MODE, 2>(p, B, smem, st);
+  if (pw == 1) return launch_fused_pw<MODE, 1>(p, B, smem, st);
+  return launch_fused_pw<MODE, 0>(p, B, smem, st);
 }
 
 static int launch_generic_stft(const float* sig, long long B, long long N, long long T, int L, int step, int nfft,
@@ -465,7 +476,7 @@ int lbx_spectrogram_f32(const float* sig, long long B, long long N, int frame_le
     p.sig = sig; p.out = out; p.N = N; p.T = T;
     p.frame_length = frame_length; p.frame_step = frame_step;
     p.sig_smem = fused_sig_smem(frame_length, frame_step);
-    p.pw_mode = pw_mode_of(power); p.power = power;
+    p.power = power;
     return launch_fused<0>(p, B, fused_smem_bytes(frame_length, frame_step, 0, 0), st);
   }
   return launch_generic_stft(sig, B, N, T, frame_length, frame_step, fft_length, power, out, st);
@@ -517,7 +528,7 @@ int lbx_logmel_f32(const float* sig, long long B, long long N, int frame_length,
     p.sig = sig; p.out = out; p.N = N; p.T = T;
     p.frame_length = frame_length; p.frame_step = frame_step;
     p.sig_smem = fused_sig_smem(frame_length, frame_step);
-    p.pw_mode = pw_mode_of(power); p.power = power;
+    p.power = power;
     p.n_mel = n_mel; p.band_start = band_start; p.band_len = band_len; p.band_off = band_off; p.band_w = band_w;
     p.n_packed = n_packed; p.log_mode = log_mode; p.eps = eps;
     return launch_fused<1>(p, B, fused_smem_bytes(frame_length, frame_step, n_mel, n_packed), st);

@@ -139,7 +139,7 @@ typedef struct lbx_gemm_t {
   int rows_per_utt; int valid_rows;
   const void* mask_src;     /* bf16, indexed like out */
   int accumulate;
-  int tile_n;               /* 0 = automatic, or 128 / 256 */
+  int tile_n;               /* 0 = automatic, or 64 / 128 / 256 */
   float* colsum;            /* optional: colsum[n % colsum_mod] += sum_m x[m,n] of the masked result (bias gradient) */
   int colsum_mod;
 } lbx_gemm_t;

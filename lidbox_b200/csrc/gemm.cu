@@ -39,12 +39,12 @@ constexpr int BIAS_SMEM_FLOATS = 3072;         // the bias vector is staged in s
 constexpr int STAGE_PITCH = 80;                // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16-byte accesses)
 constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH;
 
-// tile-N variants: 256 (large problems) and 128 (problems with fewer than ~2 tiles per SM at N=256)
+// tile-N variants: 256 (large problems), 128, and 64 (the small-M dense layers: enough CTAs without split-K)
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;    // 2 accumulator stages x BN fp32 columns
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_SMEM_FLOATS * 4 +
                                  EPI_WARPS * STAGE_BYTES_PER_WARP;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // ===================================== epilogue =====================================
     const int sub = warp & 3;                    // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
     const int chalf = (warp - LBX_CTRL_WARPS) >> 2;           // which half of the tile's columns this warp drains
-    constexpr int CHUNKS = BN / 64;              // 32-column chunks per warp
+    constexpr int CHUNKS = BN / 64;              // 32-column chunks per warp (two warps share a sub-partition)
     int acc = 0;
     uint32_t acc_phase = 0;
     // the bias vector is read by every tile: stage it once (global loads in the epilogue's critical path cost an L2
@@ -687,7 +687,7 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   CUtensorMap mA0, mA1, mB0, mB1;
   int rc;
   // tile-N 256 unless the problem is narrower than 128 columns (measured: 128 never wins on the TDNN shapes)
-  const int bn = (g->tile_n == 128 || g->tile_n == 256) ? g->tile_n : (p.N <= 128 ? 128 : 256);
+  const int bn = (g->tile_n == 64 || g->tile_n == 128 || g->tile_n == 256) ? g->tile_n : (p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256));
   const int boxA_rows = g->layout == 1 ? 64 : BM, boxB_rows = g->layout == 0 ? bn : 64;
   if ((rc = make_map(&mA0, g->a0, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
   if ((rc = make_map(&mB0, g->b0, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
@@ -705,6 +705,7 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
                                 (int)Cfg<N_>::SMEM))
     LBX_SET_SMEM(0, 256); LBX_SET_SMEM(1, 256); LBX_SET_SMEM(2, 256);
     LBX_SET_SMEM(0, 128); LBX_SET_SMEM(1, 128); LBX_SET_SMEM(2, 128);
+    LBX_SET_SMEM(0, 64); LBX_SET_SMEM(1, 64); LBX_SET_SMEM(2, 64);
 #undef LBX_SET_SMEM
     g_num_sms = n;
   }
@@ -713,7 +714,7 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = bn == 256 ? Cfg<256>::SMEM : Cfg<128>::SMEM;
+  cfg.dynamicSmemBytes = bn == 256 ? Cfg<256>::SMEM : (bn == 128 ? Cfg<128>::SMEM : Cfg<64>::SMEM);
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -726,8 +727,10 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
                   : cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, false>, mA0, mA1, mB0, mB1, p)
   if (bn == 256) {
     if (g->layout == 0) LBX_GEMM_LAUNCH(0, 256); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 256); else LBX_GEMM_LAUNCH(2, 256);
-  } else {
+  } else if (bn == 128) {
     if (g->layout == 0) LBX_GEMM_LAUNCH(0, 128); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 128); else LBX_GEMM_LAUNCH(2, 128);
+  } else {
+    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 64); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 64); else LBX_GEMM_LAUNCH(2, 64);
   }
 #undef LBX_GEMM_LAUNCH
   if (le != cudaSuccess) return set_error(LBX_ECUDA, "GEMM launch failed: %s", cudaGetErrorString(le));

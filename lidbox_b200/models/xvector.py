@@ -312,18 +312,17 @@ class XVector:
         return bufs["logits"]
 
     def _dense(self, bufs, a, a_lo, B, ly, relu, out_hi=None, out_lo=None, out_f32=None):
-        """Dense layer for a small number of rows: split-K tcgen05 GEMM accumulating atomically into a zeroed fp32
-        buffer (so that more than a handful of SMs work on it), then one finishing pass (bias, ReLU, bf16 split)."""
+        """Dense layer for a small number of rows: 128x64 output tiles give enough CTAs without split-K, so bias, ReLU
+        and the bf16 split stay fused in the GEMM epilogue (one launch per layer)."""
         split = self.precision == "fp32"
-        acc = bufs["acc"]
-        ld = acc.shape[1]
-        tiles = -(-B // 128) * -(-ly["N"] // 256)
-        ks = max(1, min(-(-ly["K"] // 64), 148 // tiles))
-        ops.gemm(a, B, ly["K"], ly["K"], self.w16, ly["K"], ly["N"], ly["ldw"], acc, ld, layout=2, a_lo=a_lo,
-                 b_lo=self.w16_lo if split else None, b_off=ly["w_off"], k_splits=ks, epi_atomic=True)
-        _lib.check(_lib.lib().lbx_dense_finish(_lib.ptr(acc), B, ly["N"], ld, _lib.ptr(self._b_view(ly)), int(relu), None,
-                                               0, _lib.ptr(out_hi), _lib.ptr(out_lo), ly["N"], _lib.ptr(out_f32),
-                                               ly["N"], None, 1, _lib.stream_ptr(self.device)))
+        if out_hi is not None:
+            ops.gemm(a, B, ly["K"], ly["K"], self.w16, ly["K"], ly["N"], ly["ldw"], out_hi, ly["N"], layout=2, a_lo=a_lo,
+                     b_lo=self.w16_lo if split else None, b_off=ly["w_off"], out_lo=out_lo, bias=self._b_view(ly),
+                     relu=relu, tile_n=64)
+        if out_f32 is not None:
+            ops.gemm(a, B, ly["K"], ly["K"], self.w16, ly["K"], ly["N"], ly["ldw"], out_f32, ly["N"], layout=2, a_lo=a_lo,
+                     b_lo=self.w16_lo if split else None, b_off=ly["w_off"], bias=self._b_view(ly), relu=relu,
+                     tile_n=64)
 
     def __call__(self, x, training=False):
         x = self._prepare_input(x)
@@ -415,26 +414,21 @@ class XVector:
         for i in range(len(self.segments), -1, -1):
             ly = self.layers[n + i]
             wgrad(acts[i], B, ly["K"], ly["K"], dz, dz_cols, dz_pitch, ly)
-            tiles = -(-B // 128) * -(-ly["K"] // 256)
-            ks = max(1, min(-(-dz_cols // 64), 148 // tiles))
-            if i > 0:      # d hidden = (dz . W^T) masked by the ReLU of the layer below; split-K + finishing pass
+            if i > 0:      # d hidden = (dz . W^T) masked by the ReLU of the layer below (+ its bias gradient), one launch
                 below = self.layers[n + i - 1]
-                ops.gemm(dz, B, dz_cols, dz_pitch, self.w16, ly["K"], ly["N"], ly["ldw"], acc, ld_acc,
-                         b_off=ly["w_off"], k_splits=ks, epi_atomic=True)
-                _lib.check(lib.lbx_dense_finish(_lib.ptr(acc), B, ly["K"], ld_acc, None, 0,
-                                                _lib.ptr(bufs["H"][i - 1]) if below["relu"] else None, ly["K"],
-                                                _lib.ptr(bufs["dH"][i - 1]), None, ly["K"], None, 0,
-                                                ops._addr(g, below["b_off"]), 1, st))
+                ops.gemm(dz, B, dz_cols, dz_pitch, self.w16, ly["K"], ly["N"], ly["ldw"], bufs["dH"][i - 1], ly["K"],
+                         b_off=ly["w_off"], mask_src=bufs["H"][i - 1] if below["relu"] else None, colsum=g,
+                         colsum_off=below["b_off"], colsum_mod=ly["K"], tile_n=64)
                 dz, dz_cols, dz_pitch = bufs["dH"][i - 1], ly["K"], ly["K"]
-            else:          # d pooled (fp32, no mask): accumulated atomically into gpool, which pool_bwd re-zeroes
+            else:          # d pooled (fp32, no mask)
                 ops.gemm(dz, B, dz_cols, dz_pitch, self.w16, ly["K"], ly["N"], ly["ldw"], bufs["gpool"], ly["K"],
-                         b_off=ly["w_off"], k_splits=ks, epi_atomic=True)
+                         b_off=ly["w_off"], tile_n=64)
         # ---- statistics pooling (+ ReLU mask and bias gradient of the last frame layer) ----
         last = self.layers[n - 1]
         _lib.check(lib.lbx_stats_pool_bwd(_lib.ptr(bufs["Y"]), B, geo.R[n - 1], geo.T[n], bufs["cn"], bufs["cnp"],
                                           STDDEV_SQRT_MIN_CLIP, _lib.ptr(bufs["pooled"]), _lib.ptr(bufs["var_raw"]),
                                           _lib.ptr(bufs["gpool"]), _lib.ptr(bufs["dZ"][n - 1]),
-                                          ops._addr(g, last["b_off"]), 1, st))
+                                          ops._addr(g, last["b_off"]), 0, st))
         # ---- frame layers, last to first ----
         for L in range(n - 1, -1, -1):
             ly = self.layers[L]

@@ -38,7 +38,8 @@ if only:
     _nt, _tn = nt, tn
     nt = lambda name, *a, **k: _nt(name, *a, **k) if only in name else None
     tn = lambda name, *a, **k: _tn(name, *a, **k) if only in name else None
-for tile_n in (256, 128):
+dense = len(sys.argv) > 2
+for tile_n in ((64,) if dense else (256, 128)):
     nt("frame1 fwd", B * 6 * P, 512, 200, lda=40, tile_n=tile_n)
     nt("frame2 fwd", B * 3 * P, 512, 1536, lda=1024, tile_n=tile_n)
     nt("frame3 fwd", B * P, 512, 1536, tile_n=tile_n)
@@ -50,6 +51,10 @@ for tile_n in (256, 128):
     nt("frame2 dgrad p1", B * 3 * P, 1024, 512, mask=True, bias=False, relu=False, ldo=1024, tile_n=tile_n)
     nt("frame2 dgrad p2 (acc)", B * 3 * P, 512, 512, mask=True, acc=True, bias=False, relu=False, ldo=1024, tile_n=tile_n)
     nt("segment1 fwd", B, 512, 3000, tile_n=tile_n)
+    nt("segment2 fwd", B, 512, 512, tile_n=tile_n)
+    nt("outputs fwd", B, 4, 512, tile_n=tile_n, out_f32=True, relu=False)
+    nt("dH2 dgrad (K=4)", B, 512, 4, tile_n=tile_n, bias=False, relu=False, mask=True)
+    nt("dH1 dgrad", B, 512, 512, tile_n=tile_n, bias=False, relu=False, mask=True)
     nt("segment1 dgrad", B, 3000, 512, bias=False, relu=False, out_f32=True, tile_n=tile_n)
     nt("big square", 8192, 8192, 8192, bias=False, relu=False, tile_n=tile_n)
     tn("frame5 wgrad", B * P, 512, 1500, splits=6, tile_n=tile_n)

@@ -352,7 +352,8 @@ class XVector:
                           step=torch.zeros(1, dtype=torch.int64, device=self.device),
                           lr_t=torch.zeros(1, dtype=torch.float32, device=self.device))
 
-    def loss_and_grads(self, x, y, loss="xent", ap_classes=None, delta_weight=1.0, global_batch=None):
+    def loss_and_grads(self, x, y, loss="xent", ap_classes=None, delta_weight=1.0, global_batch=None,
+                       process_group=None):
         """Forward + backward of one batch in bf16 (fp32 accumulation / statistics / loss).  Fills self.grads with
         d(mean loss)/d(params) (mean over `global_batch`, default this batch) and returns the per-sample losses."""
         if self.precision != "bf16":
@@ -406,6 +407,25 @@ class XVector:
             ops.gemm(a, a_rows, a_cols, lda, dz, a_rows, dz_cols, dz_pitch, g, ly["ldw"], layout=1, a_off=a_off,
                      b_off=dz_off, out_off=ly["w_off"], k_splits=ks, epi_atomic=True)
 
+        # data-parallel exchange: the flat gradient is sum-all-reduced in three buckets (dense head, upper frame
+        # layers, lower frame layers) as soon as each is complete, on the side stream, so that NCCL overlaps the
+        # remaining data-gradient chain; only the last (smallest) bucket is exposed
+        def reduce_bucket(first_layer, last_layer):
+            if process_group is None:
+                return
+            import torch.distributed as dist
+            lo = self.layers[first_layer]["w_off"]
+            hi = self.layers[last_layer]["b_off"] + self.layers[last_layer]["ldw"]
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(cur)                     # bias gradients of the bucket come from main-stream kernels
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    dist.all_reduce(g[lo:hi], group=process_group)
+            else:
+                dist.all_reduce(g[lo:hi], group=process_group)
+
+        mid = n // 2
         # ---- dense head (bias gradients come fused out of the kernels that produce each dz) ----
         dz, dz_cols, dz_pitch = bufs["dlogits"], self.num_outputs, npad
         acts = [bufs["pooled_hi"]] + bufs["H"]
@@ -423,6 +443,7 @@ class XVector:
             else:          # d pooled (fp32, no mask)
                 ops.gemm(dz, B, dz_cols, dz_pitch, self.w16, ly["K"], ly["N"], ly["ldw"], bufs["gpool"], ly["K"],
                          b_off=ly["w_off"], tile_n=64)
+        reduce_bucket(n, len(self.layers) - 1)
         # ---- statistics pooling (+ ReLU mask and bias gradient of the last frame layer) ----
         last = self.layers[n - 1]
         _lib.check(lib.lbx_stats_pool_bwd(_lib.ptr(bufs["Y"]), B, geo.R[n - 1], geo.T[n], bufs["cn"], bufs["cnp"],
@@ -437,7 +458,10 @@ class XVector:
             dz_pitch = bufs["cnp"] if L == n - 1 else ly["N"]
             dz_off = 0 if L == n - 1 else geo.pad[L + 1] * ly["N"]
             wgrad(bufs["X"][L], rows, ly["K"], ly["s"] * ly["c_in"], dZ, ly["N"], dz_pitch, ly, dz_off=dz_off)
+            if L == mid and mid > 0:
+                reduce_bucket(mid, n - 1)
             if L == 0:
+                reduce_bucket(0, max(mid - 1, 0) if mid > 0 else n - 1)
                 break
             # data gradient through the same overlapping view, masked by the ReLU of layer L-1 (= X[L] > 0; padding
             # and junk rows of X[L] are zero, so they stay zero in dZ[L-1]); the column sums of what is written are
@@ -489,16 +513,15 @@ class XVector:
         self._lo_dirty = True
 
     def train_step(self, x, y, loss="xent", process_group=None, **kw):
-        """One optimisation step; with a process group the flat fp32 gradient is sum-all-reduced over NCCL first."""
+        """One optimisation step; with a process group the flat fp32 gradient is sum-all-reduced over NCCL (three
+        buckets, overlapped with the backward pass) before Adam."""
         world = 1
         if process_group is not None:
             import torch.distributed as dist
             world = dist.get_world_size(process_group)
         B = x.shape[0]
-        losses = self.loss_and_grads(x, y, loss=loss, global_batch=B * world, **kw)
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grads, group=process_group)
+        losses = self.loss_and_grads(x, y, loss=loss, global_batch=B * world,
+                                     process_group=process_group if world > 1 else None, **kw)
         self.apply_gradients()
         return losses
 

@@ -16,6 +16,7 @@ semantics follow the reference; the arithmetic runs through the C-ABI (include/l
     precision "bf16" (training configs): bf16 operands, fp32 accumulation / statistics / loss / master weights.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -407,11 +408,14 @@ class XVector:
             ops.gemm(a, a_rows, a_cols, lda, dz, a_rows, dz_cols, dz_pitch, g, ly["ldw"], layout=1, a_off=a_off,
                      b_off=dz_off, out_off=ly["w_off"], k_splits=ks, epi_atomic=True)
 
-        # data-parallel exchange: the flat gradient is sum-all-reduced in three buckets (dense head, upper frame
-        # layers, lower frame layers) as soon as each is complete, on the side stream, so that NCCL overlaps the
-        # remaining data-gradient chain; only the last (smallest) bucket is exposed
+        # data-parallel exchange.  Default ("single"): ONE all-reduce of the flat gradient after the backward pass.
+        # "buckets" all-reduces three buckets on the side stream as soon as each is complete; measured on 2 x B200 it is
+        # SLOWER (0.712 vs 0.619 ms/step; no exchange: 0.572): the NCCL kernels take SMs away from the persistent
+        # one-CTA-per-SM GEMMs they overlap with.  Kept for experiments (LBX_DP_MODE=buckets).
+        dp_mode = os.environ.get("LBX_DP_MODE", "single")      # single | buckets | none (measurement only)
+
         def reduce_bucket(first_layer, last_layer):
-            if process_group is None:
+            if process_group is None or dp_mode != "buckets":
                 return
             import torch.distributed as dist
             lo = self.layers[first_layer]["w_off"]
@@ -497,6 +501,9 @@ class XVector:
             ev = torch.cuda.Event()
             ev.record(side)
             cur.wait_event(ev)
+        if process_group is not None and dp_mode == "single":
+            import torch.distributed as dist
+            dist.all_reduce(g, group=process_group)
         return bufs["loss"]
 
     def apply_gradients(self, grad_scale=1.0):
@@ -513,8 +520,7 @@ class XVector:
         self._lo_dirty = True
 
     def train_step(self, x, y, loss="xent", process_group=None, **kw):
-        """One optimisation step; with a process group the flat fp32 gradient is sum-all-reduced over NCCL (three
-        buckets, overlapped with the backward pass) before Adam."""
+        """One optimisation step; with a process group the flat fp32 gradient is sum-all-reduced over NCCL before Adam."""
         world = 1
         if process_group is not None:
             import torch.distributed as dist

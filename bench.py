@@ -223,7 +223,7 @@ class XVectorTrainWorkload:
                 "frames_per_utt": self.T, "cuda_graph": self.use_graph,
                 "feature_prefetch": "log-mel of batch i+1 runs on a second stream during step i (one log-mel + one "
                                     "training step per replay)" if self.pipelined else "inline",
-                "parallelism": "dp%d (NCCL all-reduce of the 18 MB fp32 gradient)" % self.world}
+                "parallelism": "dp%d" % self.world, "dp_exchange": getattr(self, "dp_exchange", None)}
 
     def _act_mb(self):
         return self.B * self.T * (512 * 2 * 2 + 256 * 2 * 2 + 2 * 1504 * 2 / 6 + 160) / 1e6
@@ -244,6 +244,14 @@ class XVectorTrainWorkload:
         self.model = xvector.create((self.T, 40), self.n_out, precision="bf16", head=self.head, seed=0)
         self.model.configure_optimizer(lr=1e-3)
         self.pg = self.dist.group.WORLD if self.dist is not None else None
+        self.dp_exchange = "none (single GPU)"
+        if self.pg is not None:
+            if os.environ.get("LBX_DP_SHARDED", "1") != "0":
+                self.model.enable_sharded_optimizer(self.pg)
+                self.dp_exchange = ("fused in the optimizer kernel: reduce-scatter by NVLink peer loads, Adam on the "
+                                    "rank's shard, all-gather by peer stores (no NCCL call in the step)")
+            else:
+                self.dp_exchange = "one NCCL all-reduce of the flat fp32 gradient, then full-size Adam"
         self.kw = dict(ap_classes=self.n_classes) if self.loss == "ap" else {}
         self.pipelined = os.environ.get("LBX_BENCH_PIPELINE", "1") != "0"
         self.i = 0

@@ -205,6 +205,21 @@ int lbx_dense_finish(float* acc, long long M, int N, int ld_acc, const float* bi
                      int ld_mask, void* out_hi, void* out_lo, int ld_out, float* out_f32, int ld_f32, float* colsum,
                      int zero_acc, void* stream);
 
+/* Data-parallel optimizer step fused with the gradient exchange over NVLink peer memory (one node, one process per
+ * GPU; replaces "all-reduce + Adam").  The flat parameter / gradient / bf16-copy buffers are SYMMETRIC allocations:
+ * params_ptrs / grads_ptrs / w16_ptrs / signal_ptrs are DEVICE arrays of `world` peer pointers (index = rank).
+ * Every rank: waits until all ranks finished their backward pass (peer flag barrier), sums ITS shard
+ * [rank*n/world, (rank+1)*n/world) of all ranks' gradients with peer loads (reduce-scatter), applies Adam to the shard
+ * (m_shard / v_shard hold n/world elements), stores the updated fp32 parameters and bf16 copy into every rank's
+ * buffers with peer stores (all-gather), waits for all ranks again, and zeroes its own gradient buffer.
+ * signal pads: 2*world uint32 per rank, zero-initialised; epoch_dev / local_sync_dev (4 uint32): zero-initialised local
+ * state advanced by every call, so the call can be replayed from a CUDA graph.  local_sync_dev[3] != 0 reports a
+ * barrier time-out.  n must be a multiple of 4*world. */
+int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, void* const* w16_ptrs,
+                          void* const* signal_ptrs, float* m_shard, float* v_shard, long long n, int rank, int world,
+                          unsigned int* epoch_dev, unsigned int* local_sync_dev, float lr, float beta1, float beta2,
+                          float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* stream);
+
 /* fp32 -> bf16 operand planes of the flat parameter buffer: hi = bf16(x), lo = bf16(x - hi) (lo optional; it feeds
  * the bf16x3 forward mode).  The buffers keep the Keras layouts ([k*C_in, C_out] per kernel, pitch padded to 8). */
 int lbx_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream);

@@ -671,6 +671,141 @@ __global__ void __launch_bounds__(256) dense_finish_kernel(float* __restrict__ a
 }
 
 
+// ------------------------------------------------------------------------------------------------------------
+// Sharded optimizer step fused with the gradient exchange over NVLink peer memory (data parallel, one node):
+//   barrier -> reduce-scatter (peer loads of every rank's gradient shard) -> Adam on the shard -> all-gather (peer
+//   stores of the updated fp32 parameters and bf16 operand copy into every rank) -> barrier -> local gradient reset.
+// Replaces "NCCL all-reduce + full-size Adam": each rank moves 2/R of the gradient over NVLink instead of running a
+// separate collective, and keeps Adam moments only for its own 1/R of the parameters.
+// ------------------------------------------------------------------------------------------------------------
+struct ShardedAdamParams {
+  float* const* params;          // [world] peer pointers (symmetric buffers, identical layout)
+  float* const* grads;
+  bf16* const* w16;
+  unsigned int* const* signals;  // [world] peer pointers to signal pads: 2*world uint32 each
+  float* m;                      // local moments of the shard [shard_n]
+  float* v;
+  long long n;                   // flat length (multiple of 4*world)
+  int rank, world;
+  unsigned int* epoch;           // local: advanced by every call
+  unsigned int* local_sync;      // local: [0] go1, [1] arrivals, [2] go2, [3] error flag
+  long long* step;
+  float* lr_t;
+  float lr, beta1, beta2, eps, grad_scale;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bounded spin: a lost peer must not hang the GPU (error flag instead)
+__device__ __forceinline__ bool spin_until_ge(const unsigned int* p, unsigned int target, bool sys_scope) {
+  for (long long it = 0; it < (1LL << 23); ++it) {   // ~1 s
+    const unsigned int v = sys_scope ? ld_acquire_sys(p) : ld_acquire_gpu(p);
+    if ((int)(v - target) >= 0) return true;
+    __nanosleep(64);
+  }
+  return false;
+}
+
+// cross-GPU barrier executed by thread 0 of block 0: slot `base + rank` of every peer's pad receives the epoch
+__device__ __forceinline__ bool peer_barrier(const ShardedAdamParams& p, unsigned int e, int base) {
+  for (int q = 0; q < p.world; ++q) st_release_sys(p.signals[q] + base + p.rank, e);
+  bool ok = true;
+  for (int q = 0; q < p.world; ++q) ok = spin_until_ge(p.signals[p.rank] + base + q, e, true) && ok;
+  return ok;
+}
+
+__global__ void __launch_bounds__(256) adam_sharded_kernel(const ShardedAdamParams p) {
+  LBX_PDL_SYNC();
+  __shared__ unsigned int s_e;
+  __shared__ float s_lr_t;
+  const unsigned int nblk = gridDim.x;
+  // ---- barrier 1: every rank has finished its backward pass (its gradient buffer is complete) ----
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned int e = *p.epoch + 1;
+    const long long t = *p.step + 1;
+    *p.step = t;
+    *p.lr_t = (float)((double)p.lr * sqrt(1.0 - pow((double)p.beta2, (double)t)) / (1.0 - pow((double)p.beta1, (double)t)));
+    __threadfence_system();                     // this rank's gradient writes are visible to the peers
+    if (!peer_barrier(p, e, 0)) p.local_sync[3] = 1;
+    __threadfence();
+    st_release_gpu(p.local_sync + 0, e);
+  }
+  if (threadIdx.x == 0) {
+    const unsigned int e = *p.epoch + 1;         // epoch is only advanced at the very end, by block 0
+    if (!spin_until_ge(p.local_sync + 0, e, false)) p.local_sync[3] = 1;
+    s_e = e;
+    s_lr_t = *reinterpret_cast<volatile float*>(p.lr_t);
+  }
+  __syncthreads();
+  const unsigned int e = s_e;
+  const float lr_t = s_lr_t;
+
+  // ---- reduce-scatter + Adam + all-gather on this rank's shard ----
+  const long long shard4 = p.n / 4 / p.world;    // float4 groups per shard
+  const long long base4 = shard4 * p.rank;
+  float4* m4 = reinterpret_cast<float4*>(p.m);
+  float4* v4 = reinterpret_cast<float4*>(p.v);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < shard4; i += (long long)nblk * blockDim.x) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < p.world; ++q) {
+      const float4 t = __ldcv(reinterpret_cast<const float4*>(p.grads[q]) + base4 + i);   // peer (NVLink) or local
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    float4 mi = m4[i], vi = v4[i];
+    float4 pi = reinterpret_cast<const float4*>(p.params[p.rank])[base4 + i];
+#define LBX_ADAM1(c)                                          \
+    {                                                         \
+      const float gg = g.c * p.grad_scale;                    \
+      mi.c = p.beta1 * mi.c + (1.0f - p.beta1) * gg;          \
+      vi.c = p.beta2 * vi.c + (1.0f - p.beta2) * gg * gg;     \
+      pi.c -= lr_t * mi.c / (sqrtf(vi.c) + p.eps);            \
+    }
+    LBX_ADAM1(x) LBX_ADAM1(y) LBX_ADAM1(z) LBX_ADAM1(w)
+#undef LBX_ADAM1
+    m4[i] = mi;
+    v4[i] = vi;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(pi.x, pi.y), hi = __floats2bfloat162_rn(pi.z, pi.w);
+    const uint2 packed = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    for (int q = 0; q < p.world; ++q) {           // all-gather by peer stores
+      reinterpret_cast<float4*>(p.params[q])[base4 + i] = pi;
+      reinterpret_cast<uint2*>(p.w16[q])[base4 + i] = packed;
+    }
+  }
+  // ---- barrier 2: all shards have been pushed everywhere and nobody reads this rank's gradient any more ----
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(p.local_sync + 1, 1u);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!spin_until_ge(p.local_sync + 1, e * nblk, false)) p.local_sync[3] = 1;
+    __threadfence_system();
+    if (!peer_barrier(p, e, p.world)) p.local_sync[3] = 1;
+    __threadfence();
+    st_release_gpu(p.local_sync + 2, e);
+  }
+  if (threadIdx.x == 0 && !spin_until_ge(p.local_sync + 2, e, false)) p.local_sync[3] = 1;
+  __syncthreads();
+  // ---- reset the local gradient for the next step ----
+  float4* g4 = reinterpret_cast<float4*>(p.grads[p.rank]);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n / 4; i += (long long)nblk * blockDim.x)
+    g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the epoch is advanced once every block has read it (all blocks passed go2, which is after their read)
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.epoch = e;
+}
+
 static inline int grid_for(long long n, int block, int cap = 148 * 16) {
   long long g = ceil_div(n, block);
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
@@ -824,6 +959,29 @@ int lbx_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream
   LBX_CHECK_ARG(x && hi, "NULL pointer argument");
   split_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, (bf16*)hi, (bf16*)lo);
   LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, void* const* w16_ptrs,
+                          void* const* signal_ptrs, float* m_shard, float* v_shard, long long n, int rank, int world,
+                          unsigned int* epoch_dev, unsigned int* local_sync_dev, float lr, float beta1, float beta2,
+                          float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* stream) {
+  LBX_CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+  LBX_CHECK_ARG(n > 0 && n % (4LL * world) == 0, "the flat length must be a multiple of 4*world (pad the buffers)");
+  LBX_CHECK_ARG(params_ptrs && grads_ptrs && w16_ptrs && signal_ptrs && m_shard && v_shard && epoch_dev &&
+                    local_sync_dev && step_dev && lr_t_dev,
+                "NULL pointer argument");
+  ShardedAdamParams p{};
+  p.params = (float* const*)params_ptrs; p.grads = (float* const*)grads_ptrs; p.w16 = (bf16* const*)w16_ptrs;
+  p.signals = (unsigned int* const*)signal_ptrs;
+  p.m = m_shard; p.v = v_shard; p.n = n; p.rank = rank; p.world = world;
+  p.epoch = epoch_dev; p.local_sync = local_sync_dev; p.step = step_dev; p.lr_t = lr_t_dev;
+  p.lr = lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale;
+  // every block must be resident at once (grid-wide flags): one block per SM is always schedulable
+  int dev = 0, sms = 0;
+  LBX_CUDA(cudaGetDevice(&dev));
+  LBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  LBX_LAUNCH_PDL(adam_sharded_kernel, dim3((unsigned)sms), dim3(256), 0, (cudaStream_t)stream, p);
   return LBX_OK;
 }
 

@@ -119,6 +119,7 @@ class XVector:
         self._build_params(seed)
         self._bufs = {}
         self._adam = None
+        self._sharded = None
         self._grads_clean = True
         self.overlap_wgrad = True
         self._side_stream = torch.cuda.Stream(device=self.device)
@@ -519,6 +520,60 @@ class XVector:
         self._weights_dirty = False        # the hi plane was refreshed by the optimizer pass
         self._lo_dirty = True
 
+    def enable_sharded_optimizer(self, process_group):
+        """Data parallel without NCCL in the step: the flat parameter / gradient / bf16 buffers move to symmetric
+        (peer-mapped) memory and the optimizer step becomes lbx_adam_step_sharded — reduce-scatter by NVLink peer
+        loads, Adam on this rank's 1/R shard, all-gather by peer stores, all inside one kernel.  Collective call."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        if self._adam is None:
+            self.configure_optimizer()
+        dev = self.device
+        n = self.params.numel()
+        unit = 4 * world
+        n_pad = -(-n // unit) * unit
+        handles = []
+
+        def make(dtype, src, length):
+            t = symm.empty(length, dtype=dtype, device=dev)
+            t.zero_()
+            if src is not None:
+                t[:src.numel()].copy_(src)
+            h = symm.rendezvous(t, group=process_group)
+            handles.append(h)
+            return t, torch.tensor(list(h.buffer_ptrs), dtype=torch.int64, device=dev)
+
+        self.params, p_ptrs = make(torch.float32, self.params, n_pad)
+        self.grads, g_ptrs = make(torch.float32, None, n_pad)
+        self.w16, w_ptrs = make(torch.bfloat16, None, n_pad)
+        sig, s_ptrs = make(torch.int32, None, max(2 * world, 64))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=process_group)                   # every rank has zeroed its pads before anyone signals
+        a = self._adam
+        self._sharded = dict(world=world, rank=rank, n=n_pad, p_ptrs=p_ptrs, g_ptrs=g_ptrs, w_ptrs=w_ptrs,
+                             s_ptrs=s_ptrs, sig=sig, handles=handles,
+                             m=torch.zeros(n_pad // world, dtype=torch.float32, device=dev),
+                             v=torch.zeros(n_pad // world, dtype=torch.float32, device=dev),
+                             epoch=torch.zeros(1, dtype=torch.int32, device=dev),
+                             local=torch.zeros(4, dtype=torch.int32, device=dev))
+        a["m"] = a["v"] = None                              # full-size moments are not needed any more
+        self._weights_dirty = self._lo_dirty = True
+        self._grads_clean = True
+        self.w16_lo = None
+
+    def _apply_sharded(self):
+        a, sh = self._adam, self._sharded
+        _lib.check(_lib.lib().lbx_adam_step_sharded(_lib.ptr(sh["p_ptrs"]), _lib.ptr(sh["g_ptrs"]),
+                                                    _lib.ptr(sh["w_ptrs"]), _lib.ptr(sh["s_ptrs"]), _lib.ptr(sh["m"]),
+                                                    _lib.ptr(sh["v"]), sh["n"], sh["rank"], sh["world"],
+                                                    _lib.ptr(sh["epoch"]), _lib.ptr(sh["local"]), a["lr"], a["beta1"],
+                                                    a["beta2"], a["eps"], _lib.ptr(a["step"]), _lib.ptr(a["lr_t"]),
+                                                    1.0, _lib.stream_ptr(self.device)))
+        self._grads_clean = True
+        self._weights_dirty = False
+        self._lo_dirty = True
+
     def train_step(self, x, y, loss="xent", process_group=None, **kw):
         """One optimisation step; with a process group the flat fp32 gradient is sum-all-reduced over NCCL before Adam."""
         world = 1
@@ -526,6 +581,12 @@ class XVector:
             import torch.distributed as dist
             world = dist.get_world_size(process_group)
         B = x.shape[0]
+        if self._sharded is not None:
+            if self._sharded["world"] != world:
+                raise ValueError("the sharded optimizer was enabled for a different process group")
+            losses = self.loss_and_grads(x, y, loss=loss, global_batch=B * world, process_group=None, **kw)
+            self._apply_sharded()
+            return losses
         losses = self.loss_and_grads(x, y, loss=loss, global_batch=B * world,
                                      process_group=process_group if world > 1 else None, **kw)
         self.apply_gradients()

@@ -22,30 +22,39 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 rng = np.random.default_rng(0)
 x = rng.standard_normal((8, 50, 40)).astype(np.float32); y = np.arange(8) %% 4
 m = xvector.create((50, 40), 4, precision="bf16", seed=3); m.configure_optimizer()
+if os.environ.get("LBX_TEST_SHARDED") == "1":
+    m.enable_sharded_optimizer(dist.group.WORLD)
 per = 8 // world
 m.train_step(x[rank*per:(rank+1)*per], y[rank*per:(rank+1)*per], process_group=dist.group.WORLD)
 if rank == 0:
     ref = xvector.create((50, 40), 4, precision="bf16", seed=3); ref.configure_optimizer()
     ref.train_step(x, y)
-    d = (m.params - ref.params).abs().mean().item(); s = (ref.params - xvector.create((50, 40), 4, precision="bf16", seed=3).params).abs().mean().item()
-    print("MEANDIFF", d, "STEP", s)
+    npar = ref.params.numel()
+    d = (m.params[:npar] - ref.params).abs().mean().item(); s = (ref.params - xvector.create((50, 40), 4, precision="bf16", seed=3).params).abs().mean().item()
+    w = (m.w16[:npar].float() - ref.w16.float()).abs().max().item()
+    err = int(m._sharded["local"][3].item()) if m._sharded is not None else 0
+    print("MEANDIFF", d, "STEP", s, "W16", w, "ERR", err)
 dist.destroy_process_group()
 ''' % ROOT
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_step_matches_single_rank(tmp_path):
+@pytest.mark.parametrize("sharded", ["0", "1"])
+def test_two_rank_step_matches_single_rank(tmp_path, sharded):
+    """sharded=0: NCCL all-reduce + Adam; sharded=1: lbx_adam_step_sharded (peer-memory reduce-scatter / all-gather)."""
     script = tmp_path / "w.py"
     script.write_text(WORKER)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
+    env = dict(os.environ, LBX_TEST_SHARDED=sharded)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
-                         capture_output=True, text=True, timeout=300)
+                         capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("MEANDIFF")][0].split()
     diff, step = float(line[1]), float(line[3])
+    assert float(line[5]) < 2e-3 and int(line[7]) == 0      # bf16 copy consistent with the fp32 master; no time-out
     # Adam's first step moves every weight by ~lr * sign(g); the two runs differ only by bf16 / atomic summation order,
     # which can flip the sign of near-zero gradients: compare the mean displacement
     assert step > 5e-4 and diff < 0.05 * step, (diff, step)

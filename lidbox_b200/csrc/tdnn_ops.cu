@@ -759,30 +759,48 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const ShardedAdamPara
   const long long base4 = shard4 * p.rank;
   float4* m4 = reinterpret_cast<float4*>(p.m);
   float4* v4 = reinterpret_cast<float4*>(p.v);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < shard4; i += (long long)nblk * blockDim.x) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < p.world; ++q) {
-      const float4 t = __ldcv(reinterpret_cast<const float4*>(p.grads[q]) + base4 + i);   // peer (NVLink) or local
-      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+  // peer loads have NVLink latency (microseconds): every thread keeps UNROLL x world 16-byte loads in flight
+  constexpr int UNROLL = 4, MAXW = 8;
+  const long long stride = (long long)nblk * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < shard4; i0 += stride * UNROLL) {
+    float4 t[UNROLL][MAXW];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = i0 + u * stride;
+#pragma unroll
+      for (int q = 0; q < MAXW; ++q)
+        if (q < p.world && i < shard4)
+          t[u][q] = __ldcv(reinterpret_cast<const float4*>(p.grads[q]) + base4 + i);   // peer (NVLink) or local
     }
-    float4 mi = m4[i], vi = v4[i];
-    float4 pi = reinterpret_cast<const float4*>(p.params[p.rank])[base4 + i];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= shard4) break;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < MAXW; ++q)
+        if (q < p.world) { g.x += t[u][q].x; g.y += t[u][q].y; g.z += t[u][q].z; g.w += t[u][q].w; }
+      float4 mi = m4[i], vi = v4[i];
+      float4 pi = reinterpret_cast<const float4*>(p.params[p.rank])[base4 + i];
 #define LBX_ADAM1(c)                                          \
-    {                                                         \
-      const float gg = g.c * p.grad_scale;                    \
-      mi.c = p.beta1 * mi.c + (1.0f - p.beta1) * gg;          \
-      vi.c = p.beta2 * vi.c + (1.0f - p.beta2) * gg * gg;     \
-      pi.c -= lr_t * mi.c / (sqrtf(vi.c) + p.eps);            \
-    }
-    LBX_ADAM1(x) LBX_ADAM1(y) LBX_ADAM1(z) LBX_ADAM1(w)
+      {                                                       \
+        const float gg = g.c * p.grad_scale;                  \
+        mi.c = p.beta1 * mi.c + (1.0f - p.beta1) * gg;        \
+        vi.c = p.beta2 * vi.c + (1.0f - p.beta2) * gg * gg;   \
+        pi.c -= lr_t * mi.c / (sqrtf(vi.c) + p.eps);          \
+      }
+      LBX_ADAM1(x) LBX_ADAM1(y) LBX_ADAM1(z) LBX_ADAM1(w)
 #undef LBX_ADAM1
-    m4[i] = mi;
-    v4[i] = vi;
-    __nv_bfloat162 lo = __floats2bfloat162_rn(pi.x, pi.y), hi = __floats2bfloat162_rn(pi.z, pi.w);
-    const uint2 packed = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-    for (int q = 0; q < p.world; ++q) {           // all-gather by peer stores
-      reinterpret_cast<float4*>(p.params[q])[base4 + i] = pi;
-      reinterpret_cast<uint2*>(p.w16[q])[base4 + i] = packed;
+      m4[i] = mi;
+      v4[i] = vi;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pi.x, pi.y), hi = __floats2bfloat162_rn(pi.z, pi.w);
+      const uint2 packed = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+#pragma unroll
+      for (int q = 0; q < MAXW; ++q)                // all-gather by peer stores
+        if (q < p.world) {
+          reinterpret_cast<float4*>(p.params[q])[base4 + i] = pi;
+          reinterpret_cast<uint2*>(p.w16[q])[base4 + i] = packed;
+        }
     }
   }
   // ---- barrier 2: all shards have been pushed everywhere and nobody reads this rank's gradient any more ----
@@ -977,11 +995,15 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
   p.m = m_shard; p.v = v_shard; p.n = n; p.rank = rank; p.world = world;
   p.epoch = epoch_dev; p.local_sync = local_sync_dev; p.step = step_dev; p.lr_t = lr_t_dev;
   p.lr = lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale;
-  // every block must be resident at once (grid-wide flags): one block per SM is always schedulable
-  int dev = 0, sms = 0;
+  LBX_CHECK_ARG(world <= 8, "at most 8 ranks (one NVLink domain)");
+  // every block must be able to be resident at once (grid-wide flags): occupancy-limited grid
+  int dev = 0, sms = 0, per_sm = 0;
   LBX_CUDA(cudaGetDevice(&dev));
   LBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  LBX_LAUNCH_PDL(adam_sharded_kernel, dim3((unsigned)sms), dim3(256), 0, (cudaStream_t)stream, p);
+  LBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adam_sharded_kernel, 256, 0));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  LBX_LAUNCH_PDL(adam_sharded_kernel, dim3((unsigned)(sms * per_sm)), dim3(256), 0, (cudaStream_t)stream, p);
   return LBX_OK;
 }
 

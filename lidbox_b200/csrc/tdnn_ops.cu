@@ -692,6 +692,7 @@ struct ShardedAdamParams {
   long long* step;
   float* lr_t;
   float lr, beta1, beta2, eps, grad_scale;
+  int push_fp32;                 // 1: also all-gather the fp32 master copy (otherwise only the owner's shard is current)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -798,7 +799,7 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const ShardedAdamPara
 #pragma unroll
       for (int q = 0; q < MAXW; ++q)                // all-gather by peer stores
         if (q < p.world) {
-          reinterpret_cast<float4*>(p.params[q])[base4 + i] = pi;
+          if (p.push_fp32 || q == p.rank) reinterpret_cast<float4*>(p.params[q])[base4 + i] = pi;
           reinterpret_cast<uint2*>(p.w16[q])[base4 + i] = packed;
         }
     }
@@ -983,7 +984,8 @@ int lbx_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream
 int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, void* const* w16_ptrs,
                           void* const* signal_ptrs, float* m_shard, float* v_shard, long long n, int rank, int world,
                           unsigned int* epoch_dev, unsigned int* local_sync_dev, float lr, float beta1, float beta2,
-                          float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* stream) {
+                          float eps, long long* step_dev, float* lr_t_dev, float grad_scale, int push_fp32,
+                          void* stream) {
   LBX_CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
   LBX_CHECK_ARG(n > 0 && n % (4LL * world) == 0, "the flat length must be a multiple of 4*world (pad the buffers)");
   LBX_CHECK_ARG(params_ptrs && grads_ptrs && w16_ptrs && signal_ptrs && m_shard && v_shard && epoch_dev &&
@@ -995,6 +997,7 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
   p.m = m_shard; p.v = v_shard; p.n = n; p.rank = rank; p.world = world;
   p.epoch = epoch_dev; p.local_sync = local_sync_dev; p.step = step_dev; p.lr_t = lr_t_dev;
   p.lr = lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale;
+  p.push_fp32 = push_fp32;
   LBX_CHECK_ARG(world <= 8, "at most 8 ranks (one NVLink domain)");
   // every block must be able to be resident at once (grid-wide flags): occupancy-limited grid
   int dev = 0, sms = 0, per_sm = 0;

@@ -181,6 +181,7 @@ class XVector:
 
     def get_weights(self):
         """dict name/kernel|bias -> numpy array in Keras layouts."""
+        self._sync_master_from_peers()
         out = {}
         for ly in self.layers:
             w = self._w_view(ly)[:, :ly["N"]].cpu()
@@ -208,6 +209,8 @@ class XVector:
 
     def _refresh(self, need_lo):
         """(Re)build the bf16 operand copy of the parameters (and the residual plane for the bf16x3 mode)."""
+        if need_lo:
+            self._sync_master_from_peers()
         if need_lo and self.w16_lo is None:
             self.w16_lo = torch.zeros_like(self.w16)
             self._lo_dirty = True
@@ -569,10 +572,31 @@ class XVector:
                                                     _lib.ptr(sh["v"]), sh["n"], sh["rank"], sh["world"],
                                                     _lib.ptr(sh["epoch"]), _lib.ptr(sh["local"]), a["lr"], a["beta1"],
                                                     a["beta2"], a["eps"], _lib.ptr(a["step"]), _lib.ptr(a["lr_t"]),
-                                                    1.0, _lib.stream_ptr(self.device)))
+                                                    1.0, 0, _lib.stream_ptr(self.device)))
         self._grads_clean = True
         self._weights_dirty = False
         self._lo_dirty = True
+        sh["master_stale"] = True
+
+    def _sync_master_from_peers(self):
+        """The sharded optimizer keeps the fp32 master copy of a shard current on its owner only; pull the other
+        shards through the peer mappings (needed before exporting weights or building the bf16x3 residual plane).
+        Every rank must call this at the same point (it ends with a barrier)."""
+        sh = self._sharded
+        if sh is None or not sh.get("master_stale"):
+            return
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+        shard = sh["n"] // sh["world"]
+        h = sh["handles"][0]
+        for q in range(sh["world"]):
+            if q != sh["rank"]:
+                peer = h.get_buffer(q, (sh["n"],), torch.float32)
+                self.params[q * shard:(q + 1) * shard].copy_(peer[q * shard:(q + 1) * shard])
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+        sh["master_stale"] = False
 
     def train_step(self, x, y, loss="xent", process_group=None, **kw):
         """One optimisation step; with a process group the flat fp32 gradient is sum-all-reduced over NCCL before Adam."""

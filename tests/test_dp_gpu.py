@@ -26,6 +26,7 @@ if os.environ.get("LBX_TEST_SHARDED") == "1":
     m.enable_sharded_optimizer(dist.group.WORLD)
 per = 8 // world
 m.train_step(x[rank*per:(rank+1)*per], y[rank*per:(rank+1)*per], process_group=dist.group.WORLD)
+w_all = m.get_weights()          # collective when sharded: gathers the fp32 master shards from their owners
 if rank == 0:
     ref = xvector.create((50, 40), 4, precision="bf16", seed=3); ref.configure_optimizer()
     ref.train_step(x, y)

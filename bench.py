@@ -363,6 +363,14 @@ class XVectorTrainWorkload:
         big_ms = big[0].elapsed_time(big[1])
         ach = alg / (ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        traffic = None
+        try:        # dram__bytes_read+write per launch from the committed ncu --set full capture of the same step
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")))
+            if tj.get("launches") == len(rec) and (self.B, self.sec) == (256, 2):
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        self._traffic = traffic
         return {"bound": "tensor", "kernel": "gemm_bf16_kernel (all %d launches of one training step, replayed "
                                              "back-to-back from a CUDA graph)" % len(rec),
                 "achieved": ach, "peak": peak, "peak_source": peaks["source"] + " (sustained: timed inside a step)",
@@ -371,7 +379,7 @@ class XVectorTrainWorkload:
                 "avg_launch_us": ms * 1e3 / len(rec),
                 "largest_launch": {"M": big[2], "N": big[3], "K": big[4], "ms": big_ms,
                                    "tflops": 2.0 * big[2] * big[3] * big[4] / (big_ms * 1e-3) / 1e12},
-                "traffic": None}
+                "algorithmic_flops_per_launch": alg / len(rec), "traffic": self._traffic}
 
     def cpu_sample(self, budget_s=20.0):
         from oracle import lidbox_oracle as O

@@ -1,0 +1,6 @@
+set -x
+# 1. launch list of one eager training step (config 3)
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 93 -c 40 --csv --log-file gpurun_out/r1_launches_train_step.csv python scratch/one_step.py 4 > /dev/null 2>&1
+# 2. full sections for every GEMM launch of one step + the other kernels
+timeout 400 ncu --set full --clock-control none --import-source on -s 93 -c 31 -o gpurun_out/r1_full_step python scratch/one_step.py 4 > /dev/null 2>&1
+ls -la gpurun_out | tail -5

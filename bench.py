@@ -481,6 +481,49 @@ def bench_embed_quick(device, B=64, sec=2):
             "algorithmic_tflops": B * fwd / (ms_graph * 1e-3) / 1e12}
 
 
+def bench_fwd_sweep(device, batches=(64, 256, 1024, 2048), seconds=(1, 2, 5)):
+    """BASELINE config 5: log-mel + TDNN forward (bf16 operands, fp32 accumulation) over batch x duration; each cell is
+    one CUDA-graph replay timed with CUDA events (inputs of the large cells exceed L2; small cells are L2-resident)."""
+    from lidbox_b200.features import audio
+    from lidbox_b200.models import xvector
+    peaks = load_peaks()
+    cells = []
+    for sec in seconds:
+        N = sec * SR
+        T = 1 + (N - 400) // 160
+        model = xvector.create((T, 40), 4, precision="bf16", seed=0)
+        fwd_flops, _ = tdnn_forward_flops(T)
+        for B in batches:
+            x = synth_signals(B, N, 1234, device=device)
+            feats = torch.empty((B, T, 40), dtype=torch.float32, device=device)
+
+            def lm():
+                audio.logmelspectrograms(x, SR, out=feats)
+
+            def run():
+                lm()
+                return model(feats)
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+            iters = 20 if B * sec <= 2048 else 5
+            ms = _time_cuda(g.replay, iters)
+            ms_lm = _time_cuda(lm, iters)
+            cells.append({"batch": B, "seconds": sec, "ms": ms, "audio_sec_per_s": B * sec / (ms * 1e-3),
+                          "logmel_ms": ms_lm, "logmel_frames_per_s": B * T / (ms_lm * 1e-3),
+                          "logmel_hbm_frac": B * (4 * N + 4 * T * 40) / (ms_lm * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "tdnn_tflops": B * fwd_flops / (max(ms - ms_lm, 1e-6) * 1e-3) / 1e12,
+                          "tdnn_tensor_frac": B * fwd_flops / (max(ms - ms_lm, 1e-6) * 1e-3) / 1e12 / peaks["bf16_tflops"]})
+            del g, x, feats
+            torch.cuda.empty_cache()
+        del model
+    return {"metric": "log-mel + TDNN forward sweep (BASELINE config 5)", "unit": "audio-sec/s", "n_gpus": 1,
+            "dtype": "bf16", "data": "synthetic", "peak_source": peaks["source"], "cells": cells}
+
+
 WORKLOADS = {"logmel": LogmelWorkload, "xvector_train": XVectorTrainWorkload,
              "xvector_ap_train": XVectorAPTrainWorkload}
 DEFAULT_WORKLOAD = os.environ.get("LBX_BENCH_WORKLOAD", "xvector_train")
@@ -522,7 +565,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="lidbox_b200", choices=["lidbox_b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + ["fwd_sweep"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--seconds", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -550,6 +593,10 @@ def main():
     from lidbox_b200 import _lib
     lib = _lib.lib()
     peaks = load_peaks()
+    if args.workload == "fwd_sweep":
+        if rank == 0:
+            print(json.dumps(bench_fwd_sweep(device)), flush=True)
+        return
     wl = WORKLOADS[args.workload](args, rank, world)
     wl.dist = dist
     _log("setup")

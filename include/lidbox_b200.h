@@ -101,6 +101,23 @@ int lbx_logmel_f32_host(const float* sig_host, long long B, long long N, int sam
                         size_t dev_tables_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Feature normalisation (the step after log-mel in every pipeline: tf_utils.py:189-194, steps.py:821-834)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* lidbox/features/__init__.py:16-20 cmn (mode 0), :26-32 cmvn (mode 1), :5-9 feature_scaling over one axis (mode 2,
+ * result in [lo, hi]).  The tensor is viewed as [outer, R, inner] with R the reduced axis; fp32, two-pass statistics,
+ * population std, divide_no_nan semantics. */
+int lbx_normalize_axis_f32(const float* x, float* y, long long outer, long long R, long long inner, int mode, float lo,
+                           float hi, void* stream);
+/* feature_scaling with axis=None (min/max over the whole tensor); workspace: >= 8 bytes of device memory */
+int lbx_feature_scaling_all_f32(const float* x, float* y, long long n, float lo, float hi, void* workspace,
+                                void* stream);
+/* lidbox/features/__init__.py:40-67 window_normalization over the time axis of [B,T,F] for 1 <= window_len < T
+ * (REFLECT padding w/2 left, w/2-1+(w&1) right; mean / population std over each window) */
+int lbx_window_normalization_f32(const float* x, float* y, long long B, int T, int F, int window_len,
+                                 int normalize_variance, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * TDNN contractions (replace Keras Conv1D / Dense behind lidbox/models/xvector.py:38-43,53-64 and their gradients)
  * ---------------------------------------------------------------------------------------------------------- */
 

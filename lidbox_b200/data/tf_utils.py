@@ -9,6 +9,7 @@ Re-entrant: every call works on the calling thread's current CUDA stream and sha
 import numpy as np
 import torch
 
+from .. import features
 from ..features import audio as audio_features
 
 
@@ -40,6 +41,12 @@ def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_
         raise ValueError("unknown feature type " + repr(feattype))
     if check_finite:
         audio_features.assert_all_finite(X, feattype + " failed")
-    if feat_scale_kwargs or window_norm_kwargs:
-        raise NotImplementedError("feature_scaling / window_normalization are 'next' rows of SURVEY.md §8(f)")
+    if feat_scale_kwargs:
+        X = features.feature_scaling(X, **feat_scale_kwargs)                      # tf_utils.py:189-191
+        if check_finite:
+            audio_features.assert_all_finite(X, "feature scaling failed")
+    if window_norm_kwargs:
+        X = features.window_normalization(X, **window_norm_kwargs)                 # tf_utils.py:192-194
+        if check_finite:
+            audio_features.assert_all_finite(X, "window normalization failed")
     return X

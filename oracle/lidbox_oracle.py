@@ -173,7 +173,7 @@ def logmel(signals, sample_rate, frame_length_ms=25, frame_step_ms=10, power=2.0
 def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_kwargs=None, mfcc_kwargs=None,
                      db_spec_kwargs=None, feat_scale_kwargs=None, window_norm_kwargs=None):
     """lidbox/data/tf_utils.py:166-195 (with the broken `melspectrograms` name read as `linear_to_mel`).
-    feature scaling / window normalisation / mfcc are outside the oracle's scope ("next" rows)."""
+    mfcc is outside the oracle's scope (a "next" row)."""
     signals = np.asarray(signals, np.float32)
     if signals.ndim != 2:
         raise ValueError("signals must be [B, N]")
@@ -192,7 +192,57 @@ def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_
         raise NotImplementedError(feattype)
     if not np.isfinite(X).all():
         raise FloatingPointError(feattype + " failed")
+    if feat_scale_kwargs:
+        X = feature_scaling(X, **feat_scale_kwargs)           # tf_utils.py:189-191
+    if window_norm_kwargs:
+        X = window_normalization(X, **window_norm_kwargs)     # tf_utils.py:192-194
     return X
+
+
+# --------------------------------------------------------------------------- #
+# lidbox/features/__init__.py  (feature normalisation)
+# --------------------------------------------------------------------------- #
+
+
+def _divide_no_nan(a, b):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(b == 0, 0.0, a / np.where(b == 0, 1.0, b))
+
+
+def feature_scaling(X, min, max, axis=None):
+    """lidbox/features/__init__.py:5-9."""
+    X = np.asarray(X, np.float64)
+    x_min = X.min(axis=axis, keepdims=True)
+    x_max = X.max(axis=axis, keepdims=True)
+    return min + (max - min) * _divide_no_nan(X - x_min, x_max - x_min)
+
+
+def cmn(X, axis=1):
+    """lidbox/features/__init__.py:16-20."""
+    X = np.asarray(X, np.float64)
+    return X - X.mean(axis=axis, keepdims=True)
+
+
+def cmvn(X, axis=1):
+    """lidbox/features/__init__.py:26-32 (tf.math.reduce_std = population standard deviation)."""
+    X = np.asarray(X, np.float64)
+    return _divide_no_nan(cmn(X, axis), X.std(axis=axis, keepdims=True))
+
+
+def window_normalization(X, axis=1, window_len=-1, normalize_variance=True):
+    """lidbox/features/__init__.py:40-67: REFLECT padding (w//2 left, w//2 - 1 + (w & 1) right), tf.signal.frame(step 1)."""
+    X = np.asarray(X, np.float64)
+    if window_len == -1 or X.shape[1] <= window_len:
+        return cmvn(X, axis) if normalize_variance else cmn(X, axis)
+    assert axis == 1
+    w = window_len
+    Xp = np.pad(X, [(0, 0), (w // 2, w // 2 - 1 + (w & 1)), (0, 0)], mode="reflect")
+    idx = np.arange(X.shape[1])[:, None] + np.arange(w)[None, :]
+    windows = Xp[:, idx, :]                                   # [B, T, w, F]
+    out = X - windows.mean(axis=2)
+    if normalize_variance:
+        out = _divide_no_nan(out, windows.std(axis=2))
+    return out
 
 
 # --------------------------------------------------------------------------- #

@@ -190,3 +190,46 @@ def test_full_size_properties(audio):
     P = S[7, 0].double().cpu().numpy()
     lhs = P[0] + P[256] + 2 * P[1:256].sum()
     assert abs(lhs - 512 * (fr ** 2).sum()) / lhs < 1e-5
+
+
+def test_feature_normalisation_parity(built_lib):
+    # lidbox/features/__init__.py: fp32 kernels vs the fp64 oracle, tolerance 1e-4 normwise
+    from lidbox_b200 import features as F
+    rng = np.random.default_rng(20)
+    for shape in ((4, 198, 40), (1, 1, 1), (3, 17, 5), (2, 498, 40)):
+        x = (rng.standard_normal(shape) * 3 - 5).astype(np.float32)
+        for axis in range(3):
+            assert _normwise(F.cmn(x, axis=axis).cpu().numpy(), O.cmn(x, axis)) < 1e-4 or x.shape[axis] == 1
+            np.testing.assert_allclose(F.cmvn(x, axis=axis).cpu().numpy(), O.cmvn(x, axis), rtol=1e-4, atol=1e-4)
+        for axis in (None, 0, 1, 2):
+            y = F.feature_scaling(x, -1.0, 2.5, axis=axis).cpu().numpy()
+            np.testing.assert_allclose(y, O.feature_scaling(x, -1.0, 2.5, axis=axis), rtol=1e-5, atol=1e-5)
+    # reference property tests (tests/test_features.py:28-58) on the CUDA path
+    for _ in range(5):
+        x = rng.uniform(-100, 100, size=rng.integers(1, 20, size=3)).astype(np.float32)
+        for axis in range(3):
+            y_mv = F.cmvn(x, axis=axis).cpu().numpy()
+            assert not np.isnan(y_mv).any() and y_mv.shape == x.shape
+            assert np.abs(y_mv.mean(axis=axis)).max() < 0.1 and y_mv.var(axis=axis).max() < 10
+        for window_len in [-1] + list(range(2, x.shape[0] + 1)):
+            for nv in (True, False):
+                y = F.window_normalization(x, axis=1, window_len=window_len, normalize_variance=nv).cpu().numpy()
+                assert not np.isnan(y).any() and y.shape == x.shape
+                np.testing.assert_allclose(y, O.window_normalization(x, 1, window_len, nv), rtol=2e-4, atol=2e-4)
+    x = (rng.standard_normal((8, 298, 40)) * 2 + 1).astype(np.float32)
+    for w in (100, 101, 297):
+        y = F.window_normalization(x, window_len=w).cpu().numpy()
+        np.testing.assert_allclose(y, O.window_normalization(x, 1, w, True), rtol=2e-4, atol=2e-4)
+
+
+def test_map_stage_with_normalisation(built_lib):
+    from lidbox_b200.data import tf_utils
+    rng = np.random.default_rng(21)
+    sig = (rng.standard_normal((2, 32000)) * 0.1).astype(np.float32)
+    rates = np.array([16000, 16000])
+    kw = dict(feat_scale_kwargs={"min": 0.0, "max": 1.0, "axis": None},
+              window_norm_kwargs={"window_len": 100, "normalize_variance": True})
+    X = tf_utils.extract_features(sig, rates, "logmelspectrogram", {}, {}, {}, {}, kw["feat_scale_kwargs"],
+                                  kw["window_norm_kwargs"]).cpu().numpy()
+    ref = O.extract_features(sig, rates, "logmelspectrogram", **kw)
+    np.testing.assert_allclose(X, ref, rtol=2e-3, atol=2e-3)

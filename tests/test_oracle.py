@@ -200,3 +200,54 @@ def test_torch_logmel_baseline_matches_oracle():
     a = O.torch_logmel(torch.from_numpy(s)).numpy()
     b = O.logmel(s, 16000, dtype=np.float64)
     np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-4)
+
+
+def test_feature_scaling_reference():
+    # /root/reference/tests/test_features.py:14-26 (fewer repetitions)
+    rng = np.random.default_rng(10)
+    for rank in range(1, 5):
+        for _ in range(20):
+            delta = rng.uniform(1, 1e3)
+            lo = rng.uniform(-delta, delta)
+            hi = lo + rng.uniform(0, delta / 2)
+            x = rng.normal(0, delta ** 2, size=rng.integers(2, 20, size=rank))
+            for axis in [None] + list(range(rank)):
+                y = O.feature_scaling(x, lo, hi, axis=axis)
+                assert not np.isnan(y).any() and y.shape == x.shape
+                assert np.abs(y.min(axis=axis) - lo).max() < 1e-9
+                assert np.abs(y.max(axis=axis) - hi).max() < 1e-9
+
+
+def test_cmvn_reference():
+    # tests/test_features.py:28-43
+    rng = np.random.default_rng(11)
+    for delta_magnitude in range(2, 7):
+        for _ in range(20):
+            delta = rng.uniform(1, 10 ** delta_magnitude)
+            x = rng.uniform(-delta, delta, size=rng.integers(1, 20, size=3))
+            for axis in range(3):
+                y_m = O.cmn(x, axis=axis)
+                assert not np.isnan(y_m).any() and y_m.shape == x.shape
+                assert np.abs(y_m.mean(axis=axis)).max() < 1
+                y_mv = O.cmvn(x, axis=axis)
+                assert not np.isnan(y_mv).any() and y_mv.shape == x.shape
+                assert np.abs(y_mv.mean(axis=axis)).max() < 0.1
+                assert y_mv.var(axis=axis).max() < 10
+
+
+def test_window_normalization_reference():
+    # tests/test_features.py:45-58 + the reference's own NumPy variant (features/__init__.py:90-110) for odd windows,
+    # whose clipped (un-padded) windows coincide with the reflected ones in the interior of the signal
+    rng = np.random.default_rng(12)
+    for _ in range(20):
+        x = rng.uniform(-100, 100, size=rng.integers(1, 20, size=3))
+        for window_len in [-1] + list(range(2, x.shape[0] + 1)):
+            for nv in (True, False):
+                y = O.window_normalization(x, axis=1, window_len=window_len, normalize_variance=nv)
+                assert not np.isnan(y).any() and y.shape == x.shape
+    x = rng.standard_normal((2, 50, 3))
+    w = 7
+    y = O.window_normalization(x, window_len=w, normalize_variance=True)
+    for t in range(w // 2, 50 - w // 2):
+        win = x[:, t - w // 2:t - w // 2 + w]
+        np.testing.assert_allclose(y[:, t], (x[:, t] - win.mean(axis=1)) / win.std(axis=1), atol=1e-12)

@@ -200,7 +200,12 @@ def test_feature_normalisation_parity(built_lib):
         x = (rng.standard_normal(shape) * 3 - 5).astype(np.float32)
         for axis in range(3):
             assert _normwise(F.cmn(x, axis=axis).cpu().numpy(), O.cmn(x, axis)) < 1e-4 or x.shape[axis] == 1
-            np.testing.assert_allclose(F.cmvn(x, axis=axis).cpu().numpy(), O.cmvn(x, axis), rtol=1e-4, atol=1e-4)
+            # (x - mean) / std is ill-conditioned in fp32 when std << |x| (e.g. two nearly equal values): the bound is
+            # 1e-4 plus the fp32 rounding of x relative to std
+            ref = O.cmvn(x, axis)
+            std = x.astype(np.float64).std(axis=axis, keepdims=True)
+            tol = 1e-4 + 4e-7 * np.abs(x).max() / np.maximum(std, 1e-30)
+            assert (np.abs(F.cmvn(x, axis=axis).cpu().numpy() - ref) <= tol * (1 + np.abs(ref))).all()
         for axis in (None, 0, 1, 2):
             y = F.feature_scaling(x, -1.0, 2.5, axis=axis).cpu().numpy()
             np.testing.assert_allclose(y, O.feature_scaling(x, -1.0, 2.5, axis=axis), rtol=1e-5, atol=1e-5)

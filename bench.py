@@ -454,8 +454,12 @@ def bench_logmel_quick(device, B=2048, sec=5):
     ms = _time_cuda(lambda: audio.logmelspectrograms(x, SR, out=out), 10)
     peaks = load_peaks()
     gbs = B * (4 * N + 4 * T * 40) / (ms * 1e-3) / 1e9
+    # the fused kernel is FP32-issue bound, not HBM bound: 747 warp instructions per frame (ncu, profiles/README.md),
+    # i.e. at most 4 IPC x 148 SMs x 1.965 GHz / 747 = 1.56 G frames/s if every scheduler issued every cycle
+    issue_bound = 4 * 148 * 1.965e9 / 747.0
     return {"frames_per_s": B * T / (ms * 1e-3), "ms": ms, "hbm_GBps_algorithmic": gbs,
-            "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"]}
+            "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
+            "issue_bound_frames_per_s": issue_bound, "frac_of_issue_bound": B * T / (ms * 1e-3) / issue_bound}
 
 
 def bench_embed_quick(device, B=64, sec=2):

@@ -118,6 +118,23 @@ int lbx_window_normalization_f32(const float* x, float* y, long long B, int T, i
                                  int normalize_variance, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Energy VAD (the step before the feature stage: steps.py:417-432 compute_rms_vad, :183-200 apply_vad)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* lidbox/features/audio.py:264-271 root_mean_square over the last axis of a [rows, len] matrix */
+int lbx_row_rms_f32(const float* x, long long rows, int len, float* out, void* stream);
+/* audio.py:307-329 framewise_rms_energy_vad_decisions, batched: sig [B,N] -> decisions [B,F] (1 = voiced), F = N /
+ * frame_step non-overlapping frames; threshold = strength * max(min_rms_threshold, mean RMS of the utterance); runs of
+ * non-speech shorter than min_non_speech_frames are flipped back to speech (audio.py:289-296). rms_ws: [B,F] floats. */
+int lbx_rms_vad_f32(const float* sig, long long B, long long N, int frame_step, float strength,
+                    float min_rms_threshold, long long min_non_speech_frames, unsigned char* decisions, float* rms_ws,
+                    void* stream);
+/* audio.py:337-353 remove_silence / steps.py:191-198: keep the voiced frames of every utterance, compacted to the front
+ * of out [B,N]; out_len [B] = voiced samples; offsets_ws: [B,F] int64. */
+int lbx_vad_compact_f32(const float* sig, long long B, long long N, int frame_len, const unsigned char* decisions,
+                        long long F, float* out, long long* out_len, long long* offsets_ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * TDNN contractions (replace Keras Conv1D / Dense behind lidbox/models/xvector.py:38-43,53-64 and their gradients)
  * ---------------------------------------------------------------------------------------------------------- */
 

@@ -45,6 +45,9 @@ SIGNATURES = {
     "lbx_normalize_axis_f32": (c_int, [_P, _P, c_ll, c_ll, c_ll, c_int, c_float, c_float, _P]),
     "lbx_feature_scaling_all_f32": (c_int, [_P, _P, c_ll, c_float, c_float, _P, _P]),
     "lbx_window_normalization_f32": (c_int, [_P, _P, c_ll, c_int, c_int, c_int, c_int, _P]),
+    "lbx_row_rms_f32": (c_int, [_P, c_ll, c_int, _P, _P]),
+    "lbx_rms_vad_f32": (c_int, [_P, c_ll, c_ll, c_int, c_float, c_float, c_ll, _P, _P, _P]),
+    "lbx_vad_compact_f32": (c_int, [_P, c_ll, c_ll, c_int, _P, c_ll, _P, _P, _P, _P]),
     "lbx_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), _P]),
     "lbx_set_pdl": (c_int, [c_int]),
     "lbx_pack_rows_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, _P]),

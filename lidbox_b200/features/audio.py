@@ -110,3 +110,101 @@ def assert_all_finite(X, message):
     _lib.check(_lib.lib().lbx_check_finite_f32(_lib.ptr(Xc), Xc.numel(), _lib.ptr(flag), _lib.stream_ptr(X.device)))
     if int(flag.item()) != 0:
         raise FloatingPointError(message)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Energy VAD (lidbox/features/audio.py:264-353) — SURVEY.md §8(f) row 2.  The kernels are batched over utterances
+# ([B, N]); the reference's single-utterance signatures are served with B = 1.
+# ------------------------------------------------------------------------------------------------------------
+def root_mean_square(x, axis=-1):
+    """lidbox/features/audio.py:262-271 (rank-2 input, RMS over `axis`)."""
+    t = _as_device_f32(x, 2, "x")
+    if axis in (0, -2):
+        t = t.t().contiguous()
+    elif axis not in (1, -1):
+        raise ValueError("axis out of range for a rank-2 tensor")
+    rows, n = t.shape
+    out = torch.empty((rows,), dtype=torch.float32, device=t.device)
+    if n == 0:
+        return out.fill_(float("nan"))
+    _lib.check(_lib.lib().lbx_row_rms_f32(_lib.ptr(t), rows, n, _lib.ptr(out), _lib.stream_ptr(t.device)))
+    return out
+
+
+def run_length_encoding(v):
+    """lidbox/features/audio.py:273-283: (start positions, lengths) of the runs of equal values of an int vector.
+    Index bookkeeping on a handful of elements: done on the host."""
+    v = np.asarray(v.cpu() if isinstance(v, torch.Tensor) else v).reshape(-1)
+    if v.size == 0:
+        return torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64)
+    change = np.flatnonzero(v[1:] != v[:-1])
+    i = np.concatenate(([-1], change, [v.size - 1]))
+    pos = np.concatenate(([0], np.cumsum(i[1:] - i[:-1])))
+    return torch.from_numpy(pos[:-1].astype(np.int64)), torch.from_numpy((pos[1:] - pos[:-1]).astype(np.int64))
+
+
+def invert_too_short_consecutive_false(mask, min_length):
+    """lidbox/features/audio.py:285-296: runs of False shorter than min_length become True."""
+    m = np.asarray(mask.cpu() if isinstance(mask, torch.Tensor) else mask).astype(bool).reshape(-1)
+    if min_length == 0 or m.size == 0:
+        return torch.from_numpy(m.copy())
+    pos, lengths = run_length_encoding(m.astype(np.int32))
+    keep = np.logical_or(m[pos.numpy()], lengths.numpy() < min_length)
+    return torch.from_numpy(np.repeat(keep, lengths.numpy()))
+
+
+def batched_rms_vad(signals, sample_rate, frame_step_ms, min_non_speech_ms=0, strength=0.05, min_rms_threshold=1e-3):
+    """framewise_rms_energy_vad_decisions for a batch [B, N] in two kernel launches -> bool [B, N // frame_step]."""
+    sig = _as_device_f32(signals, 2, "signals")
+    B, N = sig.shape
+    step = ms_to_frames(sample_rate, frame_step_ms)
+    if step < 1:
+        raise ValueError("frame step must be at least one sample")
+    F = N // step
+    # audio.py:325: cast(ms_to_frames(sr, min_non_speech_ms) / frame_step, int64) — true division, then truncation
+    min_frames = int(ms_to_frames(sample_rate, min_non_speech_ms) / step)
+    dec = torch.zeros((B, F), dtype=torch.uint8, device=sig.device)
+    ws = torch.empty((B, max(F, 1)), dtype=torch.float32, device=sig.device)
+    _lib.check(_lib.lib().lbx_rms_vad_f32(_lib.ptr(sig), B, N, step, float(strength), float(min_rms_threshold),
+                                          min_frames, _lib.ptr(dec), _lib.ptr(ws), _lib.stream_ptr(sig.device)))
+    return dec.bool()
+
+
+def framewise_rms_energy_vad_decisions(signal, sample_rate, frame_step_ms, min_non_speech_ms=0, strength=0.05,
+                                       min_rms_threshold=1e-3, time_axis=0):
+    """lidbox/features/audio.py:298-329 (rank-1 signal; True = voiced)."""
+    if time_axis != 0:
+        raise NotImplementedError("only time_axis=0 (the rank-1 signature of the reference) is implemented")
+    s = torch.as_tensor(np.asarray(signal) if not isinstance(signal, torch.Tensor) else signal)
+    if s.dim() != 1:
+        raise ValueError("signal must have rank 1")
+    return batched_rms_vad(s[None], sample_rate, frame_step_ms, min_non_speech_ms, strength, min_rms_threshold)[0]
+
+
+def batched_remove_silence(signals, rate, window_ms=10, min_non_speech_ms=300, vad=None):
+    """remove_silence / apply_vad for a batch: returns (out [B, N] with the voiced windows compacted to the front,
+    lengths [B] in samples).  `vad` may carry precomputed decisions [B, F] (steps.py:191-198)."""
+    sig = _as_device_f32(signals, 2, "signals")
+    B, N = sig.shape
+    window = (int(window_ms) * int(rate)) // 1000               # audio.py:341 (integer arithmetic, not ms_to_frames)
+    if vad is None:
+        vad = batched_rms_vad(sig, rate, window_ms, min_non_speech_ms=min_non_speech_ms, strength=0.1)
+    dec = vad.to(sig.device, torch.uint8).contiguous()
+    F = dec.shape[1]
+    if window < 1 or F * window > N:
+        raise ValueError("VAD decisions do not match the signal length")
+    out = torch.zeros_like(sig)
+    lengths = torch.zeros((B,), dtype=torch.int64, device=sig.device)
+    offs = torch.empty((B, max(F, 1)), dtype=torch.int64, device=sig.device)
+    _lib.check(_lib.lib().lbx_vad_compact_f32(_lib.ptr(sig), B, N, window, _lib.ptr(dec), F, _lib.ptr(out),
+                                              _lib.ptr(lengths), _lib.ptr(offs), _lib.stream_ptr(sig.device)))
+    return out, lengths
+
+
+def remove_silence(signal, rate, window_ms=10, min_non_speech_ms=300):
+    """lidbox/features/audio.py:331-353 (rank-1 signal -> voiced samples)."""
+    s = torch.as_tensor(np.asarray(signal) if not isinstance(signal, torch.Tensor) else signal)
+    if s.dim() != 1:
+        raise ValueError("signal must have rank 1")
+    out, lengths = batched_remove_silence(s[None], rate, window_ms, min_non_speech_ms)
+    return out[0, :int(lengths[0].item())]

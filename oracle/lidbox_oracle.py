@@ -200,6 +200,60 @@ def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_
 
 
 # --------------------------------------------------------------------------- #
+# energy VAD, lidbox/features/audio.py:262-353  
+# --------------------------------------------------------------------------- #
+
+
+def root_mean_square(x, axis=-1):
+    """lidbox/features/audio.py:265-269."""
+    x = np.asarray(x, np.float64)
+    return np.sqrt(np.mean(np.square(np.abs(x)), axis=axis))
+
+
+def run_length_encoding(v):
+    """lidbox/features/audio.py:276-283."""
+    v = np.asarray(v).reshape(-1)
+    i = np.concatenate(([-1], np.flatnonzero(v[1:] != v[:-1]), [v.size - 1]))
+    pos = np.concatenate(([0], np.cumsum(i[1:] - i[:-1])))
+    return pos[:-1], pos[1:] - pos[:-1]
+
+
+def invert_too_short_consecutive_false(mask, min_length):
+    """lidbox/features/audio.py:289-296."""
+    mask = np.asarray(mask, bool)
+    if min_length == 0:
+        return mask
+    pos, lengths = run_length_encoding(mask.astype(np.int32))
+    return np.repeat(np.logical_or(mask[pos], lengths < min_length), lengths)
+
+
+def framewise_rms_energy_vad_decisions(signal, sample_rate, frame_step_ms, min_non_speech_ms=0, strength=0.05,
+                                       min_rms_threshold=1e-3, return_margin=False):
+    """lidbox/features/audio.py:307-329 (non-overlapping frames of ms_to_frames(sr, frame_step_ms) samples)."""
+    signal = np.asarray(signal, np.float64)
+    step = ms_to_frames(sample_rate, frame_step_ms)
+    F = signal.shape[0] // step
+    frames = signal[:F * step].reshape(F, step)
+    rms = root_mean_square(frames, axis=1)
+    threshold = strength * max(min_rms_threshold, rms.mean()) if F else 0.0
+    decisions = rms > threshold
+    min_frames = int(ms_to_frames(sample_rate, min_non_speech_ms) / step)
+    out = invert_too_short_consecutive_false(decisions, min_frames)
+    if return_margin:       # relative distance of every frame's RMS from the threshold (ties are not comparable in fp32)
+        return out, np.abs(rms - threshold) / max(threshold, 1e-30)
+    return out
+
+
+def remove_silence(signal, rate, window_ms=10, min_non_speech_ms=300):
+    """lidbox/features/audio.py:337-353."""
+    signal = np.asarray(signal)
+    window = (window_ms * rate) // 1000
+    vad = framewise_rms_energy_vad_decisions(signal, rate, window_ms, min_non_speech_ms=min_non_speech_ms, strength=0.1)
+    F = signal.shape[0] // window
+    return signal[:F * window].reshape(F, window)[vad[:F]].reshape(-1)
+
+
+# --------------------------------------------------------------------------- #
 # lidbox/features/__init__.py  (feature normalisation, SURVEY §8(f) row 1)
 # --------------------------------------------------------------------------- #
 

@@ -238,3 +238,43 @@ def test_map_stage_with_normalisation(built_lib):
                                   kw["window_norm_kwargs"]).cpu().numpy()
     ref = O.extract_features(sig, rates, "logmelspectrogram", **kw)
     np.testing.assert_allclose(X, ref, rtol=2e-3, atol=2e-3)
+
+
+def test_vad_parity_and_reference_properties(audio):
+    # SURVEY §8(f) row 2.  Masks must be identical to the oracle's wherever the frame RMS is not within 1e-5 (relative)
+    # of the threshold: fp32 summation order is not comparable across implementations exactly at a tie.
+    g = np.load(os.path.join(GOLDEN, "wav_fixtures.npz"))
+    for pcm in g["pcm"]:
+        s = pcm.astype(np.float32) / np.float32(32768.0)
+        vad = audio.framewise_rms_energy_vad_decisions(s, 16000, 25)
+        assert vad.dtype == torch.bool and bool(vad.all())                       # tests/test_features_audio.py:175-179
+        assert audio.remove_silence(s, 16000).shape == s.shape                   # :183-188
+    z = np.zeros(3 * 16000, np.float32)
+    assert not bool(audio.framewise_rms_energy_vad_decisions(z, 16000, 25).any())    # :180-181
+    assert audio.remove_silence(z, 16000).numel() == 0                           # :189-191
+    pos, length = audio.run_length_encoding(np.array([1, 1, 1, 2, 2, 2, 3, 4, 5, 6, 6, 7]))
+    assert pos.tolist() == [0, 3, 6, 7, 8, 9, 11] and length.tolist() == [3, 3, 1, 1, 1, 2, 1]   # :166-169 exact KAT
+    rng = np.random.default_rng(30)
+    x = rng.normal(0, 5, size=(7, 9))
+    np.testing.assert_allclose(audio.root_mean_square(x, axis=-1).cpu().numpy(), O.root_mean_square(x), rtol=1e-5)
+    # speech-like bursts separated by silence, batched
+    B, N = 6, 48000
+    sig = np.zeros((B, N), np.float32)
+    for b in range(B):
+        for _ in range(4):
+            a, n = int(rng.integers(0, N - 8000)), int(rng.integers(800, 8000))
+            tone = np.sin(2 * np.pi * rng.uniform(100, 3000) * np.arange(n) / 16000.0)
+            sig[b, a:a + n] += (rng.uniform(0.05, 0.8) * tone).astype(np.float32)
+        sig[b] += 1e-4 * rng.standard_normal(N).astype(np.float32)
+    for (ms, nonspeech, strength) in ((10, 0, 0.05), (10, 300, 0.1), (25, 100, 0.5), (30, 0, 1.0)):
+        dec = audio.batched_rms_vad(sig, 16000, ms, min_non_speech_ms=nonspeech, strength=strength).cpu().numpy()
+        for b in range(B):
+            ref, margin = O.framewise_rms_energy_vad_decisions(sig[b], 16000, ms, nonspeech, strength, return_margin=True)
+            assert dec[b].shape == ref.shape
+            if (margin > 1e-5).all():
+                assert (dec[b] == ref).all()
+    out, lengths = audio.batched_remove_silence(sig, 16000)
+    for b in range(B):
+        ref = O.remove_silence(sig[b], 16000)
+        assert int(lengths[b]) == ref.size
+        assert np.array_equal(out[b, :ref.size].cpu().numpy(), ref)              # compaction is a pure copy: bit-exact

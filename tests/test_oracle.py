@@ -251,3 +251,34 @@ def test_window_normalization_reference():
     for t in range(w // 2, 50 - w // 2):
         win = x[:, t - w // 2:t - w // 2 + w]
         np.testing.assert_allclose(y[:, t], (x[:, t] - win.mean(axis=1)) / win.std(axis=1), atol=1e-12)
+
+
+def test_run_length_encoding_reference_kat():
+    # /root/reference/tests/test_features_audio.py:166-169 (exact)
+    pos, length = O.run_length_encoding(np.array([1, 1, 1, 2, 2, 2, 3, 4, 5, 6, 6, 7]))
+    assert (pos == np.array([0, 3, 6, 7, 8, 9, 11])).all()
+    assert (length == np.array([3, 3, 1, 1, 1, 2, 1])).all()
+
+
+def test_root_mean_square_reference():
+    # tests/test_features_audio.py:157-163
+    rng = np.random.default_rng(13)
+    for _ in range(20):
+        x = rng.normal(0, 5, size=rng.integers(1, 10, size=2))
+        assert np.abs(np.sqrt(np.mean(np.square(np.abs(x)), axis=-1)) - O.root_mean_square(x, axis=-1)).max() < 1e-5
+
+
+def test_vad_reference_properties():
+    # tests/test_features_audio.py:175-191 on the reference's WAV fixtures (first 0.5 s, carried by the golden file)
+    g = np.load(os.path.join(GOLDEN, "wav_fixtures.npz"))
+    for pcm in g["pcm"]:
+        s = pcm.astype(np.float32) / np.float32(32768.0)
+        assert O.framewise_rms_energy_vad_decisions(s, 16000, 25).all()
+        assert O.remove_silence(s, 16000).shape == s.shape
+    z = np.zeros(3 * 16000, np.float32)
+    assert not O.framewise_rms_energy_vad_decisions(z, 16000, 25).any()
+    assert O.remove_silence(z, 16000).size == 0
+    # too-short non-speech runs are flipped back to speech
+    m = np.array([1, 0, 0, 1, 0, 0, 0, 0, 1, 0], bool)
+    assert (O.invert_too_short_consecutive_false(m, 3) == np.array([1, 1, 1, 1, 0, 0, 0, 0, 1, 1], bool)).all()
+    assert (O.invert_too_short_consecutive_false(m, 0) == m).all()

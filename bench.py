@@ -231,16 +231,10 @@ class XVectorTrainWorkload:
     def setup(self, device):
         from lidbox_b200.features import audio
         from lidbox_b200.models import xvector
-        self.audio, self.device = audio, device
+        self.audio, self.device, self.xvector = audio, device, xvector
         self.x_host, y = class_signals(self.B, self.N, self.n_classes, 1234 + self.rank, pin=True)
-        # two signal buffers and two feature buffers: while the model trains on the features of batch i, the log-mel
-        # of batch i+1 runs on a second stream (the prefetch a tf.data input pipeline does), and in the end-to-end
-        # path the H2D copy of batch i+2 runs on a copy stream.  Every replay = one log-mel + one training step.
-        self.xs = [self.x_host.to(device), self.x_host.to(device)]
-        self.x = self.xs[0]
         self.y = y.to(device)
-        self.fbuf = [torch.empty((self.B, self.T, 40), dtype=torch.float32, device=device) for _ in range(2)]
-        self.feats = self.fbuf[0]
+        self.feats = torch.empty((self.B, self.T, 40), dtype=torch.float32, device=device)
         self.model = xvector.create((self.T, 40), self.n_out, precision="bf16", head=self.head, seed=0)
         self.model.configure_optimizer(lr=1e-3)
         self.pg = self.dist.group.WORLD if self.dist is not None else None
@@ -254,21 +248,31 @@ class XVectorTrainWorkload:
                 self.dp_exchange = "one NCCL all-reduce of the flat fp32 gradient, then full-size Adam"
         self.kw = dict(ap_classes=self.n_classes) if self.loss == "ap" else {}
         self.pipelined = os.environ.get("LBX_BENCH_PIPELINE", "1") != "0"
-        self.i = 0
-        self.steps = []
-        self.audio.logmelspectrograms(self.xs[0], SR, out=self.fbuf[0])          # prime the pipeline
+        self.pipes = {}
+        self.pipe = self._build_pipe(self.x_host)
+        self.x = self.pipe["xs"][0]
+        self.graphed = self.pipe["steps"][0] if self.use_graph else None
+
+    def _build_pipe(self, x_host):
+        """Two signal buffers (dtype of x_host: float32 or 16-bit PCM) and two feature buffers: while the model trains
+        on the features of batch i, the log-mel of batch i+1 runs on a second stream (the prefetch a tf.data input
+        pipeline does), and in the end-to-end path the H2D copy of batch i+2 runs on a copy stream.
+        Every replay = one log-mel + one training step."""
+        dev, audio, xvector = self.device, self.audio, self.xvector
+        pipe = {"x_host": x_host, "xs": [x_host.to(dev), x_host.to(dev)], "i": 0, "steps": [], "e2e": None,
+                "fbuf": [torch.empty((self.B, self.T, 40), dtype=torch.float32, device=dev) for _ in range(2)]}
+        audio.logmelspectrograms(pipe["xs"][0], SR, out=pipe["fbuf"][0])          # prime the pipeline
         for k in range(2):
-            nxt = (lambda k=k: self.audio.logmelspectrograms(self.xs[1 - k], SR, out=self.fbuf[1 - k]))
-            inline = (lambda k=k: self.audio.logmelspectrograms(self.xs[k], SR, out=self.fbuf[k]))
+            nxt = (lambda k=k: audio.logmelspectrograms(pipe["xs"][1 - k], SR, out=pipe["fbuf"][1 - k]))
+            inline = (lambda k=k: audio.logmelspectrograms(pipe["xs"][k], SR, out=pipe["fbuf"][k]))
             if self.use_graph:
-                self.steps.append(xvector.GraphedTrainStep(
-                    self.model, self.fbuf[k], self.y, loss=self.loss, process_group=self.pg,
+                pipe["steps"].append(xvector.GraphedTrainStep(
+                    self.model, pipe["fbuf"][k], self.y, loss=self.loss, process_group=self.pg,
                     pre=None if self.pipelined else inline, concurrent=nxt if self.pipelined else None, **self.kw))
             else:
-                self.steps.append(lambda inline=inline: self.model.train_step(inline(), self.y, loss=self.loss,
-                                                                              process_group=self.pg, **self.kw))
-        self.graphed = self.steps[0] if self.use_graph else None
-        self.e2e = None
+                pipe["steps"].append(lambda inline=inline: self.model.train_step(inline(), self.y, loss=self.loss,
+                                                                                 process_group=self.pg, **self.kw))
+        return pipe
 
     def _features(self):
         return self.audio.logmelspectrograms(self.x, SR, out=self.feats)
@@ -279,15 +283,16 @@ class XVectorTrainWorkload:
     def units_per_step(self):
         return self.B * self.sec
 
-    def step(self):
-        out = self.steps[self.i % 2]()
-        self.i += 1
+    def step(self, pipe=None):
+        pipe = pipe or self.pipe
+        out = pipe["steps"][pipe["i"] % 2]()
+        pipe["i"] += 1
         return out
 
     def launches_per_step(self):
         return self.graphed.kernels_per_step if self.graphed is not None else None
 
-    def _setup_e2e(self):
+    def _setup_e2e(self, pipe):
         dev = self.device
         e = {"copy": torch.cuda.Stream(device=dev),
              "h2d_done": [torch.cuda.Event(), torch.cuda.Event()], "step_done": torch.cuda.Event(),
@@ -295,37 +300,54 @@ class XVectorTrainWorkload:
         cur = torch.cuda.current_stream(dev)
         torch.cuda.synchronize(dev)
         # prime: batch 0 -> xs[k0] + its features, batch 1 -> xs[1-k0]
-        k0 = self.i % 2
-        self.xs[k0].copy_(self.x_host, non_blocking=True)
-        self.audio.logmelspectrograms(self.xs[k0], SR, out=self.fbuf[k0])
+        k0 = pipe["i"] % 2
+        pipe["xs"][k0].copy_(pipe["x_host"], non_blocking=True)
+        self.audio.logmelspectrograms(pipe["xs"][k0], SR, out=pipe["fbuf"][k0])
         with torch.cuda.stream(e["copy"]):
             e["copy"].wait_stream(cur)
-            self.xs[1 - k0].copy_(self.x_host, non_blocking=True)
+            pipe["xs"][1 - k0].copy_(pipe["x_host"], non_blocking=True)
             e["h2d_done"][1 - k0].record(e["copy"])
         e["step_done"].record(cur)
-        self.e2e = e
+        pipe["e2e"] = e
 
-    def step_e2e(self):
+    def step_e2e(self, pipe=None):
         """One step of the public-API pipeline with the batch in pinned HOST memory: replay k trains on the features
         of batch i (buffer k) and extracts the features of batch i+1 from device buffer 1-k, while batch i+2 is copied
         host->device into buffer k on the copy stream; the per-sample losses of batch i are copied back."""
-        if self.e2e is None:
-            self._setup_e2e()
-        e = self.e2e
-        k = self.i % 2
+        pipe = pipe or self.pipe
+        if pipe["e2e"] is None:
+            self._setup_e2e(pipe)
+        e = pipe["e2e"]
+        k = pipe["i"] % 2
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(e["h2d_done"][1 - k])                  # signals of batch i+1 are on the device
         prev_done = e["step_done"]
-        losses = self.step()
+        losses = self.step(pipe)
         e["step_done"] = torch.cuda.Event()
         e["step_done"].record(cur)
         with torch.cuda.stream(e["copy"]):
             e["copy"].wait_event(prev_done)                    # buffer k was last read by the previous replay
-            self.xs[k].copy_(self.x_host, non_blocking=True)
+            pipe["xs"][k].copy_(pipe["x_host"], non_blocking=True)
             e["h2d_done"][k].record(e["copy"])
         e["loss_host"][k].copy_(losses, non_blocking=True)
         if k == 1:
             cur.synchronize()                                  # host reads the losses of the last two steps
+
+    def e2e_pcm16(self, steps, barrier):
+        """Same end-to-end pipeline fed with 16-bit PCM (the sample format of the WAV corpora; decoded inside the
+        log-mel kernel exactly as read_wav does): half the host->device bytes.  Reported next to the float32 e2e."""
+        pcm = torch.clamp(torch.round(self.x_host * 32768.0), -32768, 32767).to(torch.int16).pin_memory()
+        pipe = self._build_pipe(pcm)
+        for _ in range(4):
+            self.step_e2e(pipe)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.step_e2e(pipe)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / steps, self.B * self.N * 2
 
     def e2e_bytes(self):
         return self.B * self.N * 4, self.B * 4
@@ -662,6 +684,14 @@ def main():
         e_ms = float(t.item())
     h2d, d2h = wl.e2e_bytes()
     _log("e2e done")
+    pcm = None
+    if hasattr(wl, "e2e_pcm16") and os.environ.get("LBX_BENCH_PCM16", "1") != "0":
+        p_ms, p_bytes = wl.e2e_pcm16(e_steps, barrier)
+        if dist is not None:
+            t = torch.tensor([p_ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            p_ms = float(t.item())
+        pcm = (p_ms, p_bytes)
 
     if rank == 0:
         units = wl.units_per_step() * world
@@ -672,6 +702,11 @@ def main():
                 "e2e": {"value": units / (e_ms / e_steps * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / e_steps},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if pcm is not None:
+            line["e2e_pcm16"] = {"value": units / (pcm[0] * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": pcm[1],
+                                 "d2h_bytes_per_step": d2h, "ms_per_step": pcm[0],
+                                 "note": "same pipeline, batches arrive as 16-bit PCM (WAV sample format) and are "
+                                         "decoded inside the log-mel kernel"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = wl.cpu_sample()
         if hasattr(wl, "extra"):

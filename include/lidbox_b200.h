@@ -84,6 +84,13 @@ int lbx_logmel_f32(const float* sig, long long B, long long N, int frame_length,
                    const float* band_w, int n_packed, int log_mode, float eps, float* out, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Same fused chain fed with 16-bit PCM (the sample format of the WAV corpora; lidbox/features/audio.py:17-33 read_wav
+ * decodes it to float32 as x / 32768, which is what the kernel does while staging): halves the host->device bytes of
+ * the input pipeline.  Fused 512-point configuration only. */
+int lbx_logmel_i16(const short* pcm, long long B, long long N, int frame_length, int frame_step, int fft_length,
+                   float power, int n_mel, const int* band_start, const int* band_len, const int* band_off,
+                   const float* band_w, int n_packed, int log_mode, float eps, float* out, void* stream);
+
 /* lidbox/features/audio.py:167-174  power_to_db(): 20*(log10(max(amin,S)) - log10(max(amin,max_all S))),
  * floored at max_all(db) - top_db.  workspace: >= 16 bytes of device memory. */
 int lbx_power_to_db_f32(const float* S, long long numel, float amin, float top_db, float* out, void* workspace,

@@ -40,6 +40,8 @@ SIGNATURES = {
     "lbx_logmel_workspace_bytes": (c_size_t, [c_ll, c_ll, c_int, c_int, c_int, c_int]),
     "lbx_logmel_f32": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_int, c_int,
                                c_float, _P, _P, c_size_t, _P]),
+    "lbx_logmel_i16": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_int, c_int,
+                               c_float, _P, _P]),
     "lbx_power_to_db_f32": (c_int, [_P, c_ll, c_float, c_float, _P, _P, _P]),
     "lbx_check_finite_f32": (c_int, [_P, c_ll, _P, _P]),
     "lbx_normalize_axis_f32": (c_int, [_P, _P, c_ll, c_ll, c_ll, c_int, c_float, c_float, _P]),

@@ -100,6 +100,7 @@ constexpr int P_FLOATS = (FR * P_STRIDE + 3) & ~3;
 
 struct FusedParams {
   const float* sig;
+  const short* sig_i16;  // when non-NULL the input is 16-bit PCM and is converted as x / 32768 (what decode_wav does)
   float* out;
   long long N;
   long long T;
@@ -169,7 +170,24 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) logmel512_kernel(const Fused
     const long long s0 = t0 * step;
     const int n_valid = (nf - 1) * step + L;                  // samples this CTA actually needs (all in range)
     const float* g = p.sig + (long long)b * p.N + s0;
-    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    if (p.sig_i16 != nullptr) {
+      const short* gi = p.sig_i16 + (long long)b * p.N + s0;
+      if ((reinterpret_cast<uintptr_t>(gi) & 15) == 0) {
+        const int n8 = n_valid >> 3;
+        for (int i = tid; i < n8; i += FUSED_THREADS) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(gi) + i);
+          const unsigned int w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            s_sig[8 * i + 2 * k] = (float)(short)(w[k] & 0xFFFFu) * (1.0f / 32768.0f);
+            s_sig[8 * i + 2 * k + 1] = (float)(short)(w[k] >> 16) * (1.0f / 32768.0f);
+          }
+        }
+        for (int i = (n8 << 3) + tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = (float)__ldg(gi + i) * (1.0f / 32768.0f);
+      } else {
+        for (int i = tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = (float)__ldg(gi + i) * (1.0f / 32768.0f);
+      }
+    } else if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
       const int n4 = n_valid >> 2;
       const float4* g4 = reinterpret_cast<const float4*>(g);
       float4* s4 = reinterpret_cast<float4*>(s_sig);
@@ -542,6 +560,28 @@ int lbx_logmel_f32(const float* sig, long long B, long long N, int frame_length,
   if (rc) return rc;
   return lbx_linear_to_mel_f32((const float*)workspace, B * T, K, n_mel, band_start, band_len, band_off, band_w,
                                n_packed, log_mode, eps, out, stream);
+}
+
+int lbx_logmel_i16(const short* pcm, long long B, long long N, int frame_length, int frame_step, int fft_length,
+                   float power, int n_mel, const int* band_start, const int* band_len, const int* band_off,
+                   const float* band_w, int n_packed, int log_mode, float eps, float* out, void* stream) {
+  int rc = check_stft_args(reinterpret_cast<const float*>(pcm), B, N, frame_length, frame_step, fft_length);
+  if (rc) return rc;
+  LBX_CHECK_ARG(n_mel >= 1 && n_packed >= 0, "bad n_mel=%d n_packed=%d", n_mel, n_packed);
+  LBX_CHECK_ARG(log_mode == 0 || log_mode == 1, "log_mode must be 0 or 1");
+  const long long T = lbx_num_frames(N, frame_length, frame_step);
+  if (B == 0 || T == 0) return LBX_OK;
+  LBX_CHECK_ARG(out && band_start && band_len && band_off && band_w, "NULL pointer argument");
+  if (!fused_ok(frame_length, frame_step, fft_length, n_mel, n_packed))
+    return set_error(LBX_EUNSUPPORTED, "16-bit PCM input is served by the fused 512-point configuration only");
+  FusedParams p{};
+  p.sig = nullptr; p.sig_i16 = pcm; p.out = out; p.N = N; p.T = T;
+  p.frame_length = frame_length; p.frame_step = frame_step;
+  p.sig_smem = fused_sig_smem(frame_length, frame_step);
+  p.power = power;
+  p.n_mel = n_mel; p.band_start = band_start; p.band_len = band_len; p.band_off = band_off; p.band_w = band_w;
+  p.n_packed = n_packed; p.log_mode = log_mode; p.eps = eps;
+  return launch_fused<1>(p, B, fused_smem_bytes(frame_length, frame_step, n_mel, n_packed), (cudaStream_t)stream);
 }
 
 int lbx_power_to_db_f32(const float* S, long long numel, float amin, float top_db, float* out, void* workspace,

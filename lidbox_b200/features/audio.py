@@ -73,7 +73,11 @@ def linear_to_mel(spectrograms, sample_rate, num_mel_bins=40, fmin=0.0, fmax=800
 def logmelspectrograms(signals, sample_rate, frame_length_ms=25, frame_step_ms=10, power=2.0, fft_length=512,
                        num_mel_bins=40, fmin=0.0, fmax=8000.0, log=True, eps=1e-6, out=None):
     """Fused spectrograms -> linear_to_mel -> ln(x + 1e-6) (the chain of lidbox/data/tf_utils.py:172-178) in one
-    kernel: [B, N] -> [B, T, num_mel_bins].  Not a reference name: it is what the map stage calls."""
+    kernel: [B, N] -> [B, T, num_mel_bins].  Not a reference name: it is what the map stage calls.
+    An int16 torch tensor is taken as 16-bit PCM and decoded on the fly (x / 32768, as read_wav does)."""
+    if isinstance(signals, torch.Tensor) and signals.dtype == torch.int16:
+        return _logmel_pcm16(signals, sample_rate, frame_length_ms, frame_step_ms, power, fft_length, num_mel_bins,
+                             fmin, fmax, log, eps, out)
     sig = _as_device_f32(signals, 2, "signals")
     L = ms_to_frames(sample_rate, frame_length_ms)
     step = ms_to_frames(sample_rate, frame_step_ms)
@@ -90,6 +94,26 @@ def logmelspectrograms(signals, sample_rate, frame_length_ms=25, frame_step_ms=1
                                   _lib.ptr(bands.start), _lib.ptr(bands.len), _lib.ptr(bands.off), _lib.ptr(bands.w),
                                   bands.n_packed, 1 if log else 0, float(eps), _lib.ptr(out), _lib.ptr(ws), ws_bytes,
                                   _lib.stream_ptr(sig.device)))
+    return out
+
+
+def _logmel_pcm16(pcm, sample_rate, frame_length_ms, frame_step_ms, power, fft_length, num_mel_bins, fmin, fmax, log,
+                  eps, out):
+    if pcm.dim() != 2:
+        raise ValueError("signals must have rank 2, got shape %s" % (tuple(pcm.shape),))
+    pcm = pcm.to(_lib.require_cuda(), non_blocking=True).contiguous()
+    L = ms_to_frames(sample_rate, frame_length_ms)
+    step = ms_to_frames(sample_rate, frame_step_ms)
+    B, N = pcm.shape
+    lib = _lib.lib()
+    T = int(lib.lbx_num_frames(N, L, step)) if L >= 1 and step >= 1 else 0
+    bands = mel_ops.mel_bands(num_mel_bins, int(fft_length) // 2 + 1, sample_rate, fmin, fmax, pcm.device)
+    if out is None:
+        out = torch.empty((B, T, int(num_mel_bins)), dtype=torch.float32, device=pcm.device)
+    _lib.check(lib.lbx_logmel_i16(_lib.ptr(pcm), B, N, L, step, int(fft_length), float(power), bands.n_mel,
+                                  _lib.ptr(bands.start), _lib.ptr(bands.len), _lib.ptr(bands.off), _lib.ptr(bands.w),
+                                  bands.n_packed, 1 if log else 0, float(eps), _lib.ptr(out),
+                                  _lib.stream_ptr(pcm.device)))
     return out
 
 

@@ -282,3 +282,14 @@ def test_vad_parity_and_reference_properties(audio):
         ref = O.remove_silence(sig[b], 16000)
         assert int(lengths[b]) == ref.size
         assert np.array_equal(out[b, :ref.size].cpu().numpy(), ref)              # compaction is a pure copy: bit-exact
+
+
+def test_pcm16_input_is_bit_identical(audio):
+    # 16-bit PCM decoded inside the kernel (x / 32768) must equal the float32 path on the decoded signal exactly
+    g = np.load(os.path.join(GOLDEN, "wav_fixtures.npz"))
+    pcm = torch.from_numpy(g["pcm"])
+    a = audio.logmelspectrograms(pcm, 16000)
+    b = audio.logmelspectrograms(pcm.float() / 32768.0, 16000)
+    assert torch.equal(a, b)
+    odd = pcm[:, 3:7777].contiguous()          # unaligned rows
+    assert torch.equal(audio.logmelspectrograms(odd, 16000), audio.logmelspectrograms(odd.float() / 32768.0, 16000))

@@ -172,18 +172,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) logmel512_kernel(const Fused
     const float* g = p.sig + (long long)b * p.N + s0;
     if (p.sig_i16 != nullptr) {
       const short* gi = p.sig_i16 + (long long)b * p.N + s0;
-      if ((reinterpret_cast<uintptr_t>(gi) & 15) == 0) {
-        const int n8 = n_valid >> 3;
-        for (int i = tid; i < n8; i += FUSED_THREADS) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(gi) + i);
-          const unsigned int w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            s_sig[8 * i + 2 * k] = (float)(short)(w[k] & 0xFFFFu) * (1.0f / 32768.0f);
-            s_sig[8 * i + 2 * k + 1] = (float)(short)(w[k] >> 16) * (1.0f / 32768.0f);
-          }
+      if ((reinterpret_cast<uintptr_t>(gi) & 7) == 0) {
+        const int n4 = n_valid >> 2;                          // 4 samples per thread: 8-byte load, 16-byte store
+        for (int i = tid; i < n4; i += FUSED_THREADS) {
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(gi) + i);
+          reinterpret_cast<float4*>(s_sig)[i] =
+              make_float4((float)(short)(u.x & 0xFFFFu) * (1.0f / 32768.0f), (float)(short)(u.x >> 16) * (1.0f / 32768.0f),
+                          (float)(short)(u.y & 0xFFFFu) * (1.0f / 32768.0f), (float)(short)(u.y >> 16) * (1.0f / 32768.0f));
         }
-        for (int i = (n8 << 3) + tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = (float)__ldg(gi + i) * (1.0f / 32768.0f);
+        for (int i = (n4 << 2) + tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = (float)__ldg(gi + i) * (1.0f / 32768.0f);
       } else {
         for (int i = tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = (float)__ldg(gi + i) * (1.0f / 32768.0f);
       }

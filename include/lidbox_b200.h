@@ -187,6 +187,9 @@ typedef struct lbx_gemm_t {
 int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream);
 /* GEMMs are launched with programmatic dependent launch (prologue overlaps the previous kernel's tail); 0 disables. */
 int lbx_set_pdl(int enabled);
+/* 1: the 256-wide GEMM tiles run on CTA pairs (clusters of 2, tcgen05 cta_group::2: a 256x256 tile per pair, every
+ * CTA stages half of the B operand); 0: single-CTA 128x256 tiles. */
+int lbx_set_gemm_pair(int enabled);
 
 /* ------------------------------------------------------------------------------------------------------------
  * TDNN non-GEMM stages and losses

@@ -52,6 +52,7 @@ SIGNATURES = {
     "lbx_vad_compact_f32": (c_int, [_P, c_ll, c_ll, c_int, _P, c_ll, _P, _P, _P, _P]),
     "lbx_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), _P]),
     "lbx_set_pdl": (c_int, [c_int]),
+    "lbx_set_gemm_pair": (c_int, [c_int]),
     "lbx_pack_rows_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, _P]),
     "lbx_stats_pool_fwd": (c_int, [_P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
     "lbx_stats_pool_bwd": (c_int, [_P, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_int, _P]),
@@ -89,6 +90,7 @@ def lib():
             fn.argtypes = argtypes
         if os.environ.get("LBX_PDL", "1") == "0":
             handle.lbx_set_pdl(0)
+        handle.lbx_set_gemm_pair(1 if os.environ.get("LBX_GEMM_PAIR", "0") == "1" else 0)
         _lib = handle
     return _lib
 

@@ -40,11 +40,13 @@ constexpr int STAGE_PITCH = 80;                // bytes per staged row: 32 bf16 
 constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH;
 
 // tile-N variants: 256 (large problems), 128, and 64 (the small-M dense layers: enough CTAs without split-K)
-template <int BN>
+// PAIR: two CTAs of a cluster share one 256 x BN tile through tcgen05 cta_group::2 — each CTA stages its own 128 rows of
+// A and only HALF of the B tile, which cuts the operand bytes every SM has to ingest per k-block from 48 KB to 32 KB
+template <int BN, bool PAIR = false>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = PAIR ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BN;    // 2 accumulator stages x BN fp32 columns
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_SMEM_FLOATS * 4 +
                                  EPI_WARPS * STAGE_BYTES_PER_WARP;
@@ -105,6 +107,52 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- cluster / CTA-pair helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are counted on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t mbar_cluster_addr, void* dst, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -151,7 +199,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M=128, N=BN
-template <int BN>
+template <int BN, int M_INSTR = BM>
 __host__ __device__ constexpr uint32_t make_idesc(int a_mn_major, int b_mn_major) {
   return (1u << 4)                       // c_format = F32
          | (1u << 7)                     // a_format = BF16
@@ -159,7 +207,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int a_mn_major, int b_mn_major
          | ((uint32_t)a_mn_major << 15)  // a_major
          | ((uint32_t)b_mn_major << 16)  // b_major
          | ((uint32_t)(BN >> 3) << 17)   // n_dim
-         | ((uint32_t)(BM >> 4) << 24);  // m_dim
+         | ((uint32_t)(M_INSTR >> 4) << 24);  // m_dim
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -189,12 +237,14 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, bool vec,
   }
 }
 
-template <int LAYOUT, int BN, bool HAS_MASK>
+template <int LAYOUT, int BN, bool HAS_MASK, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                      const GemmParams p) {
-  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
+  constexpr int STAGES = Cfg<BN, PAIR>::STAGES, STAGE_BYTES = Cfg<BN, PAIR>::STAGE_BYTES,
+                TMEM_COLS = Cfg<BN, PAIR>::TMEM_COLS;
+  constexpr int BN_LOCAL = PAIR ? BN / 2 : BN;   // B columns staged by this CTA
   constexpr bool A_MN = LAYOUT == 1;            // A stored [K, M] (contraction index is the slow one)
   constexpr bool B_MN = LAYOUT != 0;            // B stored [K, N]
   extern __shared__ unsigned char smem_dyn[];
@@ -209,8 +259,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  const int cta_rank = PAIR ? (int)cluster_ctarank() : 0;      // rank inside the CTA pair (0 = leader, issues the MMAs)
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-  const int mn_tiles = m_tiles * n_tiles;
+  const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;     // a pair owns two consecutive 128-row tiles
+  const int mn_tiles = m_units * n_tiles;
   const int total_tiles = mn_tiles * p.k_splits;
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
@@ -223,23 +276,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tma_prefetch_desc(&mapB1);
     }
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(full_bar + i, 1);
+      mbar_init(full_bar + i, PAIR ? 2 : 1);  // pair: the producers of both CTAs arrive on the leader's barrier
       mbar_init(empty_bar + i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i, 1);
-      mbar_init(tempty_bar + i, EPI_WARPS);   // one arrival per epilogue warp
+      mbar_init(tempty_bar + i, PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // one arrival per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                 // the peer's barriers are initialised before anyone arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream;
@@ -261,9 +322,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
         const int split = tile / mn_tiles, rem = tile - split * mn_tiles;
-        const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
+        const int m_unit = rem / n_tiles, n_blk = rem - m_unit * n_tiles;
+        const int m_blk = PAIR ? 2 * m_unit + cta_rank : m_unit;
+        const int n_col0 = n_blk * BN + cta_rank * BN_LOCAL;       // first B column staged by this CTA
         const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int term = 0; term < p.n_terms; ++term) {
           const CUtensorMap* mA = p.term_a[term] ? &mapA1 : &mapA0;
@@ -273,20 +336,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             mbar_wait(empty_bar + stage, phase ^ 1);
             unsigned char* sA = smem + (size_t)stage * STAGE_BYTES;
             unsigned char* sB = sA + A_BYTES;
-            mbar_expect_tx(full_bar + stage, (uint32_t)STAGE_BYTES);
-            if (!A_MN) {
-              tma_load_2d(mA, full_bar + stage, sA, kb * BK, m_blk * BM + arow);
-            } else {
+            if (!PAIR) {
+              mbar_expect_tx(full_bar + stage, (uint32_t)STAGE_BYTES);
+              if (!A_MN) {
+                tma_load_2d(mA, full_bar + stage, sA, kb * BK, m_blk * BM + arow);
+              } else {
 #pragma unroll
-              for (int i = 0; i < BM / 64; ++i)
-                tma_load_2d(mA, full_bar + stage, sA + i * 8192, m_blk * BM + i * 64, kb * BK);
-            }
-            if (!B_MN) {
-              tma_load_2d(mB, full_bar + stage, sB, kb * BK, n_blk * BN);
-            } else {
+                for (int i = 0; i < BM / 64; ++i)
+                  tma_load_2d(mA, full_bar + stage, sA + i * 8192, m_blk * BM + i * 64, kb * BK);
+              }
+              if (!B_MN) {
+                tma_load_2d(mB, full_bar + stage, sB, kb * BK, n_blk * BN);
+              } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                tma_load_2d(mB, full_bar + stage, sB + i * 8192, n_blk * BN + i * 64, kb * BK);
+                for (int i = 0; i < BN / 64; ++i)
+                  tma_load_2d(mB, full_bar + stage, sB + i * 8192, n_blk * BN + i * 64, kb * BK);
+              }
+            } else {
+              // all bytes of both CTAs are counted on the LEADER's full barrier (the MMA issuer waits there)
+              const uint32_t lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
+              if (cta_rank == 0) mbar_expect_tx(full_bar + stage, 2u * (uint32_t)STAGE_BYTES);
+              else mbar_arrive_remote(lead_full);
+              if (!A_MN) {
+                tma_load_2d_pair(mA, lead_full, sA, kb * BK, m_blk * BM + arow);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BM / 64; ++i)
+                  tma_load_2d_pair(mA, lead_full, sA + i * 8192, m_blk * BM + i * 64, kb * BK);
+              }
+              if (!B_MN) {
+                tma_load_2d_pair(mB, lead_full, sB, kb * BK, n_col0);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BN_LOCAL / 64; ++i)
+                  tma_load_2d_pair(mB, lead_full, sB + i * 8192, n_col0 + i * 64, kb * BK);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -295,13 +379,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN>(A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc<BN, PAIR ? 256 : 128>(A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
         const int split = tile / mn_tiles;
         const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         const int iters = (kb1 - kb0) * p.n_terms;
@@ -321,12 +405,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                                      : make_smem_desc(sA + k * (UMMA_K * 2), 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(sB + k * (UMMA_K * 128), 8192, 1024)
                                      : make_smem_desc(sB + k * (UMMA_K * 2), 16, 1024);
-            tc_mma_bf16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            if (PAIR) tc_mma_bf16_pair(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar + stage);          // frees the smem stage when these MMAs retire
+          if (PAIR) tc_commit_pair(empty_bar + stage);   // frees the stage in both CTAs when these MMAs retire
+          else tc_commit(empty_bar + stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar + acc);              // accumulator ready for the epilogue
+        if (PAIR) tc_commit_pair(tfull_bar + acc);      // accumulators (in both CTAs' TMEM) ready for the epilogues
+        else tc_commit(tfull_bar + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -344,9 +431,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int i = threadIdx.x - 32 * LBX_CTRL_WARPS; i < p.N; i += 32 * EPI_WARPS) s_bias[i] = __ldg(p.bias + i);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers) {
       const int rem = tile % mn_tiles;
-      const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
+      const int m_unit = rem / n_tiles, n_blk = rem - m_unit * n_tiles;
+      const int m_blk = PAIR ? 2 * m_unit + cta_rank : m_unit;
       const int m = m_blk * BM + sub * 32 + lane;
       const bool in_range = m < p.M;
       // rows past the valid part of an utterance are stored as zeros: they land on rows of the destination that
@@ -387,7 +475,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         // all TMEM reads of this warp are done: release the accumulator stage before touching global memory
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + acc);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(tempty_bar + acc), 0));   // the leader's MMA issuer waits
+          else mbar_arrive(tempty_bar + acc);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (m_blk * BM + sub * 32 >= p.M && p.colsum == nullptr) continue;   // whole warp past the last row
@@ -577,9 +668,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                 // the peer may still be reading this CTA's shared memory / barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -622,6 +717,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 }
 
 static int g_num_sms = 0;
+static int g_use_pair = 0;
 
 }  // namespace lbx
 
@@ -688,7 +784,9 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   int rc;
   // tile-N 256 unless the problem is narrower than 128 columns (measured: 128 never wins on the TDNN shapes)
   const int bn = (g->tile_n == 64 || g->tile_n == 128 || g->tile_n == 256) ? g->tile_n : (p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256));
-  const int boxA_rows = g->layout == 1 ? 64 : BM, boxB_rows = g->layout == 0 ? bn : 64;
+  // CTA pairs (tcgen05 cta_group::2) for the 256-wide tiles: every CTA stages only half of the B tile
+  const bool pair = g_use_pair && bn == 256;
+  const int boxA_rows = g->layout == 1 ? 64 : BM, boxB_rows = g->layout == 0 ? (pair ? bn / 2 : bn) : 64;
   if ((rc = make_map(&mA0, g->a0, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
   if ((rc = make_map(&mB0, g->b0, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
   mA1 = mA0; mB1 = mB0;
@@ -698,42 +796,70 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
     int dev = 0, n = 0;
     LBX_CUDA(cudaGetDevice(&dev));
     LBX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-#define LBX_SET_SMEM(L, N_)                                                                                       \
-  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                (int)Cfg<N_>::SMEM));                                                             \
-  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+#define LBX_SET_SMEM(L, N_)                                                                                        \
+  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)Cfg<N_>::SMEM));                                                              \
+  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                 (int)Cfg<N_>::SMEM))
+#define LBX_SET_SMEM_PAIR(L)                                                                                       \
+  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)Cfg<256, true>::SMEM));                                                       \
+  LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, 256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                (int)Cfg<256, true>::SMEM))
     LBX_SET_SMEM(0, 256); LBX_SET_SMEM(1, 256); LBX_SET_SMEM(2, 256);
     LBX_SET_SMEM(0, 128); LBX_SET_SMEM(1, 128); LBX_SET_SMEM(2, 128);
     LBX_SET_SMEM(0, 64); LBX_SET_SMEM(1, 64); LBX_SET_SMEM(2, 64);
+    LBX_SET_SMEM_PAIR(0); LBX_SET_SMEM_PAIR(1); LBX_SET_SMEM_PAIR(2);
 #undef LBX_SET_SMEM
+#undef LBX_SET_SMEM_PAIR
     g_num_sms = n;
   }
-  const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.k_splits;
-  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  const long long m_tiles_h = (p.M + BM - 1) / BM;
+  const long long tiles = (pair ? (m_tiles_h + 1) / 2 : m_tiles_h) * ((p.N + bn - 1) / bn) * p.k_splits;
+  const int max_workers = pair ? g_num_sms / 2 : g_num_sms;
+  const int workers = (int)(tiles < max_workers ? tiles : max_workers);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
+  cfg.gridDim = dim3((unsigned)(pair ? 2 * workers : workers));
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = bn == 256 ? Cfg<256>::SMEM : (bn == 128 ? Cfg<128>::SMEM : Cfg<64>::SMEM);
+  cfg.dynamicSmemBytes = pair ? Cfg<256, true>::SMEM : (bn == 256 ? Cfg<256>::SMEM : (bn == 128 ? Cfg<128>::SMEM : Cfg<64>::SMEM));
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t le;
-#define LBX_GEMM_LAUNCH(L, N_)                                                                         \
-  le = p.mask_src ? cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, true>, mA0, mA1, mB0, mB1, p)    \
-                  : cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, false>, mA0, mA1, mB0, mB1, p)
-  if (bn == 256) {
-    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 256); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 256); else LBX_GEMM_LAUNCH(2, 256);
+#define LBX_GEMM_LAUNCH(L, N_, P_)                                                                          \
+  le = p.mask_src ? cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, true, P_>, mA0, mA1, mB0, mB1, p)     \
+                  : cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, false, P_>, mA0, mA1, mB0, mB1, p)
+  if (pair) {
+    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 256, true); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 256, true); else LBX_GEMM_LAUNCH(2, 256, true);
+  } else if (bn == 256) {
+    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 256, false); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 256, false); else LBX_GEMM_LAUNCH(2, 256, false);
   } else if (bn == 128) {
-    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 128); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 128); else LBX_GEMM_LAUNCH(2, 128);
+    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 128, false); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 128, false); else LBX_GEMM_LAUNCH(2, 128, false);
   } else {
-    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 64); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 64); else LBX_GEMM_LAUNCH(2, 64);
+    if (g->layout == 0) LBX_GEMM_LAUNCH(0, 64, false); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 64, false); else LBX_GEMM_LAUNCH(2, 64, false);
   }
 #undef LBX_GEMM_LAUNCH
   if (le != cudaSuccess) return set_error(LBX_ECUDA, "GEMM launch failed: %s", cudaGetErrorString(le));
   LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+// CTA-pair (tcgen05 cta_group::2) execution of the 256-wide tiles; LBX_GEMM_PAIR in the Python host's environment
+extern "C" int lbx_set_gemm_pair(int enabled) {
+  g_use_pair = enabled ? 1 : 0;
   return LBX_OK;
 }

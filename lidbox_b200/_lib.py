@@ -90,7 +90,7 @@ def lib():
             fn.argtypes = argtypes
         if os.environ.get("LBX_PDL", "1") == "0":
             handle.lbx_set_pdl(0)
-        handle.lbx_set_gemm_pair(1 if os.environ.get("LBX_GEMM_PAIR", "0") == "1" else 0)
+        handle.lbx_set_gemm_pair(0 if os.environ.get("LBX_GEMM_PAIR", "1") == "0" else 1)
         _lib = handle
     return _lib
 

@@ -717,7 +717,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 }
 
 static int g_num_sms = 0;
-static int g_use_pair = 0;
+static int g_use_pair = 1;
 
 }  // namespace lbx
 

@@ -119,6 +119,9 @@ int lbx_normalize_axis_f32(const float* x, float* y, long long outer, long long 
 /* feature_scaling with axis=None (min/max over the whole tensor); workspace: >= 8 bytes of device memory */
 int lbx_feature_scaling_all_f32(const float* x, float* y, long long n, float lo, float hi, void* workspace,
                                 void* stream);
+/* lidbox/data/tf_utils.py:180-185: tf.signal.mfccs_from_log_mel_spectrograms(X)[..., coef_begin:coef_end] —
+ * orthonormal-scaled DCT-II of the log-mel rows: out [rows, coef_end-coef_begin] */
+int lbx_mfcc_f32(const float* logmel, long long rows, int n_mel, int coef_begin, int coef_end, float* out, void* stream);
 /* lidbox/features/__init__.py:40-67 window_normalization over the time axis of [B,T,F] for 1 <= window_len < T
  * (REFLECT padding w/2 left, w/2-1+(w&1) right; mean / population std over each window) */
 int lbx_window_normalization_f32(const float* x, float* y, long long B, int T, int F, int window_len,

@@ -46,6 +46,7 @@ SIGNATURES = {
     "lbx_check_finite_f32": (c_int, [_P, c_ll, _P, _P]),
     "lbx_normalize_axis_f32": (c_int, [_P, _P, c_ll, c_ll, c_ll, c_int, c_float, c_float, _P]),
     "lbx_feature_scaling_all_f32": (c_int, [_P, _P, c_ll, c_float, c_float, _P, _P]),
+    "lbx_mfcc_f32": (c_int, [_P, c_ll, c_int, c_int, c_int, _P, _P]),
     "lbx_window_normalization_f32": (c_int, [_P, _P, c_ll, c_int, c_int, c_int, c_int, _P]),
     "lbx_row_rms_f32": (c_int, [_P, c_ll, c_int, _P, _P]),
     "lbx_rms_vad_f32": (c_int, [_P, c_ll, c_ll, c_int, c_float, c_float, c_ll, _P, _P, _P]),

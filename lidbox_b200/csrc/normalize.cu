@@ -163,6 +163,22 @@ __global__ void __launch_bounds__(256) window_norm_kernel(const float* __restric
   y[idx] = out;
 }
 
+// tf.signal.mfccs_from_log_mel_spectrograms (call site lidbox/data/tf_utils.py:180-185):
+// mfcc[k] = rsqrt(2 M) * 2 * sum_n x[n] cos(pi k (2n + 1) / (2 M)), k in [k0, k1)
+__global__ void __launch_bounds__(256) mfcc_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows,
+                                                  int M, int k0, int k1) {
+  LBX_PDL_SYNC();
+  const int nk = k1 - k0;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * nk) return;
+  const long long r = idx / nk;
+  const int k = k0 + (int)(idx - r * nk);
+  const float* px = x + r * M;
+  float acc = 0.0f;
+  for (int n = 0; n < M; ++n) acc = fmaf(px[n], cospif((float)(k * (2 * n + 1)) / (float)(2 * M)), acc);
+  y[idx] = 2.0f * acc * rsqrtf(2.0f * (float)M);
+}
+
 }  // namespace lbx
 
 using namespace lbx;
@@ -198,6 +214,18 @@ int lbx_feature_scaling_all_f32(const float* x, float* y, long long n, float lo,
   LBX_LAUNCH_CHECK();
   scale_all_kernel<<<blocks, 256, 0, st>>>(x, y, n, (const int*)workspace, lo, hi);
   LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_mfcc_f32(const float* logmel, long long rows, int n_mel, int coef_begin, int coef_end, float* out, void* stream) {
+  LBX_CHECK_ARG(rows >= 0 && n_mel >= 1, "bad shape");
+  LBX_CHECK_ARG(coef_begin >= 0 && coef_end >= coef_begin && coef_end <= n_mel, "bad coefficient range [%d, %d)",
+                coef_begin, coef_end);
+  if (rows == 0 || coef_end == coef_begin) return LBX_OK;
+  LBX_CHECK_ARG(logmel && out, "NULL pointer argument");
+  const long long total = rows * (coef_end - coef_begin);
+  LBX_LAUNCH_PDL(mfcc_kernel, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, (cudaStream_t)stream, logmel, out, rows,
+                 n_mel, coef_begin, coef_end);
   return LBX_OK;
 }
 

@@ -36,7 +36,12 @@ def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_
             audio_features.assert_all_finite(X, "spectrogram failed")
         X = audio_features.power_to_db(X, **(db_spec_kwargs or {}))
     elif feattype == "mfcc":
-        raise NotImplementedError("mfcc (DCT-II epilogue) is a 'next' row of SURVEY.md §8(f), not built yet")
+        X = audio_features.logmelspectrograms(sig, sample_rate, log=True, **spec_kwargs, **melspec_kwargs)
+        if check_finite:
+            audio_features.assert_all_finite(X, "logmelspectrogram failed")
+        mfcc_kwargs = mfcc_kwargs or {}
+        X = audio_features.mfccs_from_log_mel_spectrograms(X, mfcc_kwargs.get("coef_begin", 1),
+                                                           mfcc_kwargs.get("coef_end", 13))   # tf_utils.py:181-185
     else:
         raise ValueError("unknown feature type " + repr(feattype))
     if check_finite:

@@ -117,6 +117,19 @@ def _logmel_pcm16(pcm, sample_rate, frame_length_ms, frame_step_ms, power, fft_l
     return out
 
 
+def mfccs_from_log_mel_spectrograms(log_mel, coef_begin=0, coef_end=None):
+    """tf.signal.mfccs_from_log_mel_spectrograms(X)[..., coef_begin:coef_end] as used by the map stage
+    (lidbox/data/tf_utils.py:180-185): [B, T, M] -> [B, T, coef_end - coef_begin]."""
+    X = _as_device_f32(log_mel, 3, "log_mel")
+    B, T, M = X.shape
+    coef_end = M if coef_end is None else min(int(coef_end), M)
+    coef_begin = min(int(coef_begin), coef_end)
+    out = torch.empty((B, T, coef_end - coef_begin), dtype=torch.float32, device=X.device)
+    _lib.check(_lib.lib().lbx_mfcc_f32(_lib.ptr(X), B * T, M, coef_begin, coef_end, _lib.ptr(out),
+                                       _lib.stream_ptr(X.device)))
+    return out
+
+
 def power_to_db(S, amin=1e-10, top_db=80.0):
     """lidbox/features/audio.py:167-174 (max over the whole tensor, batch included)."""
     S = _as_device_f32(S, 3, "S")

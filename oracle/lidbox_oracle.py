@@ -170,10 +170,20 @@ def logmel(signals, sample_rate, frame_length_ms=25, frame_step_ms=10, power=2.0
     return log_eps(M)
 
 
+def mfccs_from_log_mel_spectrograms(log_mel):
+    """tf.signal.mfccs_from_log_mel_spectrograms (call site tf_utils.py:183): DCT-II (tf.signal.dct type 2, no norm:
+    X_k = 2 sum_n x_n cos(pi k (2n+1) / (2N))) scaled by rsqrt(2 N)."""
+    x = np.asarray(log_mel, np.float64)
+    N = x.shape[-1]
+    n = np.arange(N)
+    C = 2.0 * np.cos(np.pi * np.arange(N)[:, None] * (2 * n[None, :] + 1) / (2.0 * N))
+    return (x @ C.T) / np.sqrt(2.0 * N)
+
+
 def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_kwargs=None, mfcc_kwargs=None,
                      db_spec_kwargs=None, feat_scale_kwargs=None, window_norm_kwargs=None):
     """lidbox/data/tf_utils.py:166-195 (with the broken `melspectrograms` name read as `linear_to_mel`).
-    mfcc is outside the oracle's scope (a "next" row)."""
+    """
     signals = np.asarray(signals, np.float32)
     if signals.ndim != 2:
         raise ValueError("signals must be [B, N]")
@@ -182,10 +192,13 @@ def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_
         raise ValueError("different sample rates in a batch")
     sr = int(sample_rates[0])
     X = spectrograms(signals, sr, **(spec_kwargs or {}))
-    if feattype in ("melspectrogram", "logmelspectrogram"):
+    if feattype in ("melspectrogram", "logmelspectrogram", "mfcc"):
         X = linear_to_mel(X, sr, **(melspec_kwargs or {}))
-        if feattype == "logmelspectrogram":
+        if feattype in ("logmelspectrogram", "mfcc"):
             X = log_eps(X)
+        if feattype == "mfcc":
+            mk = mfcc_kwargs or {}
+            X = mfccs_from_log_mel_spectrograms(X)[..., mk.get("coef_begin", 1):mk.get("coef_end", 13)]
     elif feattype == "db_spectrogram":
         X = power_to_db(X, **(db_spec_kwargs or {}))
     elif feattype != "spectrogram":

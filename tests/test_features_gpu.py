@@ -293,3 +293,21 @@ def test_pcm16_input_is_bit_identical(audio):
     assert torch.equal(a, b)
     odd = pcm[:, 3:7777].contiguous()          # unaligned rows
     assert torch.equal(audio.logmelspectrograms(odd, 16000), audio.logmelspectrograms(odd.float() / 32768.0, 16000))
+
+
+def test_mfcc_map_stage(built_lib):
+    from lidbox_b200.data import tf_utils
+    from lidbox_b200.features import audio as a
+    rng = np.random.default_rng(22)
+    sig = (rng.standard_normal((3, 16000)) * 0.1).astype(np.float32)
+    rates = np.array([16000] * 3)
+    X = tf_utils.extract_features(sig, rates, "mfcc", {}, {}, {}, {}, {}, {}).cpu().numpy()
+    ref = O.extract_features(sig, rates, "mfcc")
+    assert X.shape == ref.shape == (3, 98, 12)
+    np.testing.assert_allclose(X, ref, rtol=1e-4, atol=1e-4)
+    X2 = tf_utils.extract_features(sig, rates, "mfcc", {}, {}, {"coef_begin": 0, "coef_end": 20}).cpu().numpy()
+    np.testing.assert_allclose(X2, O.extract_features(sig, rates, "mfcc", mfcc_kwargs={"coef_begin": 0, "coef_end": 20}),
+                               rtol=1e-4, atol=1e-4)
+    lm = rng.standard_normal((2, 5, 40)).astype(np.float32)
+    np.testing.assert_allclose(a.mfccs_from_log_mel_spectrograms(lm).cpu().numpy(),
+                               O.mfccs_from_log_mel_spectrograms(lm), rtol=1e-4, atol=1e-5)

@@ -282,3 +282,13 @@ def test_vad_reference_properties():
     m = np.array([1, 0, 0, 1, 0, 0, 0, 0, 1, 0], bool)
     assert (O.invert_too_short_consecutive_false(m, 3) == np.array([1, 1, 1, 1, 0, 0, 0, 0, 1, 1], bool)).all()
     assert (O.invert_too_short_consecutive_false(m, 0) == m).all()
+
+
+def test_mfcc_is_orthonormal_dct():
+    # tf.signal.mfccs_from_log_mel_spectrograms == scipy's orthonormal DCT-II except for the k = 0 scale (sqrt(2))
+    import scipy.fft
+    x = np.random.default_rng(14).standard_normal((3, 7, 40))
+    m = O.mfccs_from_log_mel_spectrograms(x)
+    ref = scipy.fft.dct(x, type=2, norm="ortho", axis=-1)
+    np.testing.assert_allclose(m[..., 1:], ref[..., 1:], atol=1e-12)
+    np.testing.assert_allclose(m[..., 0], ref[..., 0] * np.sqrt(2.0), atol=1e-12)

@@ -233,9 +233,6 @@ int lbx_ap_loss(const float* h, const int* labels, long long B, int D, int N, fl
                 float* z_out, float* theta_out, float* loss, float* grad_f32, void* grad_bf16, int g_pitch,
                 const float* gloss, float grad_scale, float* dbias, void* stream);
 
-/* bias gradient: out[n] += sum_m x[m, n], x bf16 [rows, pitch] */
-int lbx_colsum_bf16(const void* x, long long rows, int n, int pitch, float* out, void* stream);
-
 /* Keras-compatible Adam on flat fp32 buffers: g' = g * grad_scale; m,v updates;
  * p -= lr * sqrt(1-beta2^t)/(1-beta1^t) * m / (sqrt(v) + eps).  The step counter t (*step_dev, incremented by the
  * call) and the bias-corrected rate (*lr_t_dev) live in device memory so the call can be replayed from a CUDA graph.
@@ -244,13 +241,6 @@ int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, 
                   float eps, long long* step_dev, float* lr_t_dev, float grad_scale,
                   void* params_bf16 /* optional: bf16 operand copy of the flat buffer, refreshed in the same pass */,
                   int zero_grads /* reset the gradient buffer after it has been consumed */, void* stream);
-
-/* Finishing pass of a split-K Dense layer (lbx_gemm_bf16 with epi_atomic into the fp32 accumulator `acc`):
- * x = acc + bias; ReLU; zero unless mask_src > 0; outputs as bf16 hi (+ lo residual) and/or fp32; colsum[n] += sum_m x;
- * zero_acc resets acc for its next use. */
-int lbx_dense_finish(float* acc, long long M, int N, int ld_acc, const float* bias, int relu, const void* mask_src,
-                     int ld_mask, void* out_hi, void* out_lo, int ld_out, float* out_f32, int ld_f32, float* colsum,
-                     int zero_acc, void* stream);
 
 /* Data-parallel optimizer step fused with the gradient exchange over NVLink peer memory (one node, one process per
  * GPU; replaces "all-reduce + Adam").  The flat parameter / gradient / bf16-copy buffers are SYMMETRIC allocations:

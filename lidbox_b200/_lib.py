@@ -57,10 +57,8 @@ SIGNATURES = {
     "lbx_pack_rows_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, _P]),
     "lbx_stats_pool_fwd": (c_int, [_P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
     "lbx_stats_pool_bwd": (c_int, [_P, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_int, _P]),
-    "lbx_dense_finish": (c_int, [_P, c_ll, c_int, c_int, _P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, _P, c_int, _P]),
     "lbx_logsoftmax_xent": (c_int, [_P, _P, c_ll, c_int, _P, _P, _P, c_int, c_float, _P, _P]),
     "lbx_ap_loss": (c_int, [_P, _P, c_ll, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_int, _P, c_float, _P, _P]),
-    "lbx_colsum_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P]),
     "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P, c_int, _P]),
     "lbx_adam_step_sharded": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P, _P, c_float, c_float, c_float,
                                       c_float, _P, _P, c_float, c_int, _P]),

@@ -243,27 +243,6 @@ __global__ void __launch_bounds__(128) ap_loss_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// bias gradients: out[n] += sum_m x[m, n]
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long rows, int n, int pitch,
-                                                    float* __restrict__ out) {
-  __shared__ float red[8][33];
-  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  float s = 0.0f;
-  if (c < n)
-    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8)
-      s += __bfloat162float(x[r * pitch + c]);
-  red[rl][cl] = s;
-  __syncthreads();
-  if (rl == 0 && c < n) {
-#pragma unroll
-    for (int i = 1; i < 8; ++i) s += red[i][cl];
-    atomicAdd(out + c, s);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // optimizer + weight refresh
 // ------------------------------------------------------------------------------------------------------------
 // step counter and bias-corrected learning rate live in device memory so that a captured CUDA graph of the whole
@@ -629,49 +608,6 @@ __global__ void __launch_bounds__(256) stats_pool_bwd_bf16r_kernel(const bf16* _
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// finishing pass of a split-K dense layer: acc (fp32, atomically accumulated by the GEMM) -> + bias, ReLU, ReLU-backward
-// mask, bf16 hi/lo and/or fp32 outputs, column sums (bias gradient of the layer below); re-zeroes acc for its next use
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dense_finish_kernel(float* __restrict__ acc, long long M, int N, int ld_acc,
-                                                          const float* __restrict__ bias, int relu,
-                                                          const bf16* __restrict__ mask_src, int ld_mask,
-                                                          bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int ld_out,
-                                                          float* __restrict__ out_f32, int ld_f32,
-                                                          float* __restrict__ colsum, int zero_acc) {
-  LBX_PDL_SYNC();
-  __shared__ float red[8][33];
-  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + cl;
-  float cs = 0.0f;
-  if (n < N) {
-    const float bv = bias ? __ldg(bias + n) : 0.0f;
-    for (long long r = (long long)blockIdx.y * 16 + rl; r < M && r < (long long)(blockIdx.y + 1) * 16; r += 8) {
-      float x = acc[r * ld_acc + n] + bv;
-      if (zero_acc) acc[r * ld_acc + n] = 0.0f;
-      if (relu) x = fmaxf(x, 0.0f);
-      if (mask_src && !(__bfloat162float(mask_src[r * ld_mask + n]) > 0.0f)) x = 0.0f;
-      cs += x;
-      if (out_f32) out_f32[r * ld_f32 + n] = x;
-      if (out_hi) {
-        const bf16 h = __float2bfloat16_rn(x);
-        out_hi[r * ld_out + n] = h;
-        if (out_lo) out_lo[r * ld_out + n] = __float2bfloat16_rn(x - __bfloat162float(h));
-      }
-    }
-  }
-  if (colsum != nullptr) {
-    red[rl][cl] = cs;
-    __syncthreads();
-    if (rl == 0 && n < N) {
-#pragma unroll
-      for (int i = 1; i < 8; ++i) cs += red[i][cl];
-      atomicAdd(colsum + n, cs);
-    }
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------------------------
 // Sharded optimizer step fused with the gradient exchange over NVLink peer memory (data parallel, one node):
 //   barrier -> reduce-scatter (peer loads of every rank's gradient shard) -> Adam on the shard -> all-gather (peer
 //   stores of the updated fp32 parameters and bf16 operand copy into every rank) -> barrier -> local gradient reset.
@@ -931,18 +867,6 @@ int lbx_ap_loss(const float* h, const int* labels, long long B, int D, int N, fl
   return LBX_OK;
 }
 
-int lbx_colsum_bf16(const void* x, long long rows, int n, int pitch, float* out, void* stream) {
-  LBX_CHECK_ARG(rows >= 0 && n >= 1 && pitch >= n, "bad shape");
-  if (rows == 0) return LBX_OK;
-  LBX_CHECK_ARG(x && out, "NULL pointer argument");
-  long long gy = ceil_div(rows, 256);
-  if (gy > 128) gy = 128;
-  dim3 grid((unsigned)ceil_div(n, 32), (unsigned)gy);
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, rows, n, pitch, out);
-  LBX_LAUNCH_CHECK();
-  return LBX_OK;
-}
-
 int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, long long* step_dev, float* lr_t_dev, float grad_scale, void* params_bf16, int zero_grads,
                   void* stream) {
@@ -957,18 +881,6 @@ int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, 
   LBX_LAUNCH_PDL(adam_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, (float4*)params,
                  (float4*)grads, (float4*)m, (float4*)v, n / 4, (const float*)lr_t_dev, beta1, beta2, eps, grad_scale,
                  (uint2*)params_bf16, zero_grads);
-  return LBX_OK;
-}
-
-int lbx_dense_finish(float* acc, long long M, int N, int ld_acc, const float* bias, int relu, const void* mask_src,
-                     int ld_mask, void* out_hi, void* out_lo, int ld_out, float* out_f32, int ld_f32, float* colsum,
-                     int zero_acc, void* stream) {
-  LBX_CHECK_ARG(M >= 0 && N >= 1 && ld_acc >= N, "bad shape");
-  if (M == 0) return LBX_OK;
-  LBX_CHECK_ARG(acc != nullptr, "NULL accumulator");
-  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 16));
-  LBX_LAUNCH_PDL(dense_finish_kernel, grid, dim3(256), 0, (cudaStream_t)stream, acc, M, N, ld_acc, bias, relu,
-                 (const bf16*)mask_src, ld_mask, (bf16*)out_hi, (bf16*)out_lo, ld_out, out_f32, ld_f32, colsum, zero_acc);
   return LBX_OK;
 }
 

@@ -250,8 +250,6 @@ class XVector:
                     H=[], H_lo=[], emb=torch.zeros((B, self.segments[0].units), dtype=torch.float32, device=dev),
                     logits=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev),
                     out=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev))
-        widest = max([2 * cn, self.num_outputs] + [sgm.units for sgm in self.segments])
-        bufs["acc"] = torch.zeros((B, widest), dtype=torch.float32, device=dev)   # split-K accumulator (kept zeroed)
         for sgm in self.segments:
             bufs["H"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev))
             bufs["H_lo"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev) if split else None)
@@ -437,8 +435,6 @@ class XVector:
         # ---- dense head (bias gradients come fused out of the kernels that produce each dz) ----
         dz, dz_cols, dz_pitch = bufs["dlogits"], self.num_outputs, npad
         acts = [bufs["pooled_hi"]] + bufs["H"]
-        acc = bufs["acc"]
-        ld_acc = acc.shape[1]
         for i in range(len(self.segments), -1, -1):
             ly = self.layers[n + i]
             wgrad(acts[i], B, ly["K"], ly["K"], dz, dz_cols, dz_pitch, ly)

@@ -183,7 +183,7 @@ def test_ap_loss_module(built_lib):
     per = lf.call(g["y"], z)
     np.testing.assert_allclose(per.detach().cpu().numpy(), g["per_sample"], rtol=1e-5, atol=1e-5)
     loss = lf(g["y"].reshape(-1, 1), z)                     # [B,1] labels are squeezed
-    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-5
     loss.backward()
     np.testing.assert_allclose(z.grad.cpu().numpy(), g["grad"], rtol=2e-4, atol=1e-6)
     np.testing.assert_allclose(lf.theta(g["z"]).cpu().numpy(), np.arccos(g["z"][:, :N]), atol=1e-5)

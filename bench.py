@@ -242,8 +242,11 @@ class XVectorTrainWorkload:
         if self.pg is not None:
             if os.environ.get("LBX_DP_SHARDED", "1") != "0":
                 self.model.enable_sharded_optimizer(self.pg)
-                self.dp_exchange = ("fused in the optimizer kernel: reduce-scatter by NVLink peer loads, Adam on the "
-                                    "rank's shard, all-gather by peer stores (no NCCL call in the step)")
+                nvls = bool(self.model._sharded.get("mc_grads"))
+                self.dp_exchange = ("fused in the optimizer kernel: reduce-scatter by %s, Adam on the rank's shard, "
+                                    "all-gather by %s (no NCCL call in the step)"
+                                    % (("NVLS multimem.ld_reduce (in-switch sum)", "multimem.st")
+                                       if nvls else ("NVLink peer loads", "peer stores")))
             else:
                 self.dp_exchange = "one NCCL all-reduce of the flat fp32 gradient, then full-size Adam"
         self.kw = dict(ap_classes=self.n_classes) if self.loss == "ap" else {}

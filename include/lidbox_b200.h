@@ -252,12 +252,15 @@ int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, 
  * signal pads: 2*world uint32 per rank, zero-initialised; epoch_dev / local_sync_dev (4 uint32): zero-initialised local
  * state advanced by every call, so the call can be replayed from a CUDA graph.  local_sync_dev[3] != 0 reports a
  * barrier time-out.  n must be a multiple of 4*world.  push_fp32 = 0 all-gathers only the bf16 operand copy (the fp32
- * master copy of a shard then lives on its owner only, ZeRO-1 style; gather it from the peers before exporting). */
+ * master copy of a shard then lives on its owner only, ZeRO-1 style; gather it from the peers before exporting).
+ * mc_grads / mc_w16 (optional, both or none): NVLS multicast mappings of the gradient and bf16 buffers; when given the
+ * reduce-scatter is one multimem.ld_reduce per element (the sum is formed inside the NVSwitch) and the all-gather one
+ * multimem.st per element instead of `world` peer accesses. */
 int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, void* const* w16_ptrs,
                           void* const* signal_ptrs, float* m_shard, float* v_shard, long long n, int rank, int world,
                           unsigned int* epoch_dev, unsigned int* local_sync_dev, float lr, float beta1, float beta2,
                           float eps, long long* step_dev, float* lr_t_dev, float grad_scale, int push_fp32,
-                          void* stream);
+                          const void* mc_grads, void* mc_w16, void* stream);
 
 /* fp32 -> bf16 operand planes of the flat parameter buffer: hi = bf16(x), lo = bf16(x - hi) (lo optional; it feeds
  * the bf16x3 forward mode).  The buffers keep the Keras layouts ([k*C_in, C_out] per kernel, pitch padded to 8). */

@@ -61,7 +61,7 @@ SIGNATURES = {
     "lbx_ap_loss": (c_int, [_P, _P, c_ll, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_int, _P, c_float, _P, _P]),
     "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P, c_int, _P]),
     "lbx_adam_step_sharded": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P, _P, c_float, c_float, c_float,
-                                      c_float, _P, _P, c_float, c_int, _P]),
+                                      c_float, _P, _P, c_float, c_int, _P, _P, _P]),
     "lbx_split_bf16": (c_int, [_P, c_ll, _P, _P, _P]),
     "lbx_logmel_f32_host": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_float,
                                     c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),

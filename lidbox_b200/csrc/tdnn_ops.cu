@@ -629,7 +629,24 @@ struct ShardedAdamParams {
   float* lr_t;
   float lr, beta1, beta2, eps, grad_scale;
   int push_fp32;                 // 1: also all-gather the fp32 master copy (otherwise only the owner's shard is current)
+  const float* mc_grads;         // optional NVLS multicast mapping of the gradient buffers (in-switch reduction)
+  bf16* mc_w16;                  // optional NVLS multicast mapping of the bf16 operand copy (one store reaches all ranks)
 };
+
+// NVLink SHARP: one load returns the sum over all ranks of the multicast group, reduced inside the NVSwitch
+__device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const float* mc_ptr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc_ptr)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_b32x2(void* mc_ptr, uint2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc_ptr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y))
+               : "memory");
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -696,27 +713,37 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const ShardedAdamPara
   const long long base4 = shard4 * p.rank;
   float4* m4 = reinterpret_cast<float4*>(p.m);
   float4* v4 = reinterpret_cast<float4*>(p.v);
-  // peer loads have NVLink latency (microseconds): every thread keeps UNROLL x world 16-byte loads in flight
+  // peer loads have NVLink latency (microseconds): every thread keeps UNROLL x world 16-byte loads in flight;
+  // with a multicast mapping one multimem.ld_reduce per element replaces the `world` peer loads
   constexpr int UNROLL = 4, MAXW = 8;
+  const bool nvls = p.mc_grads != nullptr && p.mc_w16 != nullptr;
   const long long stride = (long long)nblk * blockDim.x;
   for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < shard4; i0 += stride * UNROLL) {
     float4 t[UNROLL][MAXW];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long i = i0 + u * stride;
+      if (nvls) {
+        if (i < shard4) t[u][0] = multimem_ld_reduce_f32x4(p.mc_grads + 4 * (base4 + i));
+      } else {
 #pragma unroll
-      for (int q = 0; q < MAXW; ++q)
-        if (q < p.world && i < shard4)
-          t[u][q] = __ldcv(reinterpret_cast<const float4*>(p.grads[q]) + base4 + i);   // peer (NVLink) or local
+        for (int q = 0; q < MAXW; ++q)
+          if (q < p.world && i < shard4)
+            t[u][q] = __ldcv(reinterpret_cast<const float4*>(p.grads[q]) + base4 + i);   // peer (NVLink) or local
+      }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long i = i0 + u * stride;
       if (i >= shard4) break;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nvls) {
+        g = t[u][0];
+      } else {
 #pragma unroll
-      for (int q = 0; q < MAXW; ++q)
-        if (q < p.world) { g.x += t[u][q].x; g.y += t[u][q].y; g.z += t[u][q].z; g.w += t[u][q].w; }
+        for (int q = 0; q < MAXW; ++q)
+          if (q < p.world) { g.x += t[u][q].x; g.y += t[u][q].y; g.z += t[u][q].z; g.w += t[u][q].w; }
+      }
       float4 mi = m4[i], vi = v4[i];
       float4 pi = reinterpret_cast<const float4*>(p.params[p.rank])[base4 + i];
 #define LBX_ADAM1(c)                                          \
@@ -732,12 +759,17 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const ShardedAdamPara
       v4[i] = vi;
       __nv_bfloat162 lo = __floats2bfloat162_rn(pi.x, pi.y), hi = __floats2bfloat162_rn(pi.z, pi.w);
       const uint2 packed = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      if (nvls && !p.push_fp32) {                   // all-gather: one multicast store reaches every rank
+        reinterpret_cast<float4*>(p.params[p.rank])[base4 + i] = pi;
+        multimem_st_b32x2(p.mc_w16 + 4 * (base4 + i), packed);
+      } else {
 #pragma unroll
-      for (int q = 0; q < MAXW; ++q)                // all-gather by peer stores
-        if (q < p.world) {
-          if (p.push_fp32 || q == p.rank) reinterpret_cast<float4*>(p.params[q])[base4 + i] = pi;
-          reinterpret_cast<uint2*>(p.w16[q])[base4 + i] = packed;
-        }
+        for (int q = 0; q < MAXW; ++q)              // all-gather by peer stores
+          if (q < p.world) {
+            if (p.push_fp32 || q == p.rank) reinterpret_cast<float4*>(p.params[q])[base4 + i] = pi;
+            reinterpret_cast<uint2*>(p.w16[q])[base4 + i] = packed;
+          }
+      }
     }
   }
   // ---- barrier 2: all shards have been pushed everywhere and nobody reads this rank's gradient any more ----
@@ -897,7 +929,7 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
                           void* const* signal_ptrs, float* m_shard, float* v_shard, long long n, int rank, int world,
                           unsigned int* epoch_dev, unsigned int* local_sync_dev, float lr, float beta1, float beta2,
                           float eps, long long* step_dev, float* lr_t_dev, float grad_scale, int push_fp32,
-                          void* stream) {
+                          const void* mc_grads, void* mc_w16, void* stream) {
   LBX_CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
   LBX_CHECK_ARG(n > 0 && n % (4LL * world) == 0, "the flat length must be a multiple of 4*world (pad the buffers)");
   LBX_CHECK_ARG(params_ptrs && grads_ptrs && w16_ptrs && signal_ptrs && m_shard && v_shard && epoch_dev &&
@@ -910,6 +942,7 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
   p.epoch = epoch_dev; p.local_sync = local_sync_dev; p.step = step_dev; p.lr_t = lr_t_dev;
   p.lr = lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale;
   p.push_fp32 = push_fp32;
+  p.mc_grads = (const float*)mc_grads; p.mc_w16 = (bf16*)mc_w16;
   LBX_CHECK_ARG(world <= 8, "at most 8 ranks (one NVLink domain)");
   // every block must be able to be resident at once (grid-wide flags): occupancy-limited grid
   int dev = 0, sms = 0, per_sm = 0;

@@ -15,6 +15,7 @@ semantics follow the reference; the arithmetic runs through the C-ABI (include/l
   * precision "fp32" (default, inference parity): bf16x3 split accumulation, fp32 statistics;
     precision "bf16" (training configs): bf16 operands, fp32 accumulation / statistics / loss / master weights.
 """
+import ctypes
 import math
 import os
 
@@ -532,7 +533,7 @@ class XVector:
         n = self.params.numel()
         unit = 4 * world
         n_pad = -(-n // unit) * unit
-        handles = []
+        handles, mc_ptrs = [], []
 
         def make(dtype, src, length):
             t = symm.empty(length, dtype=dtype, device=dev)
@@ -541,6 +542,7 @@ class XVector:
                 t[:src.numel()].copy_(src)
             h = symm.rendezvous(t, group=process_group)
             handles.append(h)
+            mc_ptrs.append(int(getattr(h, "multicast_ptr", 0) or 0))
             return t, torch.tensor(list(h.buffer_ptrs), dtype=torch.int64, device=dev)
 
         self.params, p_ptrs = make(torch.float32, self.params, n_pad)
@@ -550,7 +552,9 @@ class XVector:
         torch.cuda.synchronize(dev)
         dist.barrier(group=process_group)                   # every rank has zeroed its pads before anyone signals
         a = self._adam
+        use_nvls = os.environ.get("LBX_DP_NVLS", "1") != "0" and mc_ptrs[1] != 0 and mc_ptrs[2] != 0
         self._sharded = dict(world=world, rank=rank, n=n_pad, p_ptrs=p_ptrs, g_ptrs=g_ptrs, w_ptrs=w_ptrs,
+                             mc_grads=mc_ptrs[1] if use_nvls else 0, mc_w16=mc_ptrs[2] if use_nvls else 0,
                              s_ptrs=s_ptrs, sig=sig, handles=handles,
                              m=torch.zeros(n_pad // world, dtype=torch.float32, device=dev),
                              v=torch.zeros(n_pad // world, dtype=torch.float32, device=dev),
@@ -568,7 +572,9 @@ class XVector:
                                                     _lib.ptr(sh["v"]), sh["n"], sh["rank"], sh["world"],
                                                     _lib.ptr(sh["epoch"]), _lib.ptr(sh["local"]), a["lr"], a["beta1"],
                                                     a["beta2"], a["eps"], _lib.ptr(a["step"]), _lib.ptr(a["lr_t"]),
-                                                    1.0, 0, _lib.stream_ptr(self.device)))
+                                                    1.0, 0, ctypes.c_void_p(sh["mc_grads"] or None),
+                                                    ctypes.c_void_p(sh["mc_w16"] or None),
+                                                    _lib.stream_ptr(self.device)))
         self._grads_clean = True
         self._weights_dirty = False
         self._lo_dirty = True

@@ -34,7 +34,7 @@ if rank == 0:
     d = (m.params[:npar] - ref.params).abs().mean().item(); s = (ref.params - xvector.create((50, 40), 4, precision="bf16", seed=3).params).abs().mean().item()
     w = (m.w16[:npar].float() - ref.w16.float()).abs().max().item()
     err = int(m._sharded["local"][3].item()) if m._sharded is not None else 0
-    print("MEANDIFF", d, "STEP", s, "W16", w, "ERR", err)
+    print("MEANDIFF", d, "STEP", s, "W16", w, "ERR", err, "NVLS", bool(m._sharded and m._sharded.get("mc_grads")))
 dist.destroy_process_group()
 ''' % ROOT
 

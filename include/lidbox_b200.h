@@ -128,6 +128,32 @@ int lbx_window_normalization_f32(const float* x, float* y, long long B, int T, i
                                  int normalize_variance, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Chunking, chunk-score merging and C_avg (the callers either side of the path: SURVEY.md §8(f) rows 2-4)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* lidbox/data/steps.py:607-615 create_signal_chunks: number of chunks of chunk_length samples every chunk_step samples,
+ * including the zero-padded last one when its missing tail is <= max_pad samples (host arithmetic; <0 on bad input) */
+long long lbx_num_signal_chunks(long long N, long long chunk_length, long long chunk_step, long long max_pad);
+/* steps.py:612-615: sig [B,N] -> out [B*num_chunks, chunk_length]; chunk c of signal b is row b*num_chunks + c, samples
+ * behind the end of the signal are zero */
+int lbx_signal_chunks_f32(const float* sig, long long B, long long N, long long chunk_length, long long chunk_step,
+                          long long num_chunks, float* out, void* stream);
+/* lidbox/util.py:41-57 merge_chunk_predictions (stack_and_average): out[g,:] = mean of the rows
+ * row_index[group_offsets[g] .. group_offsets[g+1]) of pred [rows, D] */
+int lbx_group_mean_f32(const float* pred, const long long* row_index, const long long* group_offsets,
+                       long long num_groups, int D, float* out, void* stream);
+/* lidbox/metrics.py:52-72 AverageDetectionCost.update_state (onehot [B,N] f32, labels NULL) and
+ * :104-109 SparseAverageDetectionCost.update_state (labels [B] i32, onehot NULL): adds the batch to the counters
+ * tp, fn [N,Th] and fp_pairs, tn_pairs [N,N,Th] (f32, caller-zeroed at reset_states) for scores pred [B,N]. */
+int lbx_cavg_update_f32(const float* onehot, const int* labels, const float* pred, long long B, int N,
+                        const float* thresholds, int num_thresholds, float* tp, float* fn, float* fp_pairs,
+                        float* tn_pairs, void* stream);
+/* metrics.py:74-99 result(): C_avg per threshold (optional output, [Th]) and its minimum (device scalar) */
+int lbx_cavg_result_f32(const float* tp, const float* fn, const float* fp_pairs, const float* tn_pairs, int N,
+                        int num_thresholds, float C_miss, float C_fa, float P_tar, float* cavg_per_threshold,
+                        float* cavg_min, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Energy VAD (the step before the feature stage: steps.py:417-432 compute_rms_vad, :183-200 apply_vad)
  * ---------------------------------------------------------------------------------------------------------- */
 

@@ -51,6 +51,11 @@ SIGNATURES = {
     "lbx_row_rms_f32": (c_int, [_P, c_ll, c_int, _P, _P]),
     "lbx_rms_vad_f32": (c_int, [_P, c_ll, c_ll, c_int, c_float, c_float, c_ll, _P, _P, _P]),
     "lbx_vad_compact_f32": (c_int, [_P, c_ll, c_ll, c_int, _P, c_ll, _P, _P, _P, _P]),
+    "lbx_num_signal_chunks": (c_ll, [c_ll, c_ll, c_ll, c_ll]),
+    "lbx_signal_chunks_f32": (c_int, [_P, c_ll, c_ll, c_ll, c_ll, c_ll, _P, _P]),
+    "lbx_group_mean_f32": (c_int, [_P, _P, _P, c_ll, c_int, _P, _P]),
+    "lbx_cavg_update_f32": (c_int, [_P, _P, _P, c_ll, c_int, _P, c_int, _P, _P, _P, _P, _P]),
+    "lbx_cavg_result_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, c_float, c_float, _P, _P, _P]),
     "lbx_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), _P]),
     "lbx_set_pdl": (c_int, [c_int]),
     "lbx_set_gemm_pair": (c_int, [c_int]),

@@ -94,7 +94,7 @@ class _Geometry:
 
 class XVector:
     def __init__(self, input_shape, num_outputs, channel_dropout_rate=0, name="x-vector", frames=None, segments=None,
-                 precision="fp32", head="log_softmax", seed=None, device=None):
+                 precision="fp32", head="log_softmax", seed=None, device=None, output_name="outputs"):
         if len(input_shape) != 2:
             raise ValueError("input_shape must be (T or None, F)")
         self.name = name
@@ -114,6 +114,7 @@ class XVector:
         if head not in ("log_softmax", "l2_normalize", "none"):
             raise ValueError("unknown head " + head)
         self.precision, self.head = precision, head
+        self.output_name = output_name                     # "outputs" (xvector.py:64) / "output" (xvector_extended.py:40)
         self.device = _lib.require_cuda(device)
         self._dropout_seed = 0x5EED if seed is None else int(seed)
         self._dropout_calls = 0
@@ -138,7 +139,7 @@ class XVector:
         for sgm in self.segments:
             self.layers.append(dict(name=sgm.name, kind="dense", K=d_in, N=sgm.units, relu=sgm.activation == "relu"))
             d_in = sgm.units
-        self.layers.append(dict(name="outputs", kind="dense", K=d_in, N=self.num_outputs, relu=False))
+        self.layers.append(dict(name=self.output_name, kind="dense", K=d_in, N=self.num_outputs, relu=False))
         # one flat fp32 buffer holds every kernel as [K, ldw] (Keras layout, pitch padded to 8 columns) and every
         # bias (padded to 8); padding stays zero.  Gradients, Adam moments and the bf16 operand copy mirror it, so the
         # optimizer is one elementwise pass and the gradient is one all-reduce.

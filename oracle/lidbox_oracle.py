@@ -324,13 +324,26 @@ FRAME_LAYERS = (                  # lidbox/models/xvector.py:53-57  (filters, ke
     ("frame4", 512, 1, 1),
     ("frame5", 1500, 1, 1),
 )
+XVECTOR_EXTENDED_FRAME_LAYERS = (  # lidbox/models/xvector_extended.py:25-34
+    ("frame1", 512, 5, 1),
+    ("frame2", 512, 1, 1),
+    ("frame3", 512, 3, 2),
+    ("frame4", 512, 1, 1),
+    ("frame5", 512, 3, 3),
+    ("frame6", 512, 1, 1),
+    ("frame7", 512, 3, 4),
+    ("frame8", 512, 1, 1),
+    ("frame9", 512, 1, 1),
+    ("frame10", 1500, 1, 1),
+)
 
 
-def xvector_param_shapes(input_dim, num_outputs):
-    """Keras layouts: Conv1D kernel [k, C_in, C_out], Dense kernel [in, out] (xvector.py:38-65)."""
+def xvector_param_shapes(input_dim, num_outputs, frame_layers=FRAME_LAYERS, output_name="outputs"):
+    """Keras layouts: Conv1D kernel [k, C_in, C_out], Dense kernel [in, out] (xvector.py:38-65).
+    frame_layers=XVECTOR_EXTENDED_FRAME_LAYERS, output_name="output" gives xvector_extended.py:22-43."""
     shapes = {}
     c_in = input_dim
-    for name, filters, k, _ in FRAME_LAYERS:
+    for name, filters, k, _ in frame_layers:
         shapes[name + "/kernel"] = (k, c_in, filters)
         shapes[name + "/bias"] = (filters,)
         c_in = filters
@@ -338,17 +351,18 @@ def xvector_param_shapes(input_dim, num_outputs):
     shapes["segment1/bias"] = (512,)
     shapes["segment2/kernel"] = (512, 512)
     shapes["segment2/bias"] = (512,)
-    shapes["outputs/kernel"] = (512, num_outputs)
-    shapes["outputs/bias"] = (num_outputs,)
+    shapes[output_name + "/kernel"] = (512, num_outputs)
+    shapes[output_name + "/bias"] = (num_outputs,)
     return shapes
 
 
-def xvector_init(input_dim, num_outputs, seed=0, dtype=np.float32, bias_scale=0.0):
+def xvector_init(input_dim, num_outputs, seed=0, dtype=np.float32, bias_scale=0.0, frame_layers=FRAME_LAYERS,
+                 output_name="outputs"):
     """Keras default init: glorot-uniform kernels, zero biases.
     bias_scale > 0 draws small random biases instead so that tests exercise the bias path."""
     rng = np.random.default_rng(seed)
     params = {}
-    for name, shape in xvector_param_shapes(input_dim, num_outputs).items():
+    for name, shape in xvector_param_shapes(input_dim, num_outputs, frame_layers, output_name).items():
         if name.endswith("/kernel"):
             receptive = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
             fan_in, fan_out = shape[-2] * receptive, shape[-1] * receptive
@@ -387,12 +401,14 @@ def log_softmax(x):
     return z - np.log(np.exp(z).sum(axis=-1, keepdims=True))
 
 
-def xvector_forward(params, x, embedding=False, return_activations=False):
-    """lidbox/models/xvector.py:46-67 (forward, no dropout) and :70-73 (embedding = pre-ReLU segment1)."""
+def xvector_forward(params, x, embedding=False, return_activations=False, frame_layers=FRAME_LAYERS,
+                    output_name="outputs", output_activation="log_softmax"):
+    """lidbox/models/xvector.py:46-67 (forward, no dropout) and :70-73 (embedding = pre-ReLU segment1);
+    with the extended layer list: lidbox/models/xvector_extended.py:22-43."""
     dtype = x.dtype
     acts = {}
     h = x
-    for name, _, _, stride in FRAME_LAYERS:
+    for name, _, _, stride in frame_layers:
         h = conv1d_causal(h, params[name + "/kernel"].astype(dtype), params[name + "/bias"].astype(dtype), stride)
         acts[name] = h
     h = stats_pooling(h)
@@ -404,9 +420,9 @@ def xvector_forward(params, x, embedding=False, return_activations=False):
     acts["segment1"] = h
     h = np.maximum(h @ params["segment2/kernel"].astype(dtype) + params["segment2/bias"].astype(dtype), 0)
     acts["segment2"] = h
-    h = h @ params["outputs/kernel"].astype(dtype) + params["outputs/bias"].astype(dtype)
-    acts["outputs"] = h
-    out = log_softmax(h)
+    h = h @ params[output_name + "/kernel"].astype(dtype) + params[output_name + "/bias"].astype(dtype)
+    acts[output_name] = h
+    out = log_softmax(h) if output_activation == "log_softmax" else h
     return (out, acts) if return_activations else out
 
 
@@ -458,7 +474,8 @@ def _bf16_ste(t, round_grad=False):
     return r
 
 
-def torch_xvector_forward(params, x, embedding=False, l2_normalize=False, emulate_bf16=False):
+def torch_xvector_forward(params, x, embedding=False, l2_normalize=False, emulate_bf16=False,
+                          frame_layers=FRAME_LAYERS, output_name="outputs"):
     """Same math as xvector_forward with torch ops so autograd provides the backward.
     params: dict name -> torch tensor in Keras layouts; x: [B, T, F].
     emulate_bf16=True restates the precision="bf16" training path: weights, stored activations and stored data
@@ -469,7 +486,7 @@ def torch_xvector_forward(params, x, embedding=False, l2_normalize=False, emulat
     import torch.nn.functional as F
     q = (lambda t, g=False: _bf16_ste(t, g)) if emulate_bf16 else (lambda t, g=False: t)
     h = q(x).transpose(1, 2)                                 # NCW for conv1d
-    for name, _, k, stride in FRAME_LAYERS:
+    for name, _, k, stride in frame_layers:
         w = q(params[name + "/kernel"]).permute(2, 1, 0)     # [k, Cin, Cout] -> [Cout, Cin, k] (cross-correlation)
         h = q(F.relu(F.conv1d(F.pad(h, (k - 1, 0)), w, params[name + "/bias"], stride=stride)), True)
     mean = h.mean(dim=2)
@@ -481,7 +498,7 @@ def torch_xvector_forward(params, x, embedding=False, l2_normalize=False, emulat
         return h
     h = q(F.relu(h), True)
     h = q(F.relu(h @ q(params["segment2/kernel"]) + params["segment2/bias"]), True)
-    h = h @ q(params["outputs/kernel"]) + params["outputs/bias"]
+    h = h @ q(params[output_name + "/kernel"]) + params[output_name + "/bias"]
     if emulate_bf16 and h.requires_grad:
         h.register_hook(lambda g: g.to(torch.bfloat16).to(g.dtype))
     if l2_normalize:                                         # spherespeaker.py:28-31 style head for the AP config
@@ -509,3 +526,106 @@ def torch_logmel(signals, sample_rate=16000, frame_length_ms=25, frame_step_ms=1
     S = torch.fft.rfft(frames, n=fft_length, dim=-1).abs() ** power
     W = torch.from_numpy(linear_to_mel_weight_matrix(num_mel_bins, fft_length // 2 + 1, sample_rate, fmin, fmax))
     return torch.log(S @ W + 1e-6)
+
+
+# --------------------------------------------------------------------------- #
+# lidbox/data/steps.py:579-632 create_signal_chunks, lidbox/util.py:41-57, lidbox/metrics.py
+# --------------------------------------------------------------------------- #
+
+
+def create_signal_chunks(signal, sample_rate, length_ms, step_ms, max_pad_ms=0):
+    """steps.py:586-588, :600-615 for one signal: [N] -> [num_chunks, chunk_length] (float32 time arithmetic,
+    int32 truncation, optional zero padding of the last chunk, tf.signal.frame with pad_end=False)."""
+    signal = np.asarray(signal)
+    sr = np.float32(sample_rate)
+    chunk_length = int(np.int32(sr * np.float32(1e-3 * length_ms)))
+    chunk_step = int(np.int32(sr * np.float32(1e-3 * step_ms)))
+    max_pad = int(np.int32(sr * np.float32(1e-3 * max_pad_ms)))
+    num_full_chunks = max(0, 1 + (signal.size - chunk_length) // chunk_step)      # python // floors like tf int32 //
+    last_chunk_length = signal.size - num_full_chunks * chunk_step
+    if last_chunk_length < chunk_length and chunk_length <= last_chunk_length + max_pad:
+        signal = np.concatenate([signal, np.zeros(chunk_length - last_chunk_length, signal.dtype)])
+    n = num_frames(signal.size, chunk_length, chunk_step)
+    if n == 0:
+        return np.zeros((0, chunk_length), signal.dtype)
+    return np.stack([signal[c * chunk_step:c * chunk_step + chunk_length] for c in range(n)])
+
+
+def merge_chunk_predictions(chunk_ids, predictions):
+    """util.py:41-57 with the default stack_and_average: rows whose id shares everything before the last '-' are
+    averaged; returns (sorted parent ids, [G, ...] means)."""
+    groups = {}
+    for cid, p in zip(chunk_ids, predictions):
+        groups.setdefault(cid.rsplit('-', 1)[0], []).append(np.asarray(p))
+    ids = sorted(groups)
+    return ids, np.stack([np.stack(groups[i]).mean(axis=0) for i in ids])
+
+
+class AverageDetectionCost:
+    """lidbox/metrics.py:6-99 restated with numpy float32 counters."""
+
+    def __init__(self, N, thresholds, C_miss=1.0, C_fa=1.0, P_tar=0.5):
+        assert N >= 2, "C_avg is undefined for less than 2 classes."          # metrics.py:21
+        self.thresholds = np.asarray(thresholds, np.float32)
+        assert self.thresholds.ndim == 1                                      # metrics.py:22
+        T = self.thresholds.size
+        self.N, self.C_miss, self.C_fa, self.P_tar = N, C_miss, C_fa, P_tar
+        self.fn, self.tp = np.zeros((N, T), np.float32), np.zeros((N, T), np.float32)
+        self.fp_pairs, self.tn_pairs = np.zeros((N, N, T), np.float32), np.zeros((N, N, T), np.float32)
+
+    def reset_states(self):
+        for a in (self.fn, self.tp, self.fp_pairs, self.tn_pairs):
+            a[...] = 0
+
+    def update_state(self, true_positives, predictions):
+        tpos = np.asarray(true_positives, np.float32)                         # metrics.py:56-61
+        label = tpos.argmax(axis=-1)
+        tpos = tpos[:, :, None]
+        tneg = (~tpos.astype(bool)).astype(np.float32)
+        pred = np.asarray(predictions, np.float32)[:, :, None]
+        ppos = (pred >= self.thresholds).astype(np.float32)
+        pneg = (pred < self.thresholds).astype(np.float32)
+        self.tp += (ppos * tpos).sum(axis=0)                                  # metrics.py:63-66
+        self.fn += (pneg * tpos).sum(axis=0)
+        np.add.at(self.fp_pairs, label, ppos * tneg)                          # metrics.py:68-71 scatter_nd_add
+        np.add.at(self.tn_pairs, label, pneg * tneg)
+
+    def result_per_threshold(self):
+        f32 = np.float32
+        P_miss = _divide_no_nan(self.fn, self.fn + self.tp).mean(axis=0, dtype=f32)      # metrics.py:81-86
+        P_fa = _divide_no_nan(_divide_no_nan(self.fp_pairs, self.fp_pairs + self.tn_pairs).sum(axis=1, dtype=f32),
+                              f32(self.N - 1)).mean(axis=0, dtype=f32)                   # metrics.py:89-98
+        return f32(self.C_miss * self.P_tar) * P_miss + f32(self.C_fa * (1 - self.P_tar)) * P_fa
+
+    def result(self):
+        return self.result_per_threshold().min()                              # metrics.py:105
+
+
+class SparseAverageDetectionCost(AverageDetectionCost):
+    """metrics.py:104-109: tf.one_hot(labels, N) (out-of-range labels give an all-zero row), then the dense update."""
+
+    def update_state(self, true_positives, predictions):
+        y = np.asarray(true_positives).astype(np.int64).reshape(-1)
+        onehot = np.zeros((y.size, self.N), np.float32)
+        ok = (y >= 0) & (y < self.N)
+        onehot[np.arange(y.size)[ok], y[ok]] = 1
+        super().update_state(onehot, predictions)
+
+
+def cavg_by_definition(labels, scores, threshold, N, C_miss=1.0, C_fa=1.0, P_tar=0.5):
+    """Independent statement of Li, Ma & Lee (2013) eq. 32 with python loops (small cases only): used to pin the
+    counter-based implementation above.  Classes without any trial contribute 0, as divide_no_nan does."""
+    labels, scores = np.asarray(labels), np.asarray(scores, np.float64)
+    p_miss = 0.0
+    p_fa = 0.0
+    for l in range(N):
+        target = scores[labels == l]                       # trials whose true class is l
+        if len(target):
+            p_miss += np.mean(target[:, l] < threshold)    # class l rejected although true
+        fa_l = 0.0
+        for m in range(N):
+            if m == l or not len(target):
+                continue
+            fa_l += np.mean(target[:, m] >= threshold)     # class m accepted although the truth is l
+        p_fa += fa_l / (N - 1)
+    return C_miss * P_tar * p_miss / N + C_fa * (1 - P_tar) * p_fa / N

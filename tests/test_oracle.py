@@ -292,3 +292,141 @@ def test_mfcc_is_orthonormal_dct():
     ref = scipy.fft.dct(x, type=2, norm="ortho", axis=-1)
     np.testing.assert_allclose(m[..., 1:], ref[..., 1:], atol=1e-12)
     np.testing.assert_allclose(m[..., 0], ref[..., 0] * np.sqrt(2.0), atol=1e-12)
+
+
+def test_xvector_extended_reference_shapes():
+    import torch
+    # /root/reference/lidbox/models/xvector_extended.py:25-40 + tests/test_models.py:104-107 (shape / no-NaN checks)
+    ext = dict(frame_layers=O.XVECTOR_EXTENDED_FRAME_LAYERS, output_name="output")
+    shapes = O.xvector_param_shapes(40, 7, **ext)
+    assert shapes["frame7/kernel"] == (3, 512, 512) and shapes["frame10/kernel"] == (1, 512, 1500)
+    assert shapes["segment1/kernel"] == (3000, 512) and shapes["output/kernel"] == (512, 7)
+    n = sum(int(np.prod(s)) for s in shapes.values())
+    conv = 5 * 40 * 512 + 512 * 512 + 3 * 512 * 512 + 512 * 512 + 3 * 512 * 512 + 512 * 512 + 3 * 512 * 512 \
+        + 512 * 512 + 512 * 512 + 512 * 1500 + 9 * 512 + 1500
+    assert n == conv + 3000 * 512 + 512 + 512 * 512 + 512 + 512 * 7 + 7
+    rng = np.random.default_rng(0)
+    for (B, T, F, n_out) in ((1, 1, 1, 1), (3, 50, 24, 5), (2, 400, 100, 100)):
+        params = O.xvector_init(F, n_out, seed=1, bias_scale=0.05, **ext)
+        x = rng.standard_normal((B, T, F))
+        p64 = {k: v.astype(np.float64) for k, v in params.items()}
+        lp, acts = O.xvector_forward(p64, x, return_activations=True, **ext)
+        assert lp.shape == (B, n_out) and not np.isnan(lp).any()
+        np.testing.assert_allclose(np.exp(lp).sum(axis=1), 1.0, rtol=1e-9)
+        assert acts["frame10"].shape == (B, -(-(-(-(-(-T // 2)) // 3)) // 4), 1500)     # ceil(ceil(ceil(T/2)/3)/4)
+        tp = {k: torch.tensor(v) for k, v in p64.items()}
+        lp_t = O.torch_xvector_forward(tp, torch.tensor(x), **ext).numpy()
+        np.testing.assert_allclose(lp_t, lp, rtol=1e-9, atol=1e-9)
+        raw = O.xvector_forward(p64, x, output_activation=None, **ext)
+        np.testing.assert_allclose(raw - np.log(np.exp(raw).sum(axis=1, keepdims=True)), lp, rtol=1e-9, atol=1e-9)
+
+
+def test_activation_row_geometry_for_any_layer_list():
+    # host logic of models/xvector.py: consecutive buffers share one row geometry, also when kernel_size < strides
+    from lidbox_b200.models.xvector import _Geometry, frame_layer
+    from lidbox_b200.models.xvector_extended import frame_layers
+    lists = [frame_layers(), [frame_layer(8, 5, 1), frame_layer(8, 3, 2), frame_layer(8, 3, 3), frame_layer(8, 1, 1)],
+             [frame_layer(8, 3, 4)], [frame_layer(8, 2, 5), frame_layer(8, 7, 2)]]
+    for frames in lists:
+        for T in (1, 2, 5, 23, 24, 25, 198, 400, 499):
+            geo = _Geometry(T, frames)
+            for L, f in enumerate(frames):
+                assert geo.T[L + 1] == -(-geo.T[L] // f.strides)
+                assert geo.Tpad[L] >= geo.T[L] + f.kernel_size - 1            # room for the causal left padding
+                assert geo.Tpad[L] % f.strides == 0 and geo.R[L] >= geo.T[L + 1]
+                if L + 1 < len(frames):
+                    assert geo.R[L] == geo.Tpad[L + 1]
+
+
+# --------------------------------------------------------------------------- chunking / merging / C_avg
+_CAVG_TRUE = np.array([[1, 0, 0], [0, 1, 0], [0, 1, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1], [0, 1, 0], [0, 0, 1]],
+                      np.float32)                               # the self-test inputs of lidbox/metrics.py:128-150
+_CAVG_PROB = np.array([[.1, .2, .9], [.9, .2, .0], [.1, .9, .0], [.2, .8, .5], [.6, .3, .1], [.1, .0, .7],
+                       [.1, .0, .7], [.9, .1, .0]], np.float32)
+
+
+def test_cavg_reference_selftest_and_definition():
+    with np.errstate(divide="ignore"):
+        pred = np.log(_CAVG_PROB)
+    thresholds = np.log(np.array([0.05, 0.4, 0.6, 0.95], np.float32))
+    cavg = O.AverageDetectionCost(3, thresholds)
+    assert cavg.result() == 0.0
+    cavg.update_state(_CAVG_TRUE, pred)
+    labels = _CAVG_TRUE.argmax(axis=1)
+    per_t = cavg.result_per_threshold()
+    want = [O.cavg_by_definition(labels, pred, t, 3) for t in thresholds]
+    np.testing.assert_allclose(per_t, want, rtol=1e-6)
+    assert cavg.result() == per_t.min() and 0.0 < cavg.result() < 0.5
+    # metrics.py:113-119 (_assert_P_fa): the l == m pairs never receive a count
+    idx = np.arange(3)
+    assert not cavg.fp_pairs[idx, idx].any() and not cavg.tn_pairs[idx, idx].any()
+    # counters are trial counts: every trial lands in exactly one of tp/fn per threshold
+    np.testing.assert_array_equal((cavg.tp + cavg.fn).sum(axis=0), len(labels))
+    np.testing.assert_array_equal((cavg.fp_pairs + cavg.tn_pairs).sum(axis=(0, 1)), len(labels) * 2)
+    # metrics.py:160-161: result is 0 after reset_states
+    cavg.reset_states()
+    assert cavg.result() == 0.0
+    # sparse variant == dense variant; two half batches == one batch
+    a, b = O.SparseAverageDetectionCost(3, thresholds), O.AverageDetectionCost(3, thresholds)
+    a.update_state(labels[:5], pred[:5])
+    a.update_state(labels[5:], pred[5:])
+    b.update_state(_CAVG_TRUE, pred)
+    assert a.result() == b.result()
+    # a perfect system has zero cost at a separating threshold, an inverted one the maximum P_tar*C_miss + (1-P_tar)*C_fa
+    perfect = np.where(_CAVG_TRUE > 0, 0.0, -10.0)
+    c = O.AverageDetectionCost(3, [-5.0])
+    c.update_state(_CAVG_TRUE, perfect)
+    assert c.result() == 0.0
+    c = O.AverageDetectionCost(3, [-5.0])
+    c.update_state(_CAVG_TRUE, -10.0 - perfect)
+    assert c.result() == 1.0
+
+
+def test_create_signal_chunks_reference_semantics():
+    rng = np.random.default_rng(0)
+    for (n, sr, length_ms, step_ms, pad_ms) in ((16000, 16000, 500, 250, 0), (16001, 16000, 500, 250, 0),
+                                                (20000, 16000, 1000, 1000, 0), (20000, 16000, 1000, 1000, 800),
+                                                (20000, 16000, 1000, 1000, 700), (100, 16000, 500, 250, 0),
+                                                (100, 16000, 500, 250, 500), (7999, 8000, 2000, 500, 10),
+                                                (48000, 44100, 30, 10, 5)):
+        sig = rng.standard_normal(n).astype(np.float32)
+        chunks = O.create_signal_chunks(sig, sr, length_ms, step_ms, pad_ms)
+        L = int(np.int32(np.float32(sr) * np.float32(1e-3 * length_ms)))
+        step = int(np.int32(np.float32(sr) * np.float32(1e-3 * step_ms)))
+        pad = int(np.int32(np.float32(sr) * np.float32(1e-3 * pad_ms)))
+        full = max(0, 1 + (n - L) // step)
+        assert chunks.shape[1] == L and chunks.shape[0] in (full, full + 1)
+        for c in range(full):
+            np.testing.assert_array_equal(chunks[c], sig[c * step:c * step + L])
+        if chunks.shape[0] == full + 1:               # padded tail chunk: the rest of the signal, then zeros
+            rest = n - full * step
+            assert rest < L <= rest + pad
+            np.testing.assert_array_equal(chunks[full, :rest], sig[full * step:])
+            assert not chunks[full, rest:].any()
+    assert O.create_signal_chunks(np.zeros(20000, np.float32), 16000, 1000, 1000, 800).shape == (2, 16000)
+    assert O.create_signal_chunks(np.zeros(20000, np.float32), 16000, 1000, 1000, 700).shape == (1, 16000)
+    assert O.create_signal_chunks(np.zeros(100, np.float32), 16000, 500, 250, 0).shape == (0, 8000)
+
+
+def test_merge_chunk_predictions_reference():
+    ids = ["utt-b-000001", "utt-a-000002", "utt-b-000002", "utt-a-000001", "solo-000001"]
+    pred = np.arange(15, dtype=np.float32).reshape(5, 3)
+    parents, merged = O.merge_chunk_predictions(ids, pred)
+    assert parents == ["solo", "utt-a", "utt-b"]
+    np.testing.assert_allclose(merged, [pred[4], (pred[1] + pred[3]) / 2, (pred[0] + pred[2]) / 2])
+
+
+def test_chunk_host_logic_matches_oracle():
+    # host side of lidbox_b200/data/steps.py (no GPU): geometry, chunk counts through the C-ABI, chunk ids
+    from lidbox_b200.data import steps
+    for (n, sr, length_ms, step_ms, pad_ms) in ((16000, 16000, 500, 250, 0), (20000, 16000, 1000, 1000, 800),
+                                                (20000, 16000, 1000, 1000, 700), (100, 16000, 500, 250, 0),
+                                                (100, 16000, 500, 250, 500), (7999, 8000, 2000, 500, 10),
+                                                (48000, 44100, 30, 10, 5), (0, 16000, 500, 250, 500)):
+        L, step, pad = steps.chunk_geometry(sr, length_ms, step_ms, pad_ms)
+        want = O.create_signal_chunks(np.zeros(n, np.float32), sr, length_ms, step_ms, pad_ms)
+        assert (steps.num_signal_chunks(n, L, step, pad), L) == want.shape
+    assert steps.chunk_ids("utt", 3) == ["utt-000001", "utt-000002", "utt-000003"]     # steps.py:589-591: width 6
+    assert steps.chunk_ids("utt", 1, max_num_chunks_per_signal=100) == ["utt-01"]
+    with pytest.raises(ValueError):
+        steps.chunk_geometry(16000, 0, 10)

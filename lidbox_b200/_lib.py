@@ -59,6 +59,7 @@ SIGNATURES = {
     "lbx_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), _P]),
     "lbx_set_pdl": (c_int, [c_int]),
     "lbx_set_gemm_pair": (c_int, [c_int]),
+    "lbx_set_gemm_fast_epilogue": (c_int, [c_int]),
     "lbx_pack_rows_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, _P]),
     "lbx_stats_pool_fwd": (c_int, [_P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
     "lbx_stats_pool_bwd": (c_int, [_P, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_int, _P]),
@@ -95,6 +96,7 @@ def lib():
         if os.environ.get("LBX_PDL", "1") == "0":
             handle.lbx_set_pdl(0)
         handle.lbx_set_gemm_pair(0 if os.environ.get("LBX_GEMM_PAIR", "1") == "0" else 1)
+        handle.lbx_set_gemm_fast_epilogue(0 if os.environ.get("LBX_GEMM_FAST_EPI", "1") == "0" else 1)
         _lib = handle
     return _lib
 

@@ -38,18 +38,26 @@ constexpr int GEMM_THREADS = 32 * LBX_CTRL_WARPS + 32 * EPI_WARPS;   // warpgrou
 constexpr int BIAS_SMEM_FLOATS = 3072;         // the bias vector is staged in shared memory when N fits
 constexpr int STAGE_PITCH = 80;                // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16-byte accesses)
 constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH;
+// fast bf16 epilogue: per warp one 32 x 64 B tile in the TMA 64-byte swizzle as the source of bulk tensor stores, and
+// (ReLU-backward launches) one more as the destination of bulk tensor loads of the mask
+constexpr int FAST_TILE_BYTES = 32 * 64;
+constexpr int BAR_BYTES = 1024;                // mbarriers + TMEM pointer (keeps the epilogue tiles 1024-byte aligned)
 
 // tile-N variants: 256 (large problems), 128, and 64 (the small-M dense layers: enough CTAs without split-K)
 // PAIR: two CTAs of a cluster share one 256 x BN tile through tcgen05 cta_group::2 — each CTA stages its own 128 rows of
 // A and only HALF of the B tile, which cuts the operand bytes every SM has to ingest per k-block from 48 KB to 32 KB
-template <int BN, bool PAIR = false>
+template <int BN, bool PAIR = false, bool HAS_MASK = false>
 struct Cfg {
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = PAIR ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+  // the mask tiles of the ReLU-backward launches take the shared memory of one pipeline stage
+  static constexpr int STAGES = (PAIR ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8))) - (HAS_MASK ? 1 : 0);
   static constexpr int TMEM_COLS = 2 * BN;    // 2 accumulator stages x BN fp32 columns
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_SMEM_FLOATS * 4 +
-                                 EPI_WARPS * STAGE_BYTES_PER_WARP;
+  static constexpr int EPI_BYTES = HAS_MASK ? EPI_WARPS * 2 * FAST_TILE_BYTES : EPI_WARPS * STAGE_BYTES_PER_WARP;
+  static_assert(EPI_BYTES >= EPI_WARPS * STAGE_BYTES_PER_WARP && EPI_BYTES >= EPI_WARPS * FAST_TILE_BYTES, "epilogue tiles");
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + EPI_BYTES +
+                                 BIAS_SMEM_FLOATS * 4;
+  static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 struct GemmParams {
@@ -72,6 +80,7 @@ struct GemmParams {
   int accumulate;          // 1: out = out + x (read-modify-write, non-atomic)
   float* colsum;           // optional: colsum[n % colsum_mod] += sum_m x[m, n] (bias gradient of the layer below)
   int colsum_mod;
+  int fast;                // 1: bf16 output through the lean epilogue (TMA stores / TMA mask loads, prefetched TMEM loads)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -106,6 +115,27 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// ---- bulk tensor store (shared -> global) of the fast epilogue ----
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 // ---- cluster / CTA-pair helpers ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -241,9 +271,10 @@ template <int LAYOUT, int BN, bool HAS_MASK, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+                     const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapMask,
                      const GemmParams p) {
-  constexpr int STAGES = Cfg<BN, PAIR>::STAGES, STAGE_BYTES = Cfg<BN, PAIR>::STAGE_BYTES,
-                TMEM_COLS = Cfg<BN, PAIR>::TMEM_COLS;
+  constexpr int STAGES = Cfg<BN, PAIR, HAS_MASK>::STAGES, STAGE_BYTES = Cfg<BN, PAIR, HAS_MASK>::STAGE_BYTES,
+                TMEM_COLS = Cfg<BN, PAIR, HAS_MASK>::TMEM_COLS;
   constexpr int BN_LOCAL = PAIR ? BN / 2 : BN;   // B columns staged by this CTA
   constexpr bool A_MN = LAYOUT == 1;            // A stored [K, M] (contraction index is the slow one)
   constexpr bool B_MN = LAYOUT != 0;            // B stored [K, N]
@@ -253,9 +284,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES + 256);
-  unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_bias + BIAS_SMEM_FLOATS);
+  uint64_t* mask_bar = tempty_bar + 2;          // one per epilogue warp (fast epilogue: mask tile landed)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mask_bar + EPI_WARPS);
+  static_assert((2 * 8 + 4 + EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier area");
+  unsigned char* s_stage = smem + (size_t)STAGES * STAGE_BYTES + BAR_BYTES;        // 1024-byte aligned epilogue tiles
+  float* s_bias = reinterpret_cast<float*>(s_stage + Cfg<BN, PAIR, HAS_MASK>::EPI_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -282,6 +315,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i, 1);
       mbar_init(tempty_bar + i, PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // one arrival per epilogue warp (of both CTAs)
+    }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(mask_bar + i, 1);
+    if (p.fast) {
+      tma_prefetch_desc(&mapOut);
+      if (HAS_MASK) tma_prefetch_desc(&mapMask);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -427,10 +465,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // the bias vector is read by every tile: stage it once (global loads in the epilogue's critical path cost an L2
     // round trip per 32-column chunk with only two warps per scheduler to hide it)
     const bool bias_smem = LBX_BIAS_SMEM && p.bias != nullptr && p.N <= BIAS_SMEM_FLOATS;
-    if (bias_smem) {
-      for (int i = threadIdx.x - 32 * LBX_CTRL_WARPS; i < p.N; i += 32 * EPI_WARPS) s_bias[i] = __ldg(p.bias + i);
+    if (bias_smem) {      // zero-filled up to the next multiple of 32 so that the last (partial) chunk needs no guard
+      for (int i = threadIdx.x - 32 * LBX_CTRL_WARPS; i < ((p.N + 31) & ~31) && i < BIAS_SMEM_FLOATS; i += 32 * EPI_WARPS)
+        s_bias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     }
+    uint32_t mphase = 0;                         // parity of this warp's mask barrier (fast epilogue)
     for (int tile = worker; tile < total_tiles; tile += n_workers) {
       const int rem = tile % mn_tiles;
       const int m_unit = rem / n_tiles, n_blk = rem - m_unit * n_tiles;
@@ -458,6 +498,126 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const bool mvec = HAS_MASK && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
       const bool pvec = p.accumulate && p.out_dtype == LBX_BF16 && !p.epi_atomic && in_range &&
                         ((reinterpret_cast<uintptr_t>(prow) & 15) == 0);
+      if (p.fast) {
+        // ---------------- lean bf16 epilogue ----------------
+        // per 32-column chunk: TMEM load (the next chunk's load is already in flight) -> bias -> ReLU-backward mask
+        // (tile fetched by a bulk tensor load one chunk ahead) -> zero junk rows -> bf16 (ReLU folded into the
+        // conversion) -> swizzled shared-memory tile -> one bulk tensor store (clipped at M / N by the tensor map)
+        const int wi = warp - LBX_CTRL_WARPS;
+        unsigned char* st_out = s_stage + wi * FAST_TILE_BYTES;
+        unsigned char* st_msk = s_stage + (EPI_WARPS + wi) * FAST_TILE_BYTES;
+        uint64_t* mbar_m = mask_bar + wi;
+        const int ncols_rem = p.N - col_base;
+        const int nch = (ncols_rem <= 0 || warp_row0 >= p.M) ? 0 : min(CHUNKS, (ncols_rem + 31) >> 5);
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);           // 64-byte swizzle: 16-byte chunk index ^= (row / 2) % 4
+        const bool kill_row = row_zero || !in_range;
+        if (HAS_MASK && nch > 0 && lane == 0) {
+          mbar_expect_tx(mbar_m, FAST_TILE_BYTES);
+          tma_load_2d(&mapMask, mbar_m, st_msk, col_base, warp_row0);
+        }
+        mbar_wait(tfull_bar + acc, acc_phase);
+        tc_fence_after();
+        uint32_t v[32];
+        if (nch > 0) tc_ld32(taddr, v);
+        bool released = false;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          const int n0 = col_base + c * 32;
+          tc_wait_ld();
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          if (c + 1 < nch) {
+            tc_ld32(taddr + (c + 1) * 32, v);
+          } else {
+            // every TMEM read of this warp has landed: hand the accumulator stage back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(tempty_bar + acc), 0));
+              else mbar_arrive(tempty_bar + acc);
+            }
+            released = true;
+          }
+          if (bias_smem) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + 4 * q);
+              x[4 * q] += b4.x; x[4 * q + 1] += b4.y; x[4 * q + 2] += b4.z; x[4 * q + 3] += b4.w;
+            }
+          }
+          if (HAS_MASK) {
+            mbar_wait(mbar_m, mphase);
+            mphase ^= 1;
+            uint4 mk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              mk[q] = *reinterpret_cast<const uint4*>(st_msk + lane * 64 + (((uint32_t)q ^ sw) << 4));
+            __syncwarp();                                          // all lanes have read the tile: refill it
+            if (c + 1 < nch && lane == 0) {
+              mbar_expect_tx(mbar_m, FAST_TILE_BYTES);
+              tma_load_2d(&mapMask, mbar_m, st_msk, n0 + 32, warp_row0);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t w[4] = {mk[q].x, mk[q].y, mk[q].z, mk[q].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {     // keep x where the bf16 mask value is > 0 (sign clear, magnitude non-zero)
+                if ((int)(w[i] << 16) <= 0) x[8 * q + 2 * i] = 0.0f;
+                if ((int)(w[i] & 0xFFFF0000u) <= 0) x[8 * q + 2 * i + 1] = 0.0f;
+              }
+            }
+          }
+          if (kill_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+          }
+          uint32_t pk[16];
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = cvt_bf16x2_relu(x[2 * j], x[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = cvt_bf16x2(x[2 * j], x[2 * j + 1]);
+          }
+          if (lane == 0) bulk_wait_read0();                        // the previous store has finished reading the tile
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(st_out + lane * 64 + (((uint32_t)q ^ sw) << 4)) =
+                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapOut, smem_u32(st_out), n0, warp_row0);
+            bulk_commit();
+          }
+          if (p.colsum != nullptr) {             // host guarantees relu == 0 here: x is what was stored (before rounding)
+            const int ncols = min(32, p.N - n0);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send = up ? x[i] : x[i + off];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                x[i] = (up ? x[i + off] : x[i]) + recv;
+              }
+            }
+            if (lane < ncols) atomicAdd(p.colsum + (n0 + lane) % p.colsum_mod, x[0]);
+          }
+        }
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(tempty_bar + acc), 0));
+            else mbar_arrive(tempty_bar + acc);
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
 #ifndef LBX_EPI_GROUP
@@ -666,6 +826,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   }
 
+  if (p.fast && warp >= LBX_CTRL_WARPS && lane == 0) bulk_wait0();   // bulk stores complete before shared memory goes away
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();                 // the peer may still be reading this CTA's shared memory / barriers
@@ -700,7 +861,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 tensor map: inner extent `cols` (pitch 1), outer extent `rows` with pitch `ld` elements (ld may be < cols)
 static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
-                    int box_rows) {
+                    int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_error(LBX_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -708,7 +869,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(LBX_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld base=%p", (int)r, rows,
@@ -718,6 +879,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 
 static int g_num_sms = 0;
 static int g_use_pair = 1;
+static int g_use_fast_epi = 1;
 
 }  // namespace lbx
 
@@ -780,8 +942,13 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   p.colsum_mod = g->colsum_mod > 0 ? g->colsum_mod : 1;
   LBX_CHECK_ARG(!(g->colsum && (g->out_lo || g->epi_atomic)), "colsum cannot be combined with out_lo / atomic epilogues");
 
-  CUtensorMap mA0, mA1, mB0, mB1;
+  CUtensorMap mA0, mA1, mB0, mB1, mOut, mMask;
   int rc;
+  // lean epilogue: bf16 result, plain store (no atomics / read-modify-write / residual plane), 16-byte aligned rows
+  const bool al16 = (g->ldo % 8 == 0) && (reinterpret_cast<uintptr_t>(g->out) & 15) == 0;
+  p.fast = g_use_fast_epi && g->out_dtype == LBX_BF16 && !g->epi_atomic && !g->accumulate && g->out_lo == nullptr &&
+           al16 && (g->bias == nullptr || ((p.N + 31) & ~31) <= BIAS_SMEM_FLOATS) && !(g->colsum && g->relu) &&
+           (g->mask_src == nullptr || (reinterpret_cast<uintptr_t>(g->mask_src) & 15) == 0);
   // tile-N 256 unless the problem is narrower than 128 columns (measured: 128 never wins on the TDNN shapes)
   const int bn = (g->tile_n == 64 || g->tile_n == 128 || g->tile_n == 256) ? g->tile_n : (p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256));
   // CTA pairs (tcgen05 cta_group::2) for the 256-wide tiles: every CTA stages only half of the B tile
@@ -792,6 +959,12 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   mA1 = mA0; mB1 = mB0;
   if (g->a1 && (rc = make_map(&mA1, g->a1, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
   if (g->b1 && (rc = make_map(&mB1, g->b1, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
+  mOut = mA0; mMask = mA0;
+  if (p.fast) {
+    if ((rc = make_map(&mOut, g->out, p.M, p.N, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (g->mask_src && (rc = make_map(&mMask, g->mask_src, p.M, p.N, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
+  }
   if (g_num_sms == 0) {
     int dev = 0, n = 0;
     LBX_CUDA(cudaGetDevice(&dev));
@@ -800,12 +973,12 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)Cfg<N_>::SMEM));                                                              \
   LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, N_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                (int)Cfg<N_>::SMEM))
+                                (int)Cfg<N_, false, true>::SMEM))
 #define LBX_SET_SMEM_PAIR(L)                                                                                       \
   LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)Cfg<256, true>::SMEM));                                                       \
   LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<L, 256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                (int)Cfg<256, true>::SMEM))
+                                (int)Cfg<256, true, true>::SMEM))
     LBX_SET_SMEM(0, 256); LBX_SET_SMEM(1, 256); LBX_SET_SMEM(2, 256);
     LBX_SET_SMEM(0, 128); LBX_SET_SMEM(1, 128); LBX_SET_SMEM(2, 128);
     LBX_SET_SMEM(0, 64); LBX_SET_SMEM(1, 64); LBX_SET_SMEM(2, 64);
@@ -821,7 +994,12 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(pair ? 2 * workers : workers));
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = pair ? Cfg<256, true>::SMEM : (bn == 256 ? Cfg<256>::SMEM : (bn == 128 ? Cfg<128>::SMEM : Cfg<64>::SMEM));
+  const bool hm = p.mask_src != nullptr;
+  cfg.dynamicSmemBytes =
+      pair ? (hm ? Cfg<256, true, true>::SMEM : Cfg<256, true>::SMEM)
+           : (bn == 256 ? (hm ? Cfg<256, false, true>::SMEM : Cfg<256>::SMEM)
+                        : (bn == 128 ? (hm ? Cfg<128, false, true>::SMEM : Cfg<128>::SMEM)
+                                     : (hm ? Cfg<64, false, true>::SMEM : Cfg<64>::SMEM)));
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
@@ -841,8 +1019,8 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   cfg.numAttrs = na;
   cudaError_t le;
 #define LBX_GEMM_LAUNCH(L, N_, P_)                                                                          \
-  le = p.mask_src ? cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, true, P_>, mA0, mA1, mB0, mB1, p)     \
-                  : cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, false, P_>, mA0, mA1, mB0, mB1, p)
+  le = p.mask_src ? cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, true, P_>, mA0, mA1, mB0, mB1, mOut, mMask, p)  \
+                  : cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, false, P_>, mA0, mA1, mB0, mB1, mOut, mMask, p)
   if (pair) {
     if (g->layout == 0) LBX_GEMM_LAUNCH(0, 256, true); else if (g->layout == 1) LBX_GEMM_LAUNCH(1, 256, true); else LBX_GEMM_LAUNCH(2, 256, true);
   } else if (bn == 256) {
@@ -855,6 +1033,12 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
 #undef LBX_GEMM_LAUNCH
   if (le != cudaSuccess) return set_error(LBX_ECUDA, "GEMM launch failed: %s", cudaGetErrorString(le));
   LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+// lean bf16 epilogue (TMA stores, TMA mask loads, prefetched TMEM loads); LBX_GEMM_FAST_EPI=0 selects the general one
+extern "C" int lbx_set_gemm_fast_epilogue(int enabled) {
+  g_use_fast_epi = enabled ? 1 : 0;
   return LBX_OK;
 }
 

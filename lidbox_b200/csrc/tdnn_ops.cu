@@ -255,32 +255,67 @@ __global__ void adam_tick_kernel(long long* step, float* lr_t, float lr, float b
 }
 
 // n4 = n / 4 float4 groups (the flat buffers are padded to a multiple of 4); optionally refreshes the bf16 operand
-// copy of the parameters (same flat layout) and resets the gradient for the next step
+// copy of the parameters (same flat layout) and resets the gradient for the next step.  Every thread keeps
+// 4 * LBX_ADAM_UNROLL 16-byte loads in flight; the moments are touched once per step and bypass L2 residency
+// (ld/st .cs) so that they do not evict the activations and weights the next step re-reads.
+#ifndef LBX_ADAM_UNROLL
+#define LBX_ADAM_UNROLL 2
+#endif
+#ifndef LBX_ADAM_STREAM
+#define LBX_ADAM_STREAM 1
+#endif
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                                   float4* __restrict__ v, long long n4,
                                                   const float* __restrict__ lr_t_ptr, float beta1, float beta2,
                                                   float eps, float grad_scale, uint2* __restrict__ p_bf16,
                                                   int zero_grads) {
   LBX_PDL_SYNC();
+  constexpr int U = LBX_ADAM_UNROLL;
   const float lr_t = *lr_t_ptr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
-    if (zero_grads) g[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#define LBX_ADAM1(c)                                        \
-    {                                                       \
-      const float gg = gi.c * grad_scale;                   \
-      mi.c = beta1 * mi.c + (1.0f - beta1) * gg;            \
-      vi.c = beta2 * vi.c + (1.0f - beta2) * gg * gg;       \
-      pi.c -= lr_t * mi.c / (sqrtf(vi.c) + eps);            \
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+    float4 gi[U], mi[U], vi[U], pi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        gi[u] = g[i];
+        pi[u] = p[i];
+#if LBX_ADAM_STREAM
+        mi[u] = __ldcs(m + i);
+        vi[u] = __ldcs(v + i);
+#else
+        mi[u] = m[i];
+        vi[u] = v[i];
+#endif
+      }
     }
-    LBX_ADAM1(x) LBX_ADAM1(y) LBX_ADAM1(z) LBX_ADAM1(w)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n4) break;
+      if (zero_grads) g[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#define LBX_ADAM1(c)                                              \
+      {                                                           \
+        const float gg = gi[u].c * grad_scale;                    \
+        mi[u].c = beta1 * mi[u].c + (1.0f - beta1) * gg;          \
+        vi[u].c = beta2 * vi[u].c + (1.0f - beta2) * gg * gg;     \
+        pi[u].c -= lr_t * mi[u].c / (sqrtf(vi[u].c) + eps);       \
+      }
+      LBX_ADAM1(x) LBX_ADAM1(y) LBX_ADAM1(z) LBX_ADAM1(w)
 #undef LBX_ADAM1
-    m[i] = mi;
-    v[i] = vi;
-    p[i] = pi;
-    if (p_bf16) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(pi.x, pi.y), hi = __floats2bfloat162_rn(pi.z, pi.w);
-      p_bf16[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+#if LBX_ADAM_STREAM
+      __stcs(m + i, mi[u]);
+      __stcs(v + i, vi[u]);
+#else
+      m[i] = mi[u];
+      v[i] = vi[u];
+#endif
+      p[i] = pi[u];
+      if (p_bf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(pi[u].x, pi[u].y), hi = __floats2bfloat162_rn(pi[u].z, pi[u].w);
+        p_bf16[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
     }
   }
 }
@@ -607,6 +642,124 @@ __global__ void __launch_bounds__(256) stats_pool_bwd_bf16r_kernel(const bf16* _
   }
 }
 
+// Column-owner variants for short time axes (T <= MAXT): a thread owns TWO channels of one utterance and keeps all T
+// values in registers (one 4-byte load per row, a warp reads 128 contiguous bytes per row, every load is issued before
+// the first use).  No cross-thread reduction is needed for the statistics; the backward kernel reduces the bias
+// gradient over the 4 utterances of a block in shared memory before its atomics.
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+template <int MAXT>
+__global__ void __launch_bounds__(128) stats_pool_fwd_bf16c_kernel(const bf16* __restrict__ y, int rows_per_utt, int T,
+                                                                  int C, int pitch, float clip_min,
+                                                                  float* __restrict__ out, float* __restrict__ var_raw,
+                                                                  bf16* __restrict__ out_hi) {
+  LBX_PDL_SYNC();
+  const int cp = blockIdx.x * 128 + threadIdx.x;          // channel pair
+  const int c0 = 2 * cp;
+  if (c0 >= C) return;
+  const long long b = blockIdx.y;
+  const int p2 = pitch >> 1;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(y + b * rows_per_utt * (long long)pitch) + cp;
+  uint32_t raw[MAXT];
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) raw[t] = t < T ? __ldg(base + (long long)t * p2) : 0u;
+  float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) {       // rows >= T hold zeros
+    s0 += bf16lo(raw[t]);
+    s1 += bf16hi(raw[t]);
+  }
+  const float inv_t = 1.0f / (float)T;
+  const float m0 = s0 / (float)T, m1 = s1 / (float)T;
+  float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) {
+    if (t < T) {
+      const float d0 = bf16lo(raw[t]) - m0, d1 = bf16hi(raw[t]) - m1;
+      q0 = fmaf(d0, d0, q0);
+      q1 = fmaf(d1, d1, q1);
+    }
+  }
+  (void)inv_t;
+  const float mean[2] = {m0, m1}, var[2] = {q0 / (float)T, q1 / (float)T};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = c0 + i;
+    if (c >= C) break;
+    const float sd = sqrtf(fminf(fmaxf(var[i], clip_min), 3.402823466e+38f));
+    out[b * 2 * C + c] = mean[i];
+    out[b * 2 * C + C + c] = sd;
+    if (var_raw) var_raw[b * C + c] = var[i];
+    if (out_hi) {
+      out_hi[b * 2 * C + c] = __float2bfloat16_rn(mean[i]);
+      out_hi[b * 2 * C + C + c] = __float2bfloat16_rn(sd);
+    }
+  }
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(256) stats_pool_bwd_bf16c_kernel(const bf16* __restrict__ y, long long B,
+                                                                  int rows_per_utt, int T, int C, int pitch,
+                                                                  float clip_min, const float* __restrict__ pooled,
+                                                                  const float* __restrict__ var_raw,
+                                                                  float* __restrict__ gpool, bf16* __restrict__ dz,
+                                                                  float* __restrict__ dbias, int zero_gpool) {
+  LBX_PDL_SYNC();
+  __shared__ float red[4][64][2];
+  const int px = threadIdx.x & 63, bl = threadIdx.x >> 6;
+  const int cp = blockIdx.x * 64 + px;
+  const int c0 = 2 * cp;
+  const long long b = (long long)blockIdx.y * 4 + bl;
+  const bool active = c0 < C && b < B;
+  float acc[2] = {0.0f, 0.0f};
+  if (active) {
+    const int p2 = pitch >> 1;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(y + b * rows_per_utt * (long long)pitch) + cp;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(dz + b * rows_per_utt * (long long)pitch) + cp;
+    uint32_t raw[MAXT];
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) raw[t] = t < T ? __ldg(src + (long long)t * p2) : 0u;
+    float mean[2], gm[2], gs[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = c0 + i;
+      if (c < C) {
+        mean[i] = pooled[b * 2 * C + c];
+        const float sd = pooled[b * 2 * C + C + c];
+        gm[i] = gpool[b * 2 * C + c] / (float)T;
+        gs[i] = var_raw[b * C + c] > clip_min ? gpool[b * 2 * C + C + c] / ((float)T * sd) : 0.0f;
+        if (zero_gpool) {
+          gpool[b * 2 * C + c] = 0.0f;
+          gpool[b * 2 * C + C + c] = 0.0f;
+        }
+      } else {
+        mean[i] = gm[i] = gs[i] = 0.0f;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+      if (t < T) {
+        const float f0 = bf16lo(raw[t]), f1 = bf16hi(raw[t]);
+        const float g0 = f0 > 0.0f ? fmaf(gs[0], f0 - mean[0], gm[0]) : 0.0f;
+        const float g1 = f1 > 0.0f ? fmaf(gs[1], f1 - mean[1], gm[1]) : 0.0f;
+        acc[0] += g0;
+        acc[1] += g1;
+        dst[(long long)t * p2] = pack2(g0, g1);
+      }
+    }
+  }
+  if (dbias == nullptr) return;
+  red[bl][px][0] = acc[0];
+  red[bl][px][1] = acc[1];
+  __syncthreads();
+  if (bl == 0 && c0 < C) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (c0 + i < C) atomicAdd(dbias + c0 + i, red[0][px][i] + red[1][px][i] + red[2][px][i] + red[3][px][i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Sharded optimizer step fused with the gradient exchange over NVLink peer memory (data parallel, one node):
 //   barrier -> reduce-scatter (peer loads of every rank's gradient shard) -> Adam on the shard -> all-gather (peer
@@ -830,6 +983,19 @@ int lbx_stats_pool_fwd(const void* y, int y_dtype, long long B, int rows_per_utt
                                                                          (bf16*)out_lo);
   else if (y_dtype == LBX_BF16 && out_lo == nullptr && pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
   {
+#ifndef LBX_POOL_COLUMN_OWNER
+#define LBX_POOL_COLUMN_OWNER 1
+#endif
+    if (LBX_POOL_COLUMN_OWNER && T <= 56) {
+      const dim3 g2((unsigned)ceil_div((C + 1) / 2, 128), (unsigned)B);
+      if (T <= 40)
+        LBX_LAUNCH_PDL(stats_pool_fwd_bf16c_kernel<40>, g2, dim3(128), 0, (cudaStream_t)stream, (const bf16*)y,
+                       rows_per_utt, T, C, pitch, clip_min, out, var_raw, (bf16*)out_hi);
+      else
+        LBX_LAUNCH_PDL(stats_pool_fwd_bf16c_kernel<56>, g2, dim3(128), 0, (cudaStream_t)stream, (const bf16*)y,
+                       rows_per_utt, T, C, pitch, clip_min, out, var_raw, (bf16*)out_hi);
+      return LBX_OK;
+    }
     if (T <= 48) {
       LBX_LAUNCH_PDL(stats_pool_fwd_bf16r_kernel<6>, dim3((unsigned)ceil_div(pitch / 8, 32), (unsigned)B), dim3(256), 0,
                      (cudaStream_t)stream, (const bf16*)y, rows_per_utt, T, C, pitch, clip_min, out, var_raw,
@@ -861,6 +1027,16 @@ int lbx_stats_pool_bwd(const void* y_bf16, long long B, int rows_per_utt, int T,
   LBX_CHECK_ARG(((reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(dz_bf16)) & 15) == 0,
                 "activation buffers must be 16-byte aligned");
   dim3 grid((unsigned)ceil_div(pitch / 8, 32), (unsigned)B);
+  if (LBX_POOL_COLUMN_OWNER && T <= 56) {
+    const dim3 g2((unsigned)ceil_div((C + 1) / 2, 64), (unsigned)ceil_div(B, 4));
+    if (T <= 40)
+      LBX_LAUNCH_PDL(stats_pool_bwd_bf16c_kernel<40>, g2, dim3(256), 0, (cudaStream_t)stream, (const bf16*)y_bf16, B,
+                     rows_per_utt, T, C, pitch, clip_min, pooled, var_raw, gpool, (bf16*)dz_bf16, dbias, zero_gpool);
+    else
+      LBX_LAUNCH_PDL(stats_pool_bwd_bf16c_kernel<56>, g2, dim3(256), 0, (cudaStream_t)stream, (const bf16*)y_bf16, B,
+                     rows_per_utt, T, C, pitch, clip_min, pooled, var_raw, gpool, (bf16*)dz_bf16, dbias, zero_gpool);
+    return LBX_OK;
+  }
   if (T <= 48) {
     LBX_LAUNCH_PDL(stats_pool_bwd_bf16r_kernel<6>, grid, dim3(256), 0, (cudaStream_t)stream, (const bf16*)y_bf16,
                    rows_per_utt, T, C, pitch, clip_min, pooled, var_raw, gpool, (bf16*)dz_bf16, dbias, zero_gpool);
@@ -910,7 +1086,7 @@ int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, 
                     (reinterpret_cast<uintptr_t>(params_bf16) & 7) == 0,
                 "flat buffers must be 16-byte aligned");
   LBX_LAUNCH_PDL(adam_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev, lr_t_dev, lr, beta1, beta2);
-  LBX_LAUNCH_PDL(adam_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, (float4*)params,
+  LBX_LAUNCH_PDL(adam_kernel, dim3(grid_for(ceil_div(n / 4, LBX_ADAM_UNROLL), 256)), dim3(256), 0, (cudaStream_t)stream, (float4*)params,
                  (float4*)grads, (float4*)m, (float4*)v, n / 4, (const float*)lr_t_dev, beta1, beta2, eps, grad_scale,
                  (uint2*)params_bf16, zero_grads);
   return LBX_OK;

@@ -55,6 +55,51 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
   }
 }
 
+// vectorised variant (pitch % 8 == 0, 16-byte aligned planes): a thread converts 8 consecutive features of one frame
+// (index arithmetic once per 8 elements, one 16-byte store per plane)
+__global__ void __launch_bounds__(256) pack_rows_vec_kernel(const float* __restrict__ x, long long B, int T, int F,
+                                                           bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                                           int rows_per_utt, int row_off, int pitch, float drop_rate,
+                                                           unsigned long long seed, int x_vec) {
+  LBX_PDL_SYNC();
+  const int gpr = pitch >> 3;                       // 8-feature groups per row
+  const long long total = B * T * (long long)gpr;
+  const float keep_scale = drop_rate > 0.0f ? 1.0f / (1.0f - drop_rate) : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int gi = (int)(i % gpr);
+    const long long bt = i / gpr;
+    const int t = (int)(bt % T);
+    const long long b = bt / T;
+    const int c0 = gi * 8;
+    float v[8];
+    const float* src = x + bt * F + c0;
+    if (x_vec && c0 + 8 <= F) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = c0 + j < F ? __ldg(src + j) : 0.0f;
+    }
+    if (drop_rate > 0.0f) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < F) v[j] = hash_uniform(seed, (unsigned)b, (unsigned)(c0 + j)) < drop_rate ? 0.0f : v[j] * keep_scale;
+    }
+    const long long o = (b * rows_per_utt + row_off + t) * pitch + c0;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bf16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+      h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      const bf16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+      const bf16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+      l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo != nullptr) *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // GlobalMeanStddevPooling1D (xvector.py:25-35): two-pass population variance in fp32, clip 1e-10, sqrt
 // ------------------------------------------------------------------------------------------------------------
@@ -965,6 +1010,13 @@ int lbx_pack_rows_bf16(const float* x, long long B, int T, int F, void* hi, void
   LBX_CHECK_ARG(drop_rate >= 0.0f && drop_rate < 1.0f, "drop_rate must be in [0, 1)");
   if (B * T == 0) return LBX_OK;
   LBX_CHECK_ARG(x && hi, "NULL pointer argument");
+  if (pitch % 8 == 0 && ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0) {
+    const int x_vec = F % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    LBX_LAUNCH_PDL(pack_rows_vec_kernel, dim3(grid_for(B * T * (long long)(pitch / 8), 256)), dim3(256), 0,
+                   (cudaStream_t)stream, x, B, T, F, (bf16*)hi, (bf16*)lo, rows_per_utt, row_off, pitch, drop_rate, seed,
+                   x_vec);
+    return LBX_OK;
+  }
   LBX_LAUNCH_PDL(pack_rows_kernel, dim3(grid_for(B * T * (long long)pitch, 256)), dim3(256), 0, (cudaStream_t)stream, x, B,
                  T, F, (bf16*)hi, (bf16*)lo, rows_per_utt, row_off, pitch, drop_rate, seed);
   return LBX_OK;

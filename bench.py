@@ -213,6 +213,7 @@ class XVectorTrainWorkload:
         self.T = 1 + (self.N - 400) // 160
         self.rank, self.world = rank, world
         self.use_graph = os.environ.get("LBX_BENCH_GRAPH", "1") != "0"
+        self.pipelined = os.environ.get("LBX_BENCH_PIPELINE", "1") != "0"
         self.dist = None
 
     def config(self):
@@ -564,6 +565,8 @@ def run_reference(args, rank, world):
         return
     wl = WORKLOADS[args.workload](args, 0, 1)
     per = max(2.0, 60.0 / max(1, args.steps + args.warmup))
+    if os.environ.get("LBX_REF_BUDGET_S"):          # tests shorten the bounded CPU sample
+        per = float(os.environ["LBX_REF_BUDGET_S"])
     for _ in range(args.warmup):
         wl.cpu_sample(budget_s=min(per, 3.0))
     vals = []

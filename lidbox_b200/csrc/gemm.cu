@@ -8,7 +8,9 @@
 // the A operand is a plain 2-D TMA view whose row pitch (stride*C_in) is smaller than its width (k*C_in).
 //
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2-3 idle,
-// warps 4..11 = epilogue (TMEM -> registers -> bias/ReLU/mask -> global).  Operands are bf16 in 128B-swizzled
+// warps 4..11 = epilogue (TMEM -> registers -> bias/ReLU/mask -> global).  bf16 results take the lean epilogue
+// (prefetched tcgen05.ld, mask tiles by TMA bulk loads, one TMA bulk store per 32-column chunk); fp32 / atomic /
+// read-modify-write / residual-plane results take the general one.  Operands are bf16 in 128B-swizzled
 // shared memory (4 stages x 48 KB), accumulators fp32 in TMEM, double-buffered (2 x 256 columns) so the epilogue
 // of tile i overlaps the main loop of tile i+1.  "bf16x3" mode runs three accumulating passes
 // (A_hi B_hi + A_hi B_lo + A_lo B_hi) for fp32-grade results from bf16 tensor cores.
@@ -22,14 +24,8 @@ namespace lbx {
 #ifndef LBX_BIAS_SMEM
 #define LBX_BIAS_SMEM 1
 #endif
-#ifndef LBX_MASK_PREFETCH
-#define LBX_MASK_PREFETCH 1
-#endif
 #ifndef LBX_CTRL_WARPS
 #define LBX_CTRL_WARPS 4
-#endif
-#ifndef LBX_GEMM_SETMAXNREG
-#define LBX_GEMM_SETMAXNREG 0
 #endif
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
@@ -346,15 +342,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  // register budget: 384 threads start with 168 registers each; the control warpgroup gives most of its share to the
-  // two epilogue warpgroups (4*32*56 + 8*32*224 = 64512 <= 65536)
-#if LBX_GEMM_SETMAXNREG
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-  }
-#endif
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {

@@ -533,160 +533,6 @@ __global__ void __launch_bounds__(256) stats_pool_bwd_bf16v_kernel(const bf16* _
 }
 
 
-// Register-cached variants for short time axes (T <= 8 * MAXR): every thread issues all of its row loads up front
-// (memory-level parallelism instead of a dependent load->add loop) and the forward pass reads the activations once.
-template <int MAXR>
-__global__ void __launch_bounds__(256) stats_pool_fwd_bf16r_kernel(const bf16* __restrict__ y, int rows_per_utt, int T,
-                                                                  int C, int pitch, float clip_min,
-                                                                  float* __restrict__ out, float* __restrict__ var_raw,
-                                                                  bf16* __restrict__ out_hi) {
-  LBX_PDL_SYNC();
-  __shared__ float red[8][32][9];
-  const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
-  const int cv = blockIdx.x * 32 + lane;
-  const int c0 = cv * 8;
-  const long long b = blockIdx.y;
-  const bool active = c0 < pitch;
-  const uint4* base = reinterpret_cast<const uint4*>(y + b * rows_per_utt * (long long)pitch) + cv;
-  const int p8 = pitch >> 3;
-  uint4 raw[MAXR];
-#pragma unroll
-  for (int r = 0; r < MAXR; ++r) {
-    const int t = tl + 8 * r;
-    raw[r] = (active && t < T) ? __ldg(base + (long long)t * p8) : make_uint4(0u, 0u, 0u, 0u);
-  }
-  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-  for (int r = 0; r < MAXR; ++r) {
-    float f[8];
-    unpack_bf16x8(raw[r], f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] += f[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[tl][lane][i] = s[i];
-  __syncthreads();
-  float mean[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float a = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a += red[j][lane][i];
-    mean[i] = a / (float)T;
-  }
-  __syncthreads();
-  float q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-  for (int r = 0; r < MAXR; ++r) {
-    if (tl + 8 * r < T) {
-      float f[8];
-      unpack_bf16x8(raw[r], f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = f[i] - mean[i];
-        q[i] = fmaf(d, d, q[i]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[tl][lane][i] = q[i];
-  __syncthreads();
-  if (tl == 0 && active) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      if (c >= C) break;
-      float var = 0.0f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) var += red[j][lane][i];
-      var /= (float)T;
-      const float sd = sqrtf(fminf(fmaxf(var, clip_min), 3.402823466e+38f));
-      out[b * 2 * C + c] = mean[i];
-      out[b * 2 * C + C + c] = sd;
-      if (var_raw) var_raw[b * C + c] = var;
-      if (out_hi) {
-        out_hi[b * 2 * C + c] = __float2bfloat16_rn(mean[i]);
-        out_hi[b * 2 * C + C + c] = __float2bfloat16_rn(sd);
-      }
-    }
-  }
-}
-
-template <int MAXR>
-__global__ void __launch_bounds__(256) stats_pool_bwd_bf16r_kernel(const bf16* __restrict__ y, int rows_per_utt, int T,
-                                                                  int C, int pitch, float clip_min,
-                                                                  const float* __restrict__ pooled,
-                                                                  const float* __restrict__ var_raw,
-                                                                  float* __restrict__ gpool, bf16* __restrict__ dz,
-                                                                  float* __restrict__ dbias, int zero_gpool) {
-  LBX_PDL_SYNC();
-  __shared__ float red[8][32][9];
-  const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
-  const int cv = blockIdx.x * 32 + lane;
-  const int c0 = cv * 8;
-  const long long b = blockIdx.y;
-  const bool active = c0 < pitch;
-  const int p8 = pitch >> 3;
-  const uint4* src = reinterpret_cast<const uint4*>(y + b * rows_per_utt * (long long)pitch) + cv;
-  uint4* dst = reinterpret_cast<uint4*>(dz + b * rows_per_utt * (long long)pitch) + cv;
-  uint4 raw[MAXR];
-#pragma unroll
-  for (int r = 0; r < MAXR; ++r) {
-    const int t = tl + 8 * r;
-    raw[r] = (active && t < T) ? __ldg(src + (long long)t * p8) : make_uint4(0u, 0u, 0u, 0u);
-  }
-  float mean[8], gm[8], gs[8], acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    acc[i] = 0.0f;
-    if (active && c < C) {
-      mean[i] = pooled[b * 2 * C + c];
-      const float sd = pooled[b * 2 * C + C + c];
-      gm[i] = gpool[b * 2 * C + c] / (float)T;
-      gs[i] = var_raw[b * C + c] > clip_min ? gpool[b * 2 * C + C + c] / ((float)T * sd) : 0.0f;
-    } else {
-      mean[i] = gm[i] = gs[i] = 0.0f;
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < MAXR; ++r) {
-    const int t = tl + 8 * r;
-    if (active && t < T) {
-      float f[8], g[8];
-      unpack_bf16x8(raw[r], f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        g[i] = f[i] > 0.0f ? fmaf(gs[i], f[i] - mean[i], gm[i]) : 0.0f;
-        acc[i] += g[i];
-      }
-      dst[(long long)t * p8] = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
-    }
-  }
-  if (dbias != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) red[tl][lane][i] = acc[i];
-  }
-  __syncthreads();
-  if (tl == 0 && active) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      if (c >= C) break;
-      if (dbias != nullptr) {
-        float a = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a += red[j][lane][i];
-        atomicAdd(dbias + c, a);
-      }
-      if (zero_gpool) {
-        gpool[b * 2 * C + c] = 0.0f;
-        gpool[b * 2 * C + C + c] = 0.0f;
-      }
-    }
-  }
-}
-
 // Column-owner variants for short time axes (T <= MAXT): a thread owns TWO channels of one utterance and keeps all T
 // values in registers (one 4-byte load per row, a warp reads 128 contiguous bytes per row, every load is issued before
 // the first use).  No cross-thread reduction is needed for the statistics; the backward kernel reduces the bias
@@ -1036,10 +882,7 @@ int lbx_stats_pool_fwd(const void* y, int y_dtype, long long B, int rows_per_utt
                                                                          (bf16*)out_lo);
   else if (y_dtype == LBX_BF16 && out_lo == nullptr && pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
   {
-#ifndef LBX_POOL_COLUMN_OWNER
-#define LBX_POOL_COLUMN_OWNER 1
-#endif
-    if (LBX_POOL_COLUMN_OWNER && T <= 56) {
+    if (T <= 56) {
       const dim3 g2((unsigned)ceil_div((C + 1) / 2, 128), (unsigned)B);
       if (T <= 40)
         LBX_LAUNCH_PDL(stats_pool_fwd_bf16c_kernel<40>, g2, dim3(128), 0, (cudaStream_t)stream, (const bf16*)y,
@@ -1047,12 +890,6 @@ int lbx_stats_pool_fwd(const void* y, int y_dtype, long long B, int rows_per_utt
       else
         LBX_LAUNCH_PDL(stats_pool_fwd_bf16c_kernel<56>, g2, dim3(128), 0, (cudaStream_t)stream, (const bf16*)y,
                        rows_per_utt, T, C, pitch, clip_min, out, var_raw, (bf16*)out_hi);
-      return LBX_OK;
-    }
-    if (T <= 48) {
-      LBX_LAUNCH_PDL(stats_pool_fwd_bf16r_kernel<6>, dim3((unsigned)ceil_div(pitch / 8, 32), (unsigned)B), dim3(256), 0,
-                     (cudaStream_t)stream, (const bf16*)y, rows_per_utt, T, C, pitch, clip_min, out, var_raw,
-                     (bf16*)out_hi);
       return LBX_OK;
     }
     LBX_LAUNCH_PDL(stats_pool_fwd_bf16v_kernel, dim3((unsigned)ceil_div(pitch / 8, 32), (unsigned)B), dim3(256), 0,
@@ -1080,7 +917,7 @@ int lbx_stats_pool_bwd(const void* y_bf16, long long B, int rows_per_utt, int T,
   LBX_CHECK_ARG(((reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(dz_bf16)) & 15) == 0,
                 "activation buffers must be 16-byte aligned");
   dim3 grid((unsigned)ceil_div(pitch / 8, 32), (unsigned)B);
-  if (LBX_POOL_COLUMN_OWNER && T <= 56) {
+  if (T <= 56) {
     const dim3 g2((unsigned)ceil_div((C + 1) / 2, 64), (unsigned)ceil_div(B, 4));
     if (T <= 40)
       LBX_LAUNCH_PDL(stats_pool_bwd_bf16c_kernel<40>, g2, dim3(256), 0, (cudaStream_t)stream, (const bf16*)y_bf16, B,
@@ -1088,11 +925,6 @@ int lbx_stats_pool_bwd(const void* y_bf16, long long B, int rows_per_utt, int T,
     else
       LBX_LAUNCH_PDL(stats_pool_bwd_bf16c_kernel<56>, g2, dim3(256), 0, (cudaStream_t)stream, (const bf16*)y_bf16, B,
                      rows_per_utt, T, C, pitch, clip_min, pooled, var_raw, gpool, (bf16*)dz_bf16, dbias, zero_gpool);
-    return LBX_OK;
-  }
-  if (T <= 48) {
-    LBX_LAUNCH_PDL(stats_pool_bwd_bf16r_kernel<6>, grid, dim3(256), 0, (cudaStream_t)stream, (const bf16*)y_bf16,
-                   rows_per_utt, T, C, pitch, clip_min, pooled, var_raw, gpool, (bf16*)dz_bf16, dbias, zero_gpool);
     return LBX_OK;
   }
   LBX_LAUNCH_PDL(stats_pool_bwd_bf16v_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const bf16*)y_bf16, rows_per_utt, T,

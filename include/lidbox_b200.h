@@ -252,6 +252,15 @@ int lbx_logsoftmax_xent(const float* logits, const int* labels, long long B, int
                         void* dlogits_bf16, int dl_pitch, float grad_scale, float* dbias /* optional: += column sums of
                         the gradient = bias gradient of the output layer */, void* stream);
 
+/* Fused training head for few classes (N <= 8): Dense(K -> N) (lidbox/models/xvector.py:64) + log_softmax (:65) +
+ * sparse cross-entropy (keras_utils.py:141-142) and the complete backward of that layer in one launch.
+ * h_bf16 [B, K] (pitch ldh): output of the layer below; w_bf16 [K, ldw]: bf16 copy of the Keras kernel; bias [N] f32.
+ * Outputs: loss [B]; logits_out [B, N] (optional); dh_bf16 [B, K] = d loss / d h (x grad_scale), zeroed where h <= 0
+ * when relu_mask; dW [K, ldw], dbias [N], dbias_below [K] (optional) are ACCUMULATED (+=). */
+int lbx_dense_xent_head(const void* h_bf16, const void* w_bf16, const float* bias, const int* labels, long long B, int K,
+                        int N, int ldh, int ldw, float grad_scale, int relu_mask, float* logits_out, float* loss,
+                        void* dh_bf16, float* dW, float* dbias, float* dbias_below, void* stream);
+
 /* lidbox/losses.py:12-52 SparseAngularProximity(N, D, delta_weight): theta = acos(z[:, :N]),
  * loss[b] = sum_{l != y_b} sigmoid(delta_weight * (theta[b,y_b] - theta[b,l])).  normalize = 1 first maps
  * z = h / |h| (the L2-normalising head of the AP training config).  Optional outputs: z_out [B,D], theta_out [B,N],

@@ -58,6 +58,8 @@ SIGNATURES = {
     "lbx_cavg_result_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, c_float, c_float, _P, _P, _P]),
     "lbx_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), _P]),
     "lbx_set_pdl": (c_int, [c_int]),
+    "lbx_dense_xent_head": (c_int, [_P, _P, _P, _P, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P,
+                                    _P, _P]),
     "lbx_set_gemm_pair": (c_int, [c_int]),
     "lbx_set_gemm_fast_epilogue": (c_int, [c_int]),
     "lbx_pack_rows_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, _P]),

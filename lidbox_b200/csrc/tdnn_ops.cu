@@ -213,6 +213,146 @@ __global__ void __launch_bounds__(128) logsoftmax_xent_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Fused output layer of the training step for few classes (N <= 8): Dense(K -> N) (xvector.py:64) + log_softmax (:65) +
+// sparse cross-entropy + the whole backward of that layer (data gradient masked by the ReLU of the layer below, weight
+// and bias gradients, bias gradient of the layer below) in ONE launch instead of GEMM + loss + 2 GEMMs.  One warp per
+// sample; weight-gradient partial sums of the 8 samples of a block are combined in shared memory before the atomics.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int HEAD_NMAX = 8, HEAD_SPB = 8;
+
+// KI = ceil(K / 32) rounded up to 16 or 32: a lane keeps its KI activations of the sample in registers (all loads in
+// flight at once); the weights are staged once per block in shared memory as floats.
+template <int KI>
+__global__ void __launch_bounds__(32 * HEAD_SPB) dense_xent_head_kernel(
+    const bf16* __restrict__ H, const bf16* __restrict__ W, const float* __restrict__ bias, const int* __restrict__ y,
+    long long B, int K, int N, int ldh, int ldw, float grad_scale, int relu_mask, float* __restrict__ logits_out,
+    float* __restrict__ loss, bf16* __restrict__ dH, float* __restrict__ dW, float* __restrict__ dbias,
+    float* __restrict__ dbias_below) {
+  LBX_PDL_SYNC();
+  extern __shared__ float s_head[];
+  float* s_w = s_head;                                   // [K][N] weights
+  float* s_dbb = s_w + (size_t)K * N;                    // [K] bias gradient of the layer below (this block's samples)
+  float* s_dl = s_dbb + K;                               // [SPB][NMAX] gradient w.r.t. the logits
+  bf16* s_h = reinterpret_cast<bf16*>(s_dl + HEAD_SPB * HEAD_NMAX);   // [SPB][K] activations
+#pragma unroll 8
+  for (int i = threadIdx.x; i < K * N; i += blockDim.x) s_w[i] = __bfloat162float(W[(long long)(i / N) * ldw + (i % N)]);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) s_dbb[i] = 0.0f;
+  if (threadIdx.x < HEAD_SPB * HEAD_NMAX) s_dl[threadIdx.x] = 0.0f;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const long long b = (long long)blockIdx.x * HEAD_SPB + wi;
+  float hv[KI];
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    const int h = i * 32 + lane;
+    const bf16 raw = (b < B && h < K) ? H[b * ldh + h] : __float2bfloat16_rn(0.0f);
+    hv[i] = __bfloat162float(raw);
+    if (h < K) s_h[wi * K + h] = raw;
+  }
+  __syncthreads();
+  if (b < B) {
+    float acc[HEAD_NMAX];
+#pragma unroll
+    for (int j = 0; j < HEAD_NMAX; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int h = i * 32 + lane;
+      if (h < K) {
+#pragma unroll
+        for (int j = 0; j < HEAD_NMAX; ++j)
+          if (j < N) acc[j] = fmaf(hv[i], s_w[h * N + j], acc[j]);
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < HEAD_NMAX; ++j) {
+      if (j < N) {
+        acc[j] = warp_sum(acc[j]) + bias[j];
+        mx = fmaxf(mx, acc[j]);
+      }
+    }
+    float se = 0.0f;
+#pragma unroll
+    for (int j = 0; j < HEAD_NMAX; ++j)
+      if (j < N) se += expf(acc[j] - mx);
+    const float lse = mx + logf(se);
+    const int label = y[b];
+    float dl[HEAD_NMAX];
+#pragma unroll
+    for (int j = 0; j < HEAD_NMAX; ++j) {
+      dl[j] = 0.0f;
+      if (j < N) {
+        const float lp = acc[j] - lse;
+        // the gradient w.r.t. the logits is stored / consumed in bf16, like every other data gradient of the path
+        dl[j] = __bfloat162float(__float2bfloat16_rn((expf(lp) - (j == label ? 1.0f : 0.0f)) * grad_scale));
+        if (lane == 0) {
+          if (logits_out) logits_out[b * N + j] = acc[j];
+          if (j == label) loss[b] = -lp;
+          s_dl[wi * HEAD_NMAX + j] = dl[j];
+        }
+      }
+    }
+    bf16* drow = dH + b * ldh;
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int h = i * 32 + lane;
+      if (h < K) {
+        float g = 0.0f;
+#pragma unroll
+        for (int j = 0; j < HEAD_NMAX; ++j)
+          if (j < N) g = fmaf(dl[j], s_w[h * N + j], g);
+        if (relu_mask && !(hv[i] > 0.0f)) g = 0.0f;
+        const bf16 gq = __float2bfloat16_rn(g);
+        drow[h] = gq;
+        atomicAdd(s_dbb + h, __bfloat162float(gq));
+      }
+    }
+  }
+  __syncthreads();
+  // weight gradient of this block's samples: every thread owns (h, j) pairs and sums over the samples in shared memory.
+  // All blocks add into the same few cache lines, so the adds are issued as 16-byte vector reductions when the
+  // layout allows (N == 4: one row of dW per instruction)
+  if (N == 4 && (ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0) {
+    for (int h = threadIdx.x; h < K; h += blockDim.x) {
+      float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int sidx = 0; sidx < HEAD_SPB; ++sidx) {
+        const float hs = __bfloat162float(s_h[sidx * K + h]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaf(hs, s_dl[sidx * HEAD_NMAX + j], v[j]);
+      }
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dW + (long long)h * ldw), "f"(v[0]), "f"(v[1]),
+                   "f"(v[2]), "f"(v[3])
+                   : "memory");
+    }
+  } else {
+    for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
+      const int h = i / N, j = i - h * N;
+      float v = 0.0f;
+#pragma unroll
+      for (int sidx = 0; sidx < HEAD_SPB; ++sidx)
+        v = fmaf(__bfloat162float(s_h[sidx * K + h]), s_dl[sidx * HEAD_NMAX + j], v);
+      atomicAdd(dW + (long long)h * ldw + j, v);
+    }
+  }
+  if (dbias_below != nullptr) {
+    if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(dbias_below) & 15) == 0) {
+      for (int h = 4 * threadIdx.x; h < K; h += 4 * blockDim.x)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbias_below + h), "f"(s_dbb[h]),
+                     "f"(s_dbb[h + 1]), "f"(s_dbb[h + 2]), "f"(s_dbb[h + 3])
+                     : "memory");
+    } else {
+      for (int h = threadIdx.x; h < K; h += blockDim.x) atomicAdd(dbias_below + h, s_dbb[h]);
+    }
+  }
+  if (threadIdx.x < N) {
+    float v = 0.0f;
+#pragma unroll
+    for (int sidx = 0; sidx < HEAD_SPB; ++sidx) v += s_dl[sidx * HEAD_NMAX + threadIdx.x];
+    atomicAdd(dbias + threadIdx.x, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // SparseAngularProximity (losses.py:12-52): theta = acos(z[:, :N]); L_b = sum_{l != y} sigmoid(w (theta_y - theta_l))
 // optional L2-normalising head in front (z = h / |h|), as used by the AP training config
 // ------------------------------------------------------------------------------------------------------------
@@ -941,6 +1081,27 @@ int lbx_logsoftmax_xent(const float* logits, const int* labels, long long B, int
   LBX_CHECK_ARG(!dlogits_bf16 || dl_pitch >= n, "dl_pitch too small");
   LBX_LAUNCH_PDL(logsoftmax_xent_kernel, dim3((unsigned)ceil_div(B, 4)), dim3(128), 0, (cudaStream_t)stream, logits, labels,
                  B, n, logp, loss, (bf16*)dlogits_bf16, dl_pitch, grad_scale, dbias);
+  return LBX_OK;
+}
+
+int lbx_dense_xent_head(const void* h_bf16, const void* w_bf16, const float* bias, const int* labels, long long B, int K,
+                        int N, int ldh, int ldw, float grad_scale, int relu_mask, float* logits_out, float* loss,
+                        void* dh_bf16, float* dW, float* dbias, float* dbias_below, void* stream) {
+  LBX_CHECK_ARG(B >= 0 && K >= 1 && N >= 1 && N <= HEAD_NMAX && ldh >= K && ldw >= N, "bad shape (N <= %d)", HEAD_NMAX);
+  LBX_CHECK_ARG(K <= 1024, "K must be <= 1024 for the fused head");
+  const size_t smem = (size_t)(K * N + K + HEAD_SPB * HEAD_NMAX) * sizeof(float) + (size_t)HEAD_SPB * K * sizeof(bf16);
+  LBX_CHECK_ARG(smem <= 48 * 1024, "K * N too large for the fused head");
+  if (B == 0) return LBX_OK;
+  LBX_CHECK_ARG(h_bf16 && w_bf16 && bias && labels && loss && dh_bf16 && dW && dbias, "NULL pointer argument");
+  const dim3 grid((unsigned)ceil_div(B, HEAD_SPB)), block(32 * HEAD_SPB);
+  if (K <= 512)
+    LBX_LAUNCH_PDL(dense_xent_head_kernel<16>, grid, block, smem, (cudaStream_t)stream, (const bf16*)h_bf16,
+                   (const bf16*)w_bf16, bias, labels, B, K, N, ldh, ldw, grad_scale, relu_mask, logits_out, loss,
+                   (bf16*)dh_bf16, dW, dbias, dbias_below);
+  else
+    LBX_LAUNCH_PDL(dense_xent_head_kernel<32>, grid, block, smem, (cudaStream_t)stream, (const bf16*)h_bf16,
+                   (const bf16*)w_bf16, bias, labels, B, K, N, ldh, ldw, grad_scale, relu_mask, logits_out, loss,
+                   (bf16*)dh_bf16, dW, dbias, dbias_below);
   return LBX_OK;
 }
 

@@ -277,7 +277,7 @@ class XVector:
             raise ValueError("empty time axis")
         return x.to(self.device, torch.float32).contiguous()
 
-    def _forward(self, x, bufs, training, upto_embedding=False):
+    def _forward(self, x, bufs, training, upto_embedding=False, skip_outputs=False):
         lib, st = _lib.lib(), _lib.stream_ptr(self.device)
         geo = bufs["geo"]
         B, T, _ = x.shape
@@ -312,6 +312,8 @@ class XVector:
                 return bufs["emb"]
             self._dense(bufs, a, a_lo, B, ly, relu=ly["relu"], out_hi=bufs["H"][i], out_lo=bufs["H_lo"][i])
             a, a_lo = bufs["H"][i], bufs["H_lo"][i]
+        if skip_outputs:          # the fused training head computes the output layer together with the loss
+            return None
         ly = self.layers[-1]
         self._dense(bufs, a, a_lo, B, ly, relu=False, out_f32=bufs["logits"])
         return bufs["logits"]
@@ -372,15 +374,30 @@ class XVector:
         geo = bufs["geo"]
         lib, st = _lib.lib(), _lib.stream_ptr(self.device)
         n = len(self.frames)
-        logits = self._forward(x, bufs, True)
+        out_ly = self.layers[-1]
+        n_seg = len(self.segments)
+        # few classes + cross-entropy: output layer, loss and the layer's whole backward can run as ONE launch
+        # (lbx_dense_xent_head) instead of GEMM + loss + 2 GEMMs.  Opt-in (LBX_FUSED_HEAD=1): measured on B200 it removes
+        # three launches but no time (0.4396 vs 0.4391 ms/step) — the dense head is bound by the serial latency of its
+        # kernels, not by their work.
+        fused_head = (loss == "xent" and self.num_outputs <= 8 and n_seg >= 1 and out_ly["K"] <= 1024 and
+                      out_ly["K"] * (4 * self.num_outputs + 20) + 256 <= 49152 and
+                      os.environ.get("LBX_FUSED_HEAD", "0") == "1")
+        logits = self._forward(x, bufs, True, skip_outputs=fused_head)
         scale = 1.0 / float(global_batch or B)
         npad = bufs["dlogits"].shape[1]
         if not self._grads_clean:
             self.grads.zero_()
         self._grads_clean = False
         g = self.grads
-        out_ly = self.layers[-1]
-        if loss == "xent":
+        if fused_head:
+            below = self.layers[n + n_seg - 1]
+            _lib.check(lib.lbx_dense_xent_head(
+                _lib.ptr(bufs["H"][-1]), ops._addr(self.w16, out_ly["w_off"]), ops._addr(self.params, out_ly["b_off"]),
+                _lib.ptr(y), B, out_ly["K"], self.num_outputs, out_ly["K"], out_ly["ldw"], scale,
+                1 if below["relu"] else 0, _lib.ptr(bufs["logits"]), _lib.ptr(bufs["loss"]), _lib.ptr(bufs["dH"][-1]),
+                ops._addr(g, out_ly["w_off"]), ops._addr(g, out_ly["b_off"]), ops._addr(g, below["b_off"]), st))
+        elif loss == "xent":
             _lib.check(lib.lbx_logsoftmax_xent(_lib.ptr(logits), _lib.ptr(y), B, self.num_outputs, None,
                                                _lib.ptr(bufs["loss"]), _lib.ptr(bufs["dlogits"]), npad, scale,
                                                ops._addr(g, out_ly["b_off"]), st))
@@ -437,7 +454,11 @@ class XVector:
         # ---- dense head (bias gradients come fused out of the kernels that produce each dz) ----
         dz, dz_cols, dz_pitch = bufs["dlogits"], self.num_outputs, npad
         acts = [bufs["pooled_hi"]] + bufs["H"]
-        for i in range(len(self.segments), -1, -1):
+        first = n_seg
+        if fused_head:             # the output layer is done: continue from the gradient w.r.t. the last segment layer
+            first = n_seg - 1
+            dz, dz_cols, dz_pitch = bufs["dH"][-1], out_ly["K"], out_ly["K"]
+        for i in range(first, -1, -1):
             ly = self.layers[n + i]
             wgrad(acts[i], B, ly["K"], ly["K"], dz, dz_cols, dz_pitch, ly)
             if i > 0:      # d hidden = (dz . W^T) masked by the ReLU of the layer below (+ its bias gradient), one launch

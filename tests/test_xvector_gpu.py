@@ -142,6 +142,29 @@ def test_training_gradients_bf16_xent(xv, B, T, n_out):
     _check_grads(m, g_ref, 0.98, None)
 
 
+def test_fused_xent_head_matches_unfused(xv, monkeypatch):
+    # lbx_dense_xent_head (opt-in): output layer + log-softmax + cross-entropy + the layer's backward in one launch
+    rng = np.random.default_rng(14)
+    B, T, n_out = 19, 37, 4
+    x = rng.standard_normal((B, T, 40)).astype(np.float32)
+    y = rng.integers(0, n_out, B)
+    params = O.xvector_init(40, n_out, seed=3, bias_scale=0.05)
+    results = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LBX_FUSED_HEAD", flag)
+        m = xv.create((T, 40), n_out, precision="bf16")
+        m.set_weights(params)
+        per = m.loss_and_grads(x, y).cpu().numpy().copy()
+        results.append((per, m.grads.cpu().numpy().copy(), m))
+    (l0, g0, _), (l1, g1, m1) = results
+    np.testing.assert_allclose(l1, l0, rtol=1e-5, atol=1e-6)
+    cos = (g0 * g1).sum() / (np.linalg.norm(g0) * np.linalg.norm(g1))
+    assert cos > 0.9999 and np.abs(g0 - g1).max() < 2e-2 * np.abs(g0).max()
+    loss_emu, g_emu = _oracle_grads(params, x, y, emulate_bf16=True)
+    assert abs(l1.mean() - loss_emu) < 1e-3 * max(1.0, abs(loss_emu))
+    _check_grads(m1, g_emu, 0.999, 0.2)
+
+
 def test_training_gradients_bf16_ap(xv):
     # BASELINE config 4 wiring at small size: x-vector -> 64-d L2-normalised vector -> SparseAngularProximity(50, 64)
     rng = np.random.default_rng(5)

@@ -70,6 +70,34 @@ def main():
     assert np.allclose(l.item(), O.ap_loss(yz, z, N, 1.5))
     np.savez_compressed(os.path.join(OUT, "ap_loss.npz"), z=z, y=yz, N=N, delta_weight=1.5,
                         per_sample=O.ap_loss_per_sample(yz, z, N, 1.5), loss=l.item(), grad=zt.grad.numpy())
+    # 5. extended x-vector (xvector_extended.py:22-43): seeded tiny problem, fp64 oracle outputs
+    ext = dict(frame_layers=O.XVECTOR_EXTENDED_FRAME_LAYERS, output_name="output")
+    rng5 = np.random.default_rng(21)
+    xe = rng5.standard_normal((3, 50, 24)).astype(np.float32)
+    pe = {k: v.astype(np.float64) for k, v in O.xvector_init(24, 5, seed=12, bias_scale=0.05, **ext).items()}
+    np.savez_compressed(os.path.join(OUT, "xvector_extended_small.npz"), x=xe,
+                        logp=O.xvector_forward(pe, xe.astype(np.float64), **ext),
+                        emb=O.xvector_forward(pe, xe.astype(np.float64), embedding=True, **ext))
+
+    # 6. C_avg: the self-test inputs of lidbox/metrics.py:128-150 and a seeded 200 x 6 problem
+    onehot = np.array([[1, 0, 0], [0, 1, 0], [0, 1, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1], [0, 1, 0], [0, 0, 1]], np.float32)
+    prob = np.array([[.1, .2, .9], [.9, .2, .0], [.1, .9, .0], [.2, .8, .5], [.6, .3, .1], [.1, .0, .7], [.1, .0, .7],
+                     [.9, .1, .0]], np.float32)
+    with np.errstate(divide="ignore"):
+        pred = np.log(prob)
+    thr = np.log(np.array([0.05, 0.4, 0.6, 0.95], np.float32))
+    c = O.AverageDetectionCost(3, thr)
+    c.update_state(onehot, pred)
+    rng6 = np.random.default_rng(22)
+    y6 = rng6.integers(0, 6, 200)
+    s6 = rng6.standard_normal((200, 6)).astype(np.float32)
+    s6[np.arange(200), y6] += 1.5
+    thr6 = np.linspace(s6.min(), s6.max(), 25).astype(np.float32)
+    c6 = O.SparseAverageDetectionCost(6, thr6, C_miss=1.0, C_fa=2.0, P_tar=0.3)
+    c6.update_state(y6, s6)
+    np.savez_compressed(os.path.join(OUT, "cavg.npz"), onehot=onehot, pred=pred, thr=thr, cavg=c.result_per_threshold(),
+                        tp=c.tp, fn=c.fn, fp_pairs=c.fp_pairs, tn_pairs=c.tn_pairs,
+                        y6=y6, s6=s6, thr6=thr6, cavg6=c6.result_per_threshold(), fp_pairs6=c6.fp_pairs)
     print("golden written to", OUT)
 
 

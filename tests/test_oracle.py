@@ -430,3 +430,21 @@ def test_chunk_host_logic_matches_oracle():
     assert steps.chunk_ids("utt", 1, max_num_chunks_per_signal=100) == ["utt-01"]
     with pytest.raises(ValueError):
         steps.chunk_geometry(16000, 0, 10)
+
+
+def test_new_golden_fixtures_match_oracle():
+    # tests/golden/xvector_extended_small.npz and cavg.npz (make_golden.py sections 5-6) pin the restatement
+    g = np.load(os.path.join(GOLDEN, "xvector_extended_small.npz"))
+    ext = dict(frame_layers=O.XVECTOR_EXTENDED_FRAME_LAYERS, output_name="output")
+    pe = {k: v.astype(np.float64) for k, v in O.xvector_init(24, 5, seed=12, bias_scale=0.05, **ext).items()}
+    np.testing.assert_allclose(O.xvector_forward(pe, g["x"].astype(np.float64), **ext), g["logp"], rtol=1e-10, atol=1e-12)
+    c = np.load(os.path.join(GOLDEN, "cavg.npz"))
+    m = O.AverageDetectionCost(3, c["thr"])
+    m.update_state(c["onehot"], c["pred"])
+    np.testing.assert_array_equal(m.fp_pairs, c["fp_pairs"])
+    np.testing.assert_allclose(m.result_per_threshold(), c["cavg"], rtol=1e-7)
+    m6 = O.SparseAverageDetectionCost(6, c["thr6"], C_miss=1.0, C_fa=2.0, P_tar=0.3)
+    m6.update_state(c["y6"], c["s6"])
+    np.testing.assert_allclose(m6.result_per_threshold(), c["cavg6"], rtol=1e-7)
+    want = [O.cavg_by_definition(c["y6"], c["s6"], t, 6, 1.0, 2.0, 0.3) for t in c["thr6"]]
+    np.testing.assert_allclose(c["cavg6"], want, rtol=1e-5)

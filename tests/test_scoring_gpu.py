@@ -161,3 +161,18 @@ def test_cavg_reference_selftest_inputs_and_edge_cases(built_lib):
     ref = O.SparseAverageDetectionCost(4, np.linspace(sc.min(), sc.max(), 100))
     ref.update_state(yy, sc)
     assert abs(util.average_detection_cost(yy, sc, 4) - float(ref.result())) < 1e-6
+
+
+def test_cavg_golden(built_lib):
+    import os
+    from lidbox_b200 import metrics
+    c = np.load(os.path.join(os.path.dirname(__file__), "golden", "cavg.npz"))
+    m = metrics.AverageDetectionCost(3, c["thr"])
+    m.update_state(c["onehot"], c["pred"])
+    for name in ("tp", "fn", "fp_pairs", "tn_pairs"):
+        np.testing.assert_array_equal(getattr(m, name).cpu().numpy(), c[name])
+    np.testing.assert_allclose(m.result_per_threshold().cpu().numpy()[:4], c["cavg"], rtol=2e-6, atol=1e-7)
+    m6 = metrics.SparseAverageDetectionCost(6, c["thr6"], C_miss=1.0, C_fa=2.0, P_tar=0.3)
+    m6.update_state(c["y6"], c["s6"])
+    np.testing.assert_array_equal(m6.fp_pairs.cpu().numpy(), c["fp_pairs6"])
+    np.testing.assert_allclose(m6.result_per_threshold().cpu().numpy()[:25], c["cavg6"], rtol=2e-6, atol=1e-7)

@@ -113,3 +113,14 @@ def test_stride_larger_than_kernel_layer_alone(xve):
     l.backward()
     assert abs(per.mean() - float(l.detach())) < 1e-3
     _check_grads(m, {k: v.grad.numpy() for k, v in tp.items()}, 0.9999, 0.05)
+
+
+def test_golden_small_fp32(xve):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "xvector_extended_small.npz"))
+    m = xve.create((None, 24), 5)
+    m.set_weights(O.xvector_init(24, 5, seed=12, bias_scale=0.05, **EXT))
+    logp = m(g["x"]).cpu().numpy()
+    np.testing.assert_allclose(logp, g["logp"], rtol=1e-4, atol=1e-4)
+    emb = xve.as_embedding_extractor(m)(g["x"]).cpu().numpy()
+    assert _nw(emb, g["emb"]) < 1e-4

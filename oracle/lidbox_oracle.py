@@ -20,8 +20,23 @@ tests/test_oracle.py:
   * power_to_db          max <= 0, no NaN   (tests/test_features_audio.py:115-123)
   * x-vector output      shape / no NaN for B,T,F >= 1 (tests/test_models.py:104-107)
 For spectrogram / mel / log-mel VALUES, x-vector outputs, gradients and the AP
-loss the reference holds no golden vectors: those values are **parity unpinned**
-(restated from the reference source + published TF-2.3 semantics).
+loss the reference holds no golden vectors, and no number produced by TensorFlow
+exists in this repository: against the reference itself those values stay
+**parity unpinned**.  What closes most of the gap (round 2):
+  * tests/test_third_party.py checks every restated TF semantic against
+    independent third-party code in the image — scipy.signal.stft / ShortTimeFFT and
+    transformers.audio_utils (framing, Hann, END zero-padding, rFFT), transformers'
+    HTK mel filter bank (formula family; the reference's two off-by-one divisors are
+    literal in mel_ops.py:16,40-41,49-55), scipy.fft.dct (MFCC), torch conv1d /
+    linear / log_softmax / var (TDNN), torch autograd + finite differences (AP loss),
+    torch.optim.Adam (optimizer algebra).  TF's odd-length "periodic" Hann
+    (n = L + periodic*even - 1 -> symmetric window) follows the in-tree copy of the
+    TF formula in blackman_window (lidbox/features/audio.py:206-211).
+  * tests/test_vs_tf.py compares directly with the real reference and runs wherever
+    TensorFlow + /root/reference exist (skipped here).
+Still restated from memory of TF/Keras 2.3 with no executable confirmation: Keras
+Conv1D padding="causal" = left pad of k-1 and stride phase t*s + j; Keras Adam's
+epsilon placement (outside the bias-corrected sqrt); glorot-uniform limits.
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference).

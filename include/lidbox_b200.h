@@ -35,6 +35,7 @@ extern "C" {
 /* dtype tags used by the TDNN entry points */
 #define LBX_F32 0
 #define LBX_BF16 1
+#define LBX_I16 2            /* 16-bit PCM samples (feature entry points only) */
 
 const char* lbx_last_error(void);
 int lbx_version(void);
@@ -90,6 +91,26 @@ int lbx_logmel_f32(const float* sig, long long B, long long N, int frame_length,
 int lbx_logmel_i16(const short* pcm, long long B, long long N, int frame_length, int frame_step, int fft_length,
                    float power, int n_mel, const int* band_start, const int* band_len, const int* band_off,
                    const float* band_w, int n_packed, int log_mode, float eps, float* out, void* stream);
+
+/* The same fused chain with every option in one descriptor — the entry point the input pipeline binds
+ * (lidbox/data/tf_utils.py:172-178 followed directly by the first Conv1D of lidbox/models/xvector.py:53):
+ *   sig_dtype LBX_F32 | LBX_I16 (PCM decoded as x / 32768, audio.py:17-33);
+ *   out_dtype LBX_F32 | LBX_BF16; frame t of utterance b is written at out + b*out_utt_pitch + t*out_row_pitch
+ *   (elements; 0 = dense [B,T,n_mel]), so bf16 rows can land straight in the zero-left-padded activation buffer of
+ *   the first frame layer (no fp32 [B,T,n_mel] round trip, no packing pass); out_lo (optional) receives the bf16
+ *   residual x - bf16(x) for the bf16x3 forward mode.  Columns n_mel..out_row_pitch-1 are not written.
+ * workspace: as for lbx_logmel_f32 (only when the fused 512-point path does not apply; then f32 dense output only). */
+typedef struct lbx_logmel_t {
+  const void* sig; int sig_dtype;
+  long long B; long long N;
+  int frame_length; int frame_step; int fft_length; float power;
+  int n_mel; const int* band_start; const int* band_len; const int* band_off; const float* band_w; int n_packed;
+  int log_mode; float eps;
+  void* out; void* out_lo; int out_dtype;
+  long long out_utt_pitch; int out_row_pitch;
+  void* workspace; size_t workspace_bytes;
+} lbx_logmel_t;
+int lbx_logmel_ex(const lbx_logmel_t* d, void* stream);
 
 /* lidbox/features/audio.py:167-174  power_to_db(): 20*(log10(max(amin,S)) - log10(max(amin,max_all S))),
  * floored at max_all(db) - top_db.  workspace: >= 16 bytes of device memory. */
@@ -229,9 +250,14 @@ int lbx_set_gemm_fast_epilogue(int enabled);
 /* features [B,T,F] f32 -> bf16 activation rows of the first frame layer: element (b,t,c) goes to row
  * b*rows_per_utt + row_off + t, column c of a [*, pitch] buffer (hi, and lo = residual when lo != NULL);
  * columns F..pitch-1 are written as zero.  drop_rate > 0 applies SpatialDropout1D (xvector.py:50-51): whole
- * channels of a sample are zeroed with probability drop_rate, the rest scaled by 1/(1-drop_rate). */
+ * channels of a sample are zeroed with probability drop_rate, the rest scaled by 1/(1-drop_rate).
+ * The mask of a call is a hash of (seed + 7919 * *seed_counter_dev, sample, channel); seed_counter_dev (optional) is a
+ * device-side call counter advanced by lbx_counter_tick(), so that replays of a captured CUDA graph draw a new mask. */
 int lbx_pack_rows_bf16(const float* x, long long B, int T, int F, void* hi, void* lo, int rows_per_utt, int row_off,
-                       int pitch, float drop_rate, unsigned long long seed, void* stream);
+                       int pitch, float drop_rate, unsigned long long seed, const unsigned long long* seed_counter_dev,
+                       void* stream);
+/* *counter_dev += 1, enqueued on the stream (graph-capturable) */
+int lbx_counter_tick(unsigned long long* counter_dev, void* stream);
 
 /* lidbox/models/xvector.py:25-35 GlobalMeanStddevPooling1D: y [B*rows_per_utt, pitch] (first T rows of every
  * utterance, C channels; f32 or bf16) -> out [B, 2C] f32 (mean | std), two-pass population variance in fp32,

@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("LBX_LIB") or os.path.join(_PKG_DIR, "liblidbox_b200.s
 
 c_int, c_ll, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 _P = c_void_p
+F32, BF16, I16 = 0, 1, 2      # dtype tags of include/lidbox_b200.h
 
 
 
@@ -23,6 +24,19 @@ class GemmDesc(ctypes.Structure):
         ("out", c_void_p), ("out_lo", c_void_p), ("ldo", c_ll), ("bias", c_void_p), ("relu", c_int),
         ("rows_per_utt", c_int), ("valid_rows", c_int), ("mask_src", c_void_p), ("accumulate", c_int),
         ("tile_n", c_int), ("colsum", c_void_p), ("colsum_mod", c_int),
+    ]
+
+
+class LogmelDesc(ctypes.Structure):
+    """lbx_logmel_t (include/lidbox_b200.h)."""
+    _fields_ = [
+        ("sig", c_void_p), ("sig_dtype", c_int), ("B", c_ll), ("N", c_ll),
+        ("frame_length", c_int), ("frame_step", c_int), ("fft_length", c_int), ("power", c_float),
+        ("n_mel", c_int), ("band_start", c_void_p), ("band_len", c_void_p), ("band_off", c_void_p),
+        ("band_w", c_void_p), ("n_packed", c_int), ("log_mode", c_int), ("eps", c_float),
+        ("out", c_void_p), ("out_lo", c_void_p), ("out_dtype", c_int),
+        ("out_utt_pitch", c_ll), ("out_row_pitch", c_int),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
     ]
 
 
@@ -42,6 +56,7 @@ SIGNATURES = {
                                c_float, _P, _P, c_size_t, _P]),
     "lbx_logmel_i16": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_int, c_int,
                                c_float, _P, _P]),
+    "lbx_logmel_ex": (c_int, [ctypes.POINTER(LogmelDesc), _P]),
     "lbx_power_to_db_f32": (c_int, [_P, c_ll, c_float, c_float, _P, _P, _P]),
     "lbx_check_finite_f32": (c_int, [_P, c_ll, _P, _P]),
     "lbx_normalize_axis_f32": (c_int, [_P, _P, c_ll, c_ll, c_ll, c_int, c_float, c_float, _P]),
@@ -62,7 +77,9 @@ SIGNATURES = {
                                     _P, _P]),
     "lbx_set_gemm_pair": (c_int, [c_int]),
     "lbx_set_gemm_fast_epilogue": (c_int, [c_int]),
-    "lbx_pack_rows_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, _P]),
+    "lbx_pack_rows_bf16": (c_int, [_P, c_ll, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, ctypes.c_ulonglong, _P,
+                                   _P]),
+    "lbx_counter_tick": (c_int, [_P, _P]),
     "lbx_stats_pool_fwd": (c_int, [_P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
     "lbx_stats_pool_bwd": (c_int, [_P, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_int, _P]),
     "lbx_logsoftmax_xent": (c_int, [_P, _P, c_ll, c_int, _P, _P, _P, c_int, c_float, _P, _P]),

@@ -3,13 +3,17 @@
 // Replaces the TensorFlow op chain behind lidbox/features/audio.py:219-230 (spectrograms),
 // :247-261 (linear_to_mel), lidbox/data/tf_utils.py:178 (log) and audio.py:167-174 (power_to_db).
 //
-// Fast path (fft_length == 512): one CTA owns a run of 32 consecutive frames of one utterance.  The samples the
-// run covers are staged ONCE in shared memory (read amplification 1 + (L-step)/(32*step) instead of L/step), each
-// half-warp computes one 512-point real FFT as a 256-point complex FFT (radix-16 in registers, one shared-memory
-// transpose, radix-16 again) followed by a warp-shuffle split step, the power spectrum of the 32 frames is kept
-// in shared memory and reduced against the band-compressed mel filterbank with lanes = frames (conflict-free),
-// and the [32, n_mel] result leaves through shared memory as one contiguous, vectorised store.
+// Fast path (fft_length == 512): persistent CTAs (three per SM) walk runs of 16 consecutive frames of one utterance.
+// The samples of a run are staged ONCE in shared memory by a 1-D bulk copy (TMA) that is issued one run ahead (read
+// amplification 1 + (L-step)/(16*step) instead of L/step), each half-warp computes one 512-point real FFT as a
+// 256-point complex FFT (radix-16 in registers, one shared-memory transpose, radix-16 again) in packed fp32 pairs
+// (FADD2 / FMUL2 / FFMA2: one instruction per complex add, two per complex multiply) followed by a warp-shuffle split
+// step, the power spectrum of the 16 frames is kept in shared memory and reduced against the band-compressed mel
+// filterbank with lanes = frames and 128-bit reads, and the [16, n_mel] result leaves through shared memory as one
+// contiguous, vectorised store — fp32, or bf16 rows written straight into the first frame layer's activation buffer.
 #include "common.cuh"
+#include "fft_tables.h"
+#include <cuda_bf16.h>
 #include <math.h>
 #include <vector>
 
@@ -24,15 +28,6 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-// forward 4-point DFT in place (W4 = -i)
-__device__ __forceinline__ void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-  const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
-  a0 = cadd(s02, s13);
-  a2 = csub(s02, s13);
-  a1 = make_float2(d02.x + d13.y, d02.y - d13.x);
-  a3 = make_float2(d02.x - d13.y, d02.y + d13.x);
-}
-
 // position p of the in-place radix-16 output holds frequency KIDX(p)
 __host__ __device__ constexpr int KIDX(int p) { return (p >> 2) + 4 * (p & 3); }
 // inverse: frequency k lives at position PIDX(k)
@@ -41,38 +36,6 @@ __host__ __device__ constexpr int PIDX(int k) { return 4 * (k & 3) + (k >> 2); }
 #define LBX_C1 0.92387953251128674f   // cos(pi/8)
 #define LBX_S1 0.38268343236508977f   // sin(pi/8)
 #define LBX_R2 0.70710678118654752f   // sqrt(1/2)
-
-// forward 16-point DFT in place: input v[n] natural order, output v[p] = X[KIDX(p)]
-__device__ __forceinline__ void fft16(float2 (&v)[16]) {
-#pragma unroll
-  for (int b = 0; b < 4; ++b) fft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
-  // v[4c + b] *= W16^{b c},  W16^e = (cos(pi e/8), -sin(pi e/8))
-  v[5] = cmul(v[5], make_float2(LBX_C1, -LBX_S1));     // b=1,c=1 e=1
-  v[6] = cmul(v[6], make_float2(LBX_R2, -LBX_R2));     // b=2,c=1 e=2
-  v[7] = cmul(v[7], make_float2(LBX_S1, -LBX_C1));     // b=3,c=1 e=3
-  v[9] = cmul(v[9], make_float2(LBX_R2, -LBX_R2));     // b=1,c=2 e=2
-  v[10] = make_float2(v[10].y, -v[10].x);              // b=2,c=2 e=4 : * (-i)
-  v[11] = cmul(v[11], make_float2(-LBX_R2, -LBX_R2));  // b=3,c=2 e=6
-  v[13] = cmul(v[13], make_float2(LBX_S1, -LBX_C1));   // b=1,c=3 e=3
-  v[14] = cmul(v[14], make_float2(-LBX_R2, -LBX_R2));  // b=2,c=3 e=6
-  v[15] = cmul(v[15], make_float2(-LBX_C1, LBX_S1));   // b=3,c=3 e=9
-#pragma unroll
-  for (int c = 0; c < 4; ++c) fft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-}
-
-// W32^{k} = (cos(pi k/16), -sin(pi k/16)), k = 0..15, as compile-time constants
-__device__ __forceinline__ float2 w32(int k) {
-  constexpr float c[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
-                           0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f,
-                           0.0f, -0.19509032201612825f, -0.38268343236508977f, -0.55557023301960218f,
-                           -0.70710678118654752f, -0.83146961230254524f, -0.92387953251128674f,
-                           -0.98078528040323043f};
-  constexpr float s[16] = {0.0f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
-                           0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
-                           1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
-                           0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f};
-  return make_float2(c[k], -s[k]);
-}
 
 __device__ __forceinline__ float apply_power(float mag2, int pw_mode, float power) {
   if (pw_mode == 2) return mag2;                 // |X|^2
@@ -89,34 +52,89 @@ __device__ __forceinline__ float hann_value(int i, int L) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// fused 512-point kernel
+// fused 512-point kernel (persistent CTAs, packed fp32 pairs)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int FR = 16;           // frames per CTA: 8 warps x 2 half-warps, one frame per half-warp, a single pass
+// A complex value is ONE 64-bit register pair: complex add / sub are single FADD2 instructions, a complex multiply is
+// FMUL2 + FFMA2 (sm_100 packed fp32; the operand swizzles / per-half negations fold the +-i rotations).
+typedef float2 cf;
+__device__ __forceinline__ cf c_add(cf a, cf b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ cf c_sub(cf a, cf b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ cf c_mul(cf a, cf w) {   // (a.x w.x - a.y w.y, a.y w.x + a.x w.y)
+  return __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
+}
+
+__device__ __forceinline__ void fft4p(cf& a0, cf& a1, cf& a2, cf& a3) {   // forward 4-point DFT in place (W4 = -i)
+  const cf s02 = c_add(a0, a2), d02 = c_sub(a0, a2), s13 = c_add(a1, a3), d13 = c_sub(a1, a3);
+  a0 = c_add(s02, s13);
+  a2 = c_sub(s02, s13);
+  a1 = c_add(d02, make_float2(d13.y, -d13.x));
+  a3 = c_add(d02, make_float2(-d13.y, d13.x));
+}
+
+// forward 16-point DFT in place: input v[n] natural order, output v[p] = X[KIDX(p)]
+__device__ __forceinline__ void fft16p(cf (&v)[16]) {
+#pragma unroll
+  for (int b = 0; b < 4; ++b) fft4p(v[b], v[4 + b], v[8 + b], v[12 + b]);
+  // v[4c + b] *= W16^{b c},  W16^e = (cos(pi e/8), -sin(pi e/8))
+  v[5] = c_mul(v[5], make_float2(LBX_C1, -LBX_S1));     // e=1
+  v[6] = c_mul(v[6], make_float2(LBX_R2, -LBX_R2));     // e=2
+  v[7] = c_mul(v[7], make_float2(LBX_S1, -LBX_C1));     // e=3
+  v[9] = c_mul(v[9], make_float2(LBX_R2, -LBX_R2));     // e=2
+  v[10] = make_float2(v[10].y, -v[10].x);               // e=4 : * (-i)
+  v[11] = c_mul(v[11], make_float2(-LBX_R2, -LBX_R2));  // e=6
+  v[13] = c_mul(v[13], make_float2(LBX_S1, -LBX_C1));   // e=3
+  v[14] = c_mul(v[14], make_float2(-LBX_R2, -LBX_R2));  // e=6
+  v[15] = c_mul(v[15], make_float2(-LBX_C1, LBX_S1));   // e=9
+#pragma unroll
+  for (int c = 0; c < 4; ++c) fft4p(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
+// W32^k = (cos(pi k/16), -sin(pi k/16)), k = 0..7, as compile-time constants
+__device__ __forceinline__ cf w32c(int k) {
+  constexpr float c[8] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                          0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f};
+  constexpr float sn[8] = {0.0f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
+                           0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f};
+  return make_float2(c[k], -sn[k]);
+}
+
+constexpr int FR = 16;           // frames per pass: 8 warps x 2 half-warps, one frame per half-warp
 constexpr int FUSED_THREADS = 256;
-constexpr int P_STRIDE = 257;    // odd: the lanes = frames reads of the mel phase are conflict-free
+constexpr int P_STRIDE = 268;    // floats per power-spectrum row: 16-byte aligned rows; stride/4 odd -> the lanes = frames
+                                 // 128-bit reads of the mel phase are conflict-free; columns 257..267 stay zero (the
+                                 // vector walk of a band may read up to 7 bins past its end against zero weights)
+constexpr int MEL_SLOTS = FUSED_THREADS / FR;   // 16 band slots x 16 frames in the mel phase
 constexpr int SCR_ROW = 17;      // float2 per transpose row (16 + 1 pad)
-constexpr int SCR_FLOATS = 8 * 2 * 16 * SCR_ROW * 2;
-constexpr int P_FLOATS = (FR * P_STRIDE + 3) & ~3;
+constexpr int SCR_FLOAT2 = 16 * 16 * SCR_ROW;   // 16 half-warps
+constexpr int N_BINS = 257;
 
 struct FusedParams {
   const float* sig;
   const short* sig_i16;  // when non-NULL the input is 16-bit PCM and is converted as x / 32768 (what decode_wav does)
-  float* out;
   long long N;
   long long T;
   int frame_length;
   int frame_step;
-  int sig_smem;        // floats reserved for the staged signal run (multiple of 4, >= (FR-1)*step + 512 + 2)
+  int sig_smem;        // floats reserved for the staged signal run (multiple of 8, >= (FR-1)*step + 512)
+  int async_ok;        // 1: every run starts at a 16-byte aligned global address -> bulk-copy prefetch of the next run
   float power;
+  int runs_per_utt;    // runs of FR frames per utterance
+  int B;
   // mel (MODE 1)
   int n_mel;
   const int* band_start;
   const int* band_len;
   const int* band_off;
   const float* band_w;
-  int n_packed;
+  int n_w4;            // floats reserved for the 4-aligned, zero-padded copy of the band weights
   int log_mode;
   float eps;
+  // output: frame t of utterance b goes to out + b * utt_pitch + t * row_pitch (elements)
+  void* out;
+  void* out_lo;        // optional bf16 residual plane (out_bf16 only)
+  int out_bf16;
+  long long utt_pitch;
+  int row_pitch;
 };
 
 template <int PW>
@@ -126,177 +144,417 @@ __device__ __forceinline__ float power_of(float mag2, float power) {
   return powf(sqrtf(mag2), power);               // pow(abs(S), power), audio.py:230
 }
 
+__device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LM_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LM_WAIT_DONE;\n\t"
+      "bra LM_WAIT_LOOP;\n\t"
+      "LM_WAIT_DONE:\n\t"
+      "}" ::"r"(f_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+// Stage the samples of one run of FR frames.  Bulk part: ONE cp.async.bulk (TMA, 1-D) issued by thread 0, completion on
+// the mbarrier; the < 16-byte tail and the zero fill behind the run are plain stores (visible after the next barrier).
+template <bool IN16>
+__device__ __forceinline__ void stage_run_async(const FusedParams& p, int b, int r, float* s_sig, uint64_t* bar) {
+  const int tid = threadIdx.x;
+  const long long t0 = (long long)r * FR;
+  const int nf = (int)min((long long)FR, p.T - t0);
+  const int n_valid = (nf - 1) * p.frame_step + p.frame_length;          // samples the run needs (all in range)
+  const long long s0 = (long long)b * p.N + t0 * p.frame_step;
+  if (IN16) {
+    // raw PCM lands in the upper half of the float area and is expanded in place at the top of the pass
+    short* raw = reinterpret_cast<short*>(s_sig) + p.sig_smem;
+    const short* g = p.sig_i16 + s0;
+    const int n_bulk = n_valid & ~7;
+    if (tid == 0) {
+      if (n_bulk > 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(n_bulk * 2) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         f_smem_u32(raw)), "l"(g), "r"(n_bulk * 2), "r"(f_smem_u32(bar)) : "memory");
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f_smem_u32(bar)) : "memory");
+      }
+    }
+    if (tid < n_valid - n_bulk) raw[n_bulk + tid] = __ldg(g + n_bulk + tid);
+  } else {
+    const float* g = p.sig + s0;
+    const int n_bulk = n_valid & ~3;
+    if (tid == 0) {
+      if (n_bulk > 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(n_bulk * 4) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         f_smem_u32(s_sig)), "l"(g), "r"(n_bulk * 4), "r"(f_smem_u32(bar)) : "memory");
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f_smem_u32(bar)) : "memory");
+      }
+    }
+    if (tid < n_valid - n_bulk) s_sig[n_bulk + tid] = __ldg(g + n_bulk + tid);
+    for (int i = n_valid + tid; i < p.sig_smem; i += FUSED_THREADS) s_sig[i] = 0.0f;
+  }
+}
+
+// unaligned fallback: plain loads at the top of the pass
+template <bool IN16>
+__device__ __forceinline__ void stage_run_sync(const FusedParams& p, int b, long long t0, int nf, float* s_sig) {
+  const int tid = threadIdx.x;
+  const int n_valid = (nf - 1) * p.frame_step + p.frame_length;
+  const long long s0 = (long long)b * p.N + t0 * p.frame_step;
+  if (IN16) {
+    const short* g = p.sig_i16 + s0;
+    for (int i = tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = (float)__ldg(g + i) * (1.0f / 32768.0f);
+  } else {
+    const float* g = p.sig + s0;
+    for (int i = tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = __ldg(g + i);
+  }
+  for (int i = n_valid + tid; i < p.sig_smem; i += FUSED_THREADS) s_sig[i] = 0.0f;
+}
+
 // MODE 0: power spectrogram [B,T,257]; MODE 1: (log-)mel [B,T,n_mel].  PW: 2 -> |X|^2, 1 -> |X|, 0 -> generic power.
-template <int MODE, int PW>
-__global__ void __launch_bounds__(FUSED_THREADS, 3) logmel512_kernel(const FusedParams p) {
+template <int MODE, int PW, bool IN16>
+#ifndef LBX_LM_MIN_CTAS
+#define LBX_LM_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(FUSED_THREADS, LBX_LM_MIN_CTAS) logmel512_kernel(const FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* s_sig = reinterpret_cast<float*>(smem_raw);
-  float* s_win = s_sig + p.sig_smem;                         // 512 (zero beyond frame_length)
-  float2* s_twA = reinterpret_cast<float2*>(s_win + 512);    // [q][l]: W256^{l * KIDX(q)}, 256 entries
-  float2* s_w512 = s_twA + 256;                              // W512^k, k = 0..255
-  float* s_P = reinterpret_cast<float*>(s_w512 + 256);       // FR * P_STRIDE
-  float2* s_scr = reinterpret_cast<float2*>(s_P + P_FLOATS);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw);                // 16 bytes reserved
+  float* s_sig = reinterpret_cast<float*>(smem_raw + 16);
+  float* s_win = s_sig + p.sig_smem;                         // 512: 0.5 * Hann (zero beyond frame_length)
+  float* s_P = s_win + 512;                                  // FR * P_STRIDE
+  float2* s_scr = reinterpret_cast<float2*>(s_P + (FR + 1) * P_STRIDE);   // + one spare row for idle half-warps
   float* s_out = reinterpret_cast<float*>(s_scr);            // aliases the transpose scratch (dead by then)
-  float* s_bw = reinterpret_cast<float*>(s_scr) + SCR_FLOATS;
-  int* s_bstart = reinterpret_cast<int*>(s_bw + ((p.n_packed + 3) & ~3));
-  int* s_blen = s_bstart + p.n_mel;
-  int* s_boff = s_blen + p.n_mel;
+  float* s_w4 = reinterpret_cast<float*>(s_scr + SCR_FLOAT2);
+  int4* s_band = reinterpret_cast<int4*>(s_w4 + p.n_w4);     // per band: {P vector index, weight vector index, vectors, m}
+  int4* s_task = s_band + p.n_mel;                           // the same records grouped by slot (mel-phase walk order)
+  int* s_tag = reinterpret_cast<int*>(s_task + p.n_mel);     // scratch of the slot assignment
+  int* s_order = s_tag + p.n_mel;                            // band ids grouped by slot
+  int* s_slot_off = s_order + p.n_mel;                       // MEL_SLOTS + 1 offsets into s_order / s_task
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, half = lane >> 4, l16 = lane & 15;
   const int L = p.frame_length, step = p.frame_step;
-  const long long t0 = (long long)blockIdx.x * FR;
-  const int b = blockIdx.y;
-  const int nf = (int)min((long long)FR, p.T - t0);
 
-  // ---- tables that do not depend on earlier kernels: window and twiddles ----
+  // ---- per-CTA tables (once: the CTA is persistent) ----
   for (int i = tid; i < 512; i += FUSED_THREADS) {
     float w = 0.0f;
     if (i < L) {
-      // periodic Hann, tf.signal.hann_window(L, periodic=True): n = L + (1 - L%2) - 1; cos(2 pi i / n) via cospi
+      // periodic Hann, tf.signal.hann_window(L, periodic=True): n = L + (1 - L%2) - 1; cos(2 pi i / n) via cospi.
+      // The factor 1/2 of the real-FFT split step (X = (E + W O) / 2) is folded in here: an exact power-of-two scaling.
       const float n = (float)(L + (1 - (L & 1)) - 1);
-      w = L == 1 ? 1.0f : 0.5f - 0.5f * cospif(2.0f * (float)i / n);
+      w = L == 1 ? 0.5f : 0.25f - 0.25f * cospif(2.0f * (float)i / n);
     }
     s_win[i] = w;
   }
-  {
-    float sn, cs;
-    sincospif((float)tid * (1.0f / 256.0f), &sn, &cs);       // W512^tid = exp(-2 pi i tid / 512)
-    s_w512[tid] = make_float2(cs, -sn);
+  // Twiddles: shared memory bandwidth is this kernel's limiter (ncu: 74 % of the LSU wavefront peak with table
+  // look-ups), so they are COMPUTED from two per-lane constants instead of loaded: the inter-stage factor
+  // W256^{l KIDX(q)} is a power of om = W256^l (binary powering, depth <= 6 multiplies), the split-step factor
+  // W512^{l + 16 k2} is W512^l times the compile-time constant W32^{k2}.
+  const cf om = LBX_W512[2 * l16];                           // W256^l
+  const cf wl = LBX_W512[l16];                               // W512^l
+  for (int i = tid; i < FR * (P_STRIDE - N_BINS); i += FUSED_THREADS)   // pad columns of the power rows
+    s_P[(i / (P_STRIDE - N_BINS)) * P_STRIDE + N_BINS + i % (P_STRIDE - N_BINS)] = 0.0f;
+  for (int i = tid; i < p.sig_smem; i += FUSED_THREADS) s_sig[i] = 0.0f;
+  if (MODE == 1) {
+    // 8-aligned (two vectors), zero-padded copy of the band-compressed filterbank: band m covers bins
+    // [start4, start4 + 4 nvec), nvec even
+    for (int i = tid; i < p.n_w4; i += FUSED_THREADS) s_w4[i] = 0.0f;
+    if (tid == 0) {
+      int off = 0;
+      for (int m = 0; m < p.n_mel; ++m) {
+        const int st = __ldg(p.band_start + m), ln = __ldg(p.band_len + m);
+        const int st4 = st & ~3;
+        const int nv = ln > 0 ? (((st + ln - st4 + 3) >> 2) + 1) & ~1 : 0;
+        s_band[m] = make_int4(st4 >> 2, off >> 2, nv, m);
+        off += 4 * nv;
+      }
+    }
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f_smem_u32(s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (MODE == 1) {
+    for (int m = warp; m < p.n_mel; m += FUSED_THREADS / 32) {
+      const int st = __ldg(p.band_start + m), ln = __ldg(p.band_len + m), bo = __ldg(p.band_off + m);
+      float* dst = s_w4 + 4 * s_band[m].y + (st - 4 * s_band[m].x);
+      for (int j = lane; j < ln; j += 32) dst[j] = __ldg(p.band_w + bo + j);
+    }
+    // bands -> MEL_SLOTS slots of about equal work: rank the bands by length (longest first, counting sort by
+    // comparison, one band per thread) and deal the ranks out in snake order; a partial last round goes to the
+    // slots that received the shortest bands so far
+    for (int m = tid; m < p.n_mel; m += FUSED_THREADS) {
+      const int mine = s_band[m].z;
+      int rank = 0;
+      for (int o = 0; o < p.n_mel; ++o) {
+        const int other = s_band[o].z;
+        rank += (other > mine || (other == mine && o < m)) ? 1 : 0;
+      }
+      const int round = rank / MEL_SLOTS, pos = rank % MEL_SLOTS;
+      const int rounds = (p.n_mel + MEL_SLOTS - 1) / MEL_SLOTS;
+      const bool last_partial = round == rounds - 1 && (p.n_mel % MEL_SLOTS) != 0;
+      const int slot = ((round & 1) || last_partial) ? MEL_SLOTS - 1 - pos : pos;
+      s_tag[rank] = (slot << 16) | m;                         // parked by rank; grouped by slot below
+    }
+    if (tid <= MEL_SLOTS) s_slot_off[tid] = 0;
+  }
+  __syncthreads();
+  if (MODE == 1 && tid == 0) {
+    // group by slot (n_mel <= 256 entries, once per persistent CTA): count, prefix sum, place back to front
+    for (int i = 0; i < p.n_mel; ++i) s_slot_off[(s_tag[i] >> 16) + 1]++;
+    for (int i = 0; i < MEL_SLOTS; ++i) s_slot_off[i + 1] += s_slot_off[i];
+    for (int i = p.n_mel - 1; i >= 0; --i) {                  // s_slot_off[slot + 1] walks from the end of the slot down
+      const int slot = s_tag[i] >> 16;                        // to its start
+      s_order[--s_slot_off[slot + 1]] = s_tag[i] & 0xFFFF;
+    }
+    // (the band records themselves are regrouped below, once the placement is final)
+    // now s_slot_off[s + 1] is the START of slot s: shift into the usual [start, end) form
+    for (int i = 0; i < MEL_SLOTS; ++i) s_slot_off[i] = s_slot_off[i + 1];
+    s_slot_off[MEL_SLOTS] = p.n_mel;
+  }
+  __syncthreads();
+  if (MODE == 1) {
+    // slot-ordered copy of the band records: the mel phase walks s_task[s_slot_off[slot] .. s_slot_off[slot + 1])
+    for (int i = tid; i < p.n_mel; i += FUSED_THREADS) s_task[i] = s_band[s_order[i]];
   }
   LBX_PDL_SYNC();
-  // ---- stage the sample run and the mel tables ----
-  {
-    const long long s0 = t0 * step;
-    const int n_valid = (nf - 1) * step + L;                  // samples this CTA actually needs (all in range)
-    const float* g = p.sig + (long long)b * p.N + s0;
-    if (p.sig_i16 != nullptr) {
-      const short* gi = p.sig_i16 + (long long)b * p.N + s0;
-      if ((reinterpret_cast<uintptr_t>(gi) & 7) == 0) {
-        const int n4 = n_valid >> 2;                          // 4 samples per thread: 8-byte load, 16-byte store
-        for (int i = tid; i < n4; i += FUSED_THREADS) {
-          const uint2 u = __ldg(reinterpret_cast<const uint2*>(gi) + i);
-          reinterpret_cast<float4*>(s_sig)[i] =
-              make_float4((float)(short)(u.x & 0xFFFFu) * (1.0f / 32768.0f), (float)(short)(u.x >> 16) * (1.0f / 32768.0f),
-                          (float)(short)(u.y & 0xFFFFu) * (1.0f / 32768.0f), (float)(short)(u.y >> 16) * (1.0f / 32768.0f));
-        }
-        for (int i = (n4 << 2) + tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = (float)__ldg(gi + i) * (1.0f / 32768.0f);
-      } else {
-        for (int i = tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = (float)__ldg(gi + i) * (1.0f / 32768.0f);
-      }
-    } else if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
-      const int n4 = n_valid >> 2;
-      const float4* g4 = reinterpret_cast<const float4*>(g);
-      float4* s4 = reinterpret_cast<float4*>(s_sig);
-      for (int i = tid; i < n4; i += FUSED_THREADS) s4[i] = __ldg(g4 + i);
-      for (int i = (n4 << 2) + tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = __ldg(g + i);
-    } else {
-      for (int i = tid; i < n_valid; i += FUSED_THREADS) s_sig[i] = __ldg(g + i);
-    }
-    for (int i = n_valid + tid; i < p.sig_smem; i += FUSED_THREADS) s_sig[i] = 0.0f;
-    if (MODE == 1) {
-      for (int i = tid; i < p.n_packed; i += FUSED_THREADS) s_bw[i] = __ldg(p.band_w + i);
-      for (int i = tid; i < p.n_mel; i += FUSED_THREADS) {
-        s_bstart[i] = __ldg(p.band_start + i);
-        s_blen[i] = __ldg(p.band_len + i);
-        s_boff[i] = __ldg(p.band_off + i);
-      }
-    }
-  }
-  __syncthreads();
-  {
-    // twiddles between the two radix-16 steps, stored so that a half-warp reads 16 consecutive entries:
-    // s_twA[q*16 + l] = W256^{l * KIDX(q)};  W256^e = W512^{2e} (e < 128) = -W512^{2e-256} (e >= 128)
-    const int q = tid >> 4, l = tid & 15;
-    const int e = (l * KIDX(q)) & 255;
-    const float2 w = e < 128 ? s_w512[2 * e] : s_w512[2 * e - 256];
-    s_twA[tid] = e < 128 ? w : make_float2(-w.x, -w.y);
-  }
-  __syncthreads();
+  // work items = (utterance b, run r) walked with a grid-sized stride, kept as a pair (no division in the loop)
+  const int runs = p.runs_per_utt;
+  const int g_b = (int)(gridDim.x / (unsigned)runs), g_r = (int)(gridDim.x % (unsigned)runs);
+  int b = (int)(blockIdx.x / (unsigned)runs), r = (int)(blockIdx.x % (unsigned)runs);
+  if (p.async_ok && b < p.B) stage_run_async<IN16>(p, b, r, s_sig, s_bar);
+  uint32_t phase = 0;
 
-  const int f = half * 8 + warp;                              // frame within the CTA's run
-  const float* fs = s_sig + f * step;
+  const int f = (warp & 3) + 4 * half + 8 * (warp >> 2);     // frame within the run; the two half-warps of a warp are 4
+                                                             // rows apart = 16 banks: their power-row stores never collide
   float2* my_scr = s_scr + (warp * 2 + half) * 16 * SCR_ROW;
-  float2 v[16];
-  // z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1],  n = 16 n1 + l16 (rows beyond the window multiply by zero)
-  if ((step & 1) == 0) {
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-      const float2 x = *reinterpret_cast<const float2*>(fs + 32 * n1 + 2 * l16);
-      const float2 w = *reinterpret_cast<const float2*>(s_win + 32 * n1 + 2 * l16);
-      v[n1] = make_float2(x.x * w.x, x.y * w.y);
-    }
-  } else {
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-      const int i = 32 * n1 + 2 * l16;
-      v[n1] = make_float2(fs[i] * s_win[i], fs[i + 1] * s_win[i + 1]);
-    }
-  }
-  fft16(v);
-#pragma unroll
-  for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], s_twA[q * 16 + l16]);
-#pragma unroll
-  for (int q = 0; q < 16; ++q) my_scr[KIDX(q) * SCR_ROW + l16] = v[q];
-  __syncwarp();
-#pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2) v[n2] = my_scr[l16 * SCR_ROW + n2];
-  fft16(v);                                                   // v[q] = Z[l16 + 16 KIDX(q)]
-
-  // split step.  With E = (Z[k] + conj Z[256-k]) / 2, O = (Z[k] - conj Z[256-k]) / 2i and t = W512^k O:
-  //   X[k] = E + t,  X[256-k] = conj(E - t)  ->  both power bins from one evaluation; only k2 = KIDX(q) < 8 is walked.
-  // The partner Z[256-k] lives in lane (16 - l16) & 15, register 15 - q (lane 0 pairs with itself).
-  float* Prow = s_P + f * P_STRIDE;
   const int src_lane = (half << 4) | ((16 - l16) & 15);
-#pragma unroll
-  for (int qi = 0; qi < 8; ++qi) {
-    const int q = (qi >> 1) * 4 + (qi & 1);                   // 0,1,4,5,8,9,12,13
-    const int k2 = KIDX(q);
-    float cx = __shfl_sync(0xffffffffu, v[15 - q].x, src_lane);
-    float cy = __shfl_sync(0xffffffffu, v[15 - q].y, src_lane);
-    if (l16 == 0) {                                           // k1 == 0: partner 16*((16-k2)&15) is in this lane
-      cx = v[PIDX((16 - k2) & 15)].x;
-      cy = v[PIDX((16 - k2) & 15)].y;
-    }
-    const float a = v[q].x, bb = v[q].y;
-    const float ex = a + cx, ey = bb - cy;                    // 2 E
-    const float2 t = cmul(s_w512[l16 + 16 * k2], make_float2(bb + cy, cx - a));   // W512^k * 2 O
-    const float x1 = ex + t.x, y1 = ey + t.y, x2 = ex - t.x, y2 = ey - t.y;
-    const int k = l16 + 16 * k2;
-    Prow[k] = power_of<PW>(0.25f * fmaf(x1, x1, y1 * y1), p.power);
-    Prow[256 - k] = power_of<PW>(0.25f * fmaf(x2, x2, y2 * y2), p.power);
-  }
-  if (l16 == 0) Prow[128] = power_of<PW>(fmaf(v[PIDX(8)].x, v[PIDX(8)].x, v[PIDX(8)].y * v[PIDX(8)].y), p.power);
-  __syncthreads();
 
-  if (MODE == 0) {
-    float* dst = p.out + ((long long)b * p.T + t0) * 257;
-    const int total = nf * 257;                               // s_P rows are contiguous (stride 257)
-    for (int i = tid; i < total; i += FUSED_THREADS) dst[i] = s_P[i];
-  } else {
-    const int n_mel = p.n_mel;
-    const int mf = tid & 15;                                  // frame
-    const float* Pf = s_P + mf * P_STRIDE;
-    for (int m = tid >> 4; m < n_mel; m += 16) {
-      const int start = s_bstart[m], len = s_blen[m];
-      const float* w = s_bw + s_boff[m];
-      const float* Pk = Pf + start;
-      float acc = 0.0f;
-      for (int j = 0; j < len; ++j) acc = fmaf(Pk[j], w[j], acc);
-      if (p.log_mode == 1) acc = logf(acc + p.eps);
-      s_out[mf * n_mel + m] = acc;
-    }
-    __syncthreads();
-    float* dst = p.out + ((long long)b * p.T + t0) * n_mel;
-    const int total = nf * n_mel;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      const int n4 = total >> 2;
-      for (int i = tid; i < n4; i += FUSED_THREADS)
-        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_out)[i];
-      for (int i = (n4 << 2) + tid; i < total; i += FUSED_THREADS) dst[i] = s_out[i];
+  while (b < p.B) {
+    const long long t0 = (long long)r * FR;
+    const int nf = (int)min((long long)FR, p.T - t0);
+    int b_next = b + g_b, r_next = r + g_r;
+    if (r_next >= runs) { r_next -= runs; ++b_next; }
+    if (p.async_ok) {
+      f_mbar_wait(s_bar, phase);
+      phase ^= 1;
+      if (IN16) {
+        // expand the raw PCM in place (raw lives in the upper half of the float area): all reads, barrier, all writes
+        const int n_valid = (nf - 1) * step + L;
+        const uint4* raw = reinterpret_cast<const uint4*>(reinterpret_cast<const short*>(s_sig) + p.sig_smem);
+        const int nvec = p.sig_smem >> 3;
+        uint4 u[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int vi = tid + j * FUSED_THREADS;
+          u[j] = (vi < nvec && vi * 8 < n_valid) ? raw[vi] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int vi = tid + j * FUSED_THREADS;
+          if (vi < nvec) {
+            const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              x[2 * i] = (vi * 8 + 2 * i < n_valid) ? (float)(short)(w[i] & 0xFFFFu) * (1.0f / 32768.0f) : 0.0f;
+              x[2 * i + 1] = (vi * 8 + 2 * i + 1 < n_valid) ? (float)(short)(w[i] >> 16) * (1.0f / 32768.0f) : 0.0f;
+            }
+            reinterpret_cast<float4*>(s_sig)[2 * vi] = make_float4(x[0], x[1], x[2], x[3]);
+            reinterpret_cast<float4*>(s_sig)[2 * vi + 1] = make_float4(x[4], x[5], x[6], x[7]);
+          }
+        }
+      }
     } else {
-      for (int i = tid; i < total; i += FUSED_THREADS) dst[i] = s_out[i];
+      stage_run_sync<IN16>(p, b, t0, nf, s_sig);
     }
+    __syncthreads();                                          // the run is staged
+
+    cf v[16];
+    const bool active = f < nf;                               // this half-warp's frame exists
+    const bool warp_active = (f - 4 * half) < nf;             // warp-uniform: at least the lower half-warp has one
+    // a half-warp without a frame recomputes frame 0 (finite work on valid memory) and discards the result
+    const float* fs = s_sig + (active ? f : 0) * step;
+    if (warp_active) {
+      // z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1],  n = 16 n1 + l16 (rows beyond the window multiply by zero)
+      if ((step & 1) == 0) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1)
+          v[n1] = __fmul2_rn(*reinterpret_cast<const float2*>(fs + 32 * n1 + 2 * l16),
+                             *reinterpret_cast<const float2*>(s_win + 32 * n1 + 2 * l16));
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+          const int i = 32 * n1 + 2 * l16;
+          v[n1] = make_float2(fs[i] * s_win[i], fs[i + 1] * s_win[i + 1]);
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order these accesses before the next bulk copy
+    __syncthreads();                                          // every frame is in registers: the signal area is free
+    if (p.async_ok && b_next < p.B) stage_run_async<IN16>(p, b_next, r_next, s_sig, s_bar);
+    if (warp_active) {
+      fft16p(v);
+      {
+        // v[PIDX(k)] *= om^k, k = 1..15 (position PIDX(k) holds frequency k of the first pass)
+        const cf p2 = c_mul(om, om), p4 = c_mul(p2, p2), p8 = c_mul(p4, p4);
+        v[PIDX(1)] = c_mul(v[PIDX(1)], om);
+        v[PIDX(2)] = c_mul(v[PIDX(2)], p2);
+        v[PIDX(3)] = c_mul(v[PIDX(3)], c_mul(p2, om));
+        v[PIDX(4)] = c_mul(v[PIDX(4)], p4);
+        v[PIDX(5)] = c_mul(v[PIDX(5)], c_mul(p4, om));
+        const cf p6 = c_mul(p4, p2);
+        v[PIDX(6)] = c_mul(v[PIDX(6)], p6);
+        v[PIDX(7)] = c_mul(v[PIDX(7)], c_mul(p6, om));
+        v[PIDX(8)] = c_mul(v[PIDX(8)], p8);
+        v[PIDX(9)] = c_mul(v[PIDX(9)], c_mul(p8, om));
+        const cf p10 = c_mul(p8, p2);
+        v[PIDX(10)] = c_mul(v[PIDX(10)], p10);
+        v[PIDX(11)] = c_mul(v[PIDX(11)], c_mul(p10, om));
+        const cf p12 = c_mul(p8, p4);
+        v[PIDX(12)] = c_mul(v[PIDX(12)], p12);
+        v[PIDX(13)] = c_mul(v[PIDX(13)], c_mul(p12, om));
+        const cf p14 = c_mul(p12, p2);
+        v[PIDX(14)] = c_mul(v[PIDX(14)], p14);
+        v[PIDX(15)] = c_mul(v[PIDX(15)], c_mul(p14, om));
+      }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) my_scr[KIDX(q) * SCR_ROW + l16] = v[q];
+      __syncwarp();
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) v[n2] = my_scr[l16 * SCR_ROW + n2];
+      fft16p(v);                                              // v[q] = Z[l16 + 16 KIDX(q)] / 2
+    // split step (whole warp takes part in the shuffles).  With E = Z[k] + conj Z[256-k], G = Z[k] - conj Z[256-k] and
+    // t = W512^k (-i G):  X[k] = E + t,  X[256-k] = conj(E - t)  ->  both power bins from one evaluation; only
+    // k2 = KIDX(q) < 8 is walked.  The partner Z[256-k] lives in lane (16 - l16) & 15, register 15 - q (lane 0 pairs
+    // with itself).  W512^k (-i) = W512^l * (-i W32^k2): per-lane factor times a compile-time constant.
+    // A half-warp without a frame stores into the spare row behind the run (no branch around the stores).
+      float* pa = s_P + (active ? f : FR) * P_STRIDE + l16;   // row[k],       k = l16 + 16 k2
+      float* pb = pa + 256 - 2 * l16;                          // row[256 - k]
+#pragma unroll
+      for (int qi = 0; qi < 8; ++qi) {
+        const int q = (qi >> 1) * 4 + (qi & 1);               // 0,1,4,5,8,9,12,13
+        const int k2 = KIDX(q);
+        cf c = make_float2(__shfl_sync(0xffffffffu, v[15 - q].x, src_lane), __shfl_sync(0xffffffffu, v[15 - q].y, src_lane));
+        if (l16 == 0) c = v[PIDX((16 - k2) & 15)];            // k1 == 0: partner 16*((16-k2)&15) is in this lane
+        const cf a = v[q];
+        const cf e = c_add(a, make_float2(c.x, -c.y));
+        const cf g = c_add(a, make_float2(-c.x, c.y));
+        const cf wk = w32c(k2);
+        const cf t = c_mul(c_mul(g, make_float2(wk.y, -wk.x)), wl);      // (-i W32^k2) = (w.y, -w.x)
+        const cf x1 = c_add(e, t), x2 = c_sub(e, t);
+        pa[16 * k2] = power_of<PW>(fmaf(x1.x, x1.x, x1.y * x1.y), p.power);
+        pb[-16 * k2] = power_of<PW>(fmaf(x2.x, x2.x, x2.y * x2.y), p.power);
+      }
+      if (l16 == 0) {
+        const cf z = v[PIDX(8)];
+        pa[128] = power_of<PW>(4.0f * fmaf(z.x, z.x, z.y * z.y), p.power);
+      }
+    }
+    __syncthreads();                                          // power rows complete; transpose scratch is dead
+
+    if (MODE == 0) {
+      float* dst = reinterpret_cast<float*>(p.out) + (long long)b * p.utt_pitch + t0 * p.row_pitch;
+      for (int i = tid; i < nf * N_BINS; i += FUSED_THREADS) {
+        const int fr = i / N_BINS, k = i - fr * N_BINS;
+        dst[(long long)fr * p.row_pitch + k] = s_P[fr * P_STRIDE + k];
+      }
+      // (the next pass rewrites the rows only after its own two barriers)
+    } else {
+      const int n_mel = p.n_mel;
+      const int mf = tid & 15;                                // frame
+      if (mf < nf) {
+        const float4* Pf = reinterpret_cast<const float4*>(s_P + mf * P_STRIDE);
+        const float4* W4 = reinterpret_cast<const float4*>(s_w4);
+        const int slot = tid >> 4;
+        float* out_row = s_out + mf * n_mel;
+        const int4* task = s_task + s_slot_off[slot];
+        const int4* task_end = s_task + s_slot_off[slot + 1];
+        for (; task < task_end; ++task) {
+          const int4 band = *task;
+          const float4* Pk = Pf + band.x;
+          const float4* w = W4 + band.y;
+          const float4* w_end = w + band.z;
+          float2 acc0 = make_float2(0.0f, 0.0f), acc1 = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+          for (; w < w_end; w += 2, Pk += 2) {
+            const float4 p0 = Pk[0], w0 = w[0], p1 = Pk[1], w1 = w[1];
+            acc0 = __ffma2_rn(make_float2(p0.x, p0.y), make_float2(w0.x, w0.y), acc0);
+            acc1 = __ffma2_rn(make_float2(p0.z, p0.w), make_float2(w0.z, w0.w), acc1);
+            acc0 = __ffma2_rn(make_float2(p1.x, p1.y), make_float2(w1.x, w1.y), acc0);
+            acc1 = __ffma2_rn(make_float2(p1.z, p1.w), make_float2(w1.z, w1.w), acc1);
+          }
+          const float2 acc = __fadd2_rn(acc0, acc1);
+          float y = acc.x + acc.y;
+          if (p.log_mode == 1) {
+            // ln(y + eps) = lg2.approx(y + eps) * ln 2 (MUFU): absolute error ~2^-22 in log2, far inside the 1e-4
+            // contract; y + eps is a normal number, so the flush-to-zero form is exact about it
+            float l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(y + p.eps));
+            y = l2 * 0.693147180559945309f;
+          }
+          out_row[band.w] = y;
+        }
+      }
+      __syncthreads();
+      const int total = nf * n_mel;
+      if (!p.out_bf16) {
+        float* dst = reinterpret_cast<float*>(p.out) + (long long)b * p.utt_pitch + t0 * p.row_pitch;
+        if (p.row_pitch == n_mel && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          const int n4 = total >> 2;
+          for (int i = tid; i < n4; i += FUSED_THREADS)
+            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_out)[i];
+          for (int i = (n4 << 2) + tid; i < total; i += FUSED_THREADS) dst[i] = s_out[i];
+        } else {
+          for (int i = tid; i < total; i += FUSED_THREADS) {
+            const int fr = i / n_mel, m = i - fr * n_mel;
+            dst[(long long)fr * p.row_pitch + m] = s_out[i];
+          }
+        }
+      } else {
+        // bf16 rows straight into the (zero-left-padded) activation buffer of the first frame layer
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)b * p.utt_pitch + t0 * p.row_pitch;
+        __nv_bfloat16* dlo = p.out_lo ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) + (long long)b * p.utt_pitch + t0 * p.row_pitch
+                                      : nullptr;
+        if ((n_mel & 7) == 0 && (p.row_pitch & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 &&
+            (dlo == nullptr || (reinterpret_cast<uintptr_t>(dlo) & 15) == 0)) {
+          const int per_row = n_mel >> 3;
+          for (int i = tid; i < nf * per_row; i += FUSED_THREADS) {
+            const int fr = i / per_row, seg = i - fr * per_row;
+            const float4 x0 = *reinterpret_cast<const float4*>(s_out + fr * n_mel + seg * 8);
+            const float4 x1 = *reinterpret_cast<const float4*>(s_out + fr * n_mel + seg * 8 + 4);
+            const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(xs[2 * j], xs[2 * j + 1]);
+              hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(xs[2 * j] - __low2float(h), xs[2 * j + 1] - __high2float(h));
+              lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            *reinterpret_cast<uint4*>(dst + (long long)fr * p.row_pitch + seg * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (dlo) *reinterpret_cast<uint4*>(dlo + (long long)fr * p.row_pitch + seg * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        } else {
+          for (int i = tid; i < total; i += FUSED_THREADS) {
+            const int fr = i / n_mel, m = i - fr * n_mel;
+            const __nv_bfloat16 h = __float2bfloat16_rn(s_out[i]);
+            dst[(long long)fr * p.row_pitch + m] = h;
+            if (dlo) dlo[(long long)fr * p.row_pitch + m] = __float2bfloat16_rn(s_out[i] - __bfloat162float(h));
+          }
+        }
+      }
+      // s_out aliases the transpose scratch, which the next pass writes only after its two barriers
+    }
+    b = b_next;
+    r = r_next;
   }
 }
 
@@ -414,22 +672,25 @@ __global__ void __launch_bounds__(256) check_finite_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------------------------
 static int pw_mode_of(float power) { return power == 2.0f ? 2 : (power == 1.0f ? 1 : 0); }
 
-static int fused_sig_smem(int L, int step) {
-  (void)L;
-  long long n = (long long)(FR - 1) * step + 512 + 2;       // every frame reads all 512 points (window is 0 past L)
-  return (int)((n + 3) & ~3LL);
+static int fused_sig_smem(int step) {
+  const long long n = (long long)(FR - 1) * step + 512;       // every frame reads all 512 points (window is 0 past L)
+  return (int)((n + 7) & ~7LL);
 }
 
-static size_t fused_smem_bytes(int L, int step, int n_mel, int n_packed) {
-  size_t floats = (size_t)fused_sig_smem(L, step) + 512 + 512 /* s_twA */ + 512 /* s_w512 */ + (size_t)P_FLOATS +
-                  SCR_FLOATS + (size_t)((n_packed + 3) & ~3) + 3 * (size_t)n_mel;
-  return floats * 4;
+// every band is padded to a 4-aligned start and an even number of 4-float vectors: < 3 + 7 extra floats per band
+static int fused_w4_floats(int n_mel, int n_packed) { return (n_packed + 10 * n_mel + 3) & ~3; }
+
+static size_t fused_smem_bytes(int step, int n_mel, int n_packed) {
+  size_t floats = (size_t)fused_sig_smem(step) + 512 /* window */ + (size_t)(FR + 1) * P_STRIDE +
+                  2 * (size_t)SCR_FLOAT2 + (size_t)fused_w4_floats(n_mel, n_packed) + 10 * (size_t)n_mel +
+                  (MEL_SLOTS + 4);
+  return 16 + floats * 4;
 }
 
 static bool fused_ok(int L, int step, int nfft, int n_mel, int n_packed) {
   if (nfft != 512 || L > 512 || L < 1 || step < 1) return false;
-  if (n_mel > 256 || FR * n_mel > SCR_FLOATS) return false;
-  return fused_smem_bytes(L, step, n_mel, n_packed) <= 110 * 1024;
+  if (n_mel > 256 || FR * n_mel > 2 * SCR_FLOAT2) return false;
+  return fused_smem_bytes(step, n_mel, n_packed) <= 110 * 1024;
 }
 
 static int check_stft_args(const float* sig, long long B, long long N, int L, int step, int nfft) {
@@ -444,20 +705,43 @@ static int check_stft_args(const float* sig, long long B, long long N, int L, in
   return LBX_OK;
 }
 
-template <int MODE, int PW>
-static int launch_fused_pw(const FusedParams& p, long long B, size_t smem, cudaStream_t st) {
-  LBX_CUDA(cudaFuncSetAttribute(logmel512_kernel<MODE, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(p.T, FR), (unsigned)B);
-  LBX_LAUNCH_PDL((logmel512_kernel<MODE, PW>), grid, dim3(FUSED_THREADS), smem, st, p);
+template <int MODE, int PW, bool IN16>
+static int launch_fused_k(const FusedParams& p, long long n_items, size_t smem, cudaStream_t st) {
+  int dev = 0, n_sm = 0;
+  LBX_CUDA(cudaGetDevice(&dev));
+  LBX_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  LBX_CUDA(cudaFuncSetAttribute(logmel512_kernel<MODE, PW, IN16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // persistent CTAs: up to three per SM (shared memory bound), each walks runs of FR frames with a grid-sized stride
+  const long long slots = (long long)LBX_LM_MIN_CTAS * n_sm;
+  dim3 grid((unsigned)(n_items < slots ? n_items : slots));
+  LBX_LAUNCH_PDL((logmel512_kernel<MODE, PW, IN16>), grid, dim3(FUSED_THREADS), smem, st, p);
   return LBX_OK;
 }
 
+// fills the derived fields (run geometry, staging mode) and dispatches on (power, input type)
 template <int MODE>
-static int launch_fused(const FusedParams& p, long long B, size_t smem, cudaStream_t st) {
+static int launch_fused(FusedParams p, long long B, int n_packed, cudaStream_t st) {
+  p.sig_smem = fused_sig_smem(p.frame_step);
+  p.runs_per_utt = (int)ceil_div(p.T, FR);
+  p.B = (int)B;
+  const long long n_items = B * p.runs_per_utt;
+  p.n_w4 = MODE == 1 ? fused_w4_floats(p.n_mel, n_packed) : 0;
+  const long long run_samples = (long long)FR * p.frame_step;
+  if (p.sig_i16)
+    p.async_ok = (reinterpret_cast<uintptr_t>(p.sig_i16) & 15) == 0 && p.N % 8 == 0 && run_samples % 8 == 0 &&
+                 p.sig_smem <= 2 * FUSED_THREADS * 8;
+  else
+    p.async_ok = (reinterpret_cast<uintptr_t>(p.sig) & 15) == 0 && p.N % 4 == 0 && run_samples % 4 == 0;
+  const size_t smem = fused_smem_bytes(p.frame_step, MODE == 1 ? p.n_mel : 0, MODE == 1 ? n_packed : 0);
   const int pw = pw_mode_of(p.power);
-  if (pw == 2) return launch_fused_pw<MODE, 2>(p, B, smem, st);
-  if (pw == 1) return launch_fused_pw<MODE, 1>(p, B, smem, st);
-  return launch_fused_pw<MODE, 0>(p, B, smem, st);
+  if (p.sig_i16) {
+    if (pw == 2) return launch_fused_k<MODE, 2, true>(p, n_items, smem, st);
+    if (pw == 1) return launch_fused_k<MODE, 1, true>(p, n_items, smem, st);
+    return launch_fused_k<MODE, 0, true>(p, n_items, smem, st);
+  }
+  if (pw == 2) return launch_fused_k<MODE, 2, false>(p, n_items, smem, st);
+  if (pw == 1) return launch_fused_k<MODE, 1, false>(p, n_items, smem, st);
+  return launch_fused_k<MODE, 0, false>(p, n_items, smem, st);
 }
 
 static int launch_generic_stft(const float* sig, long long B, long long N, long long T, int L, int step, int nfft,
@@ -490,9 +774,9 @@ int lbx_spectrogram_f32(const float* sig, long long B, long long N, int frame_le
     FusedParams p{};
     p.sig = sig; p.out = out; p.N = N; p.T = T;
     p.frame_length = frame_length; p.frame_step = frame_step;
-    p.sig_smem = fused_sig_smem(frame_length, frame_step);
     p.power = power;
-    return launch_fused<0>(p, B, fused_smem_bytes(frame_length, frame_step, 0, 0), st);
+    p.utt_pitch = T * N_BINS; p.row_pitch = N_BINS;
+    return launch_fused<0>(p, B, 0, st);
   }
   return launch_generic_stft(sig, B, N, T, frame_length, frame_step, fft_length, power, out, st);
 }
@@ -526,59 +810,75 @@ size_t lbx_logmel_workspace_bytes(long long B, long long N, int frame_length, in
   return (size_t)B * (size_t)T * (size_t)(fft_length / 2 + 1) * sizeof(float);
 }
 
+int lbx_logmel_ex(const lbx_logmel_t* d, void* stream) {
+  LBX_CHECK_ARG(d != nullptr, "NULL descriptor");
+  LBX_CHECK_ARG(d->sig_dtype == LBX_F32 || d->sig_dtype == LBX_I16, "sig_dtype must be LBX_F32 or LBX_I16");
+  LBX_CHECK_ARG(d->out_dtype == LBX_F32 || d->out_dtype == LBX_BF16, "out_dtype must be LBX_F32 or LBX_BF16");
+  int rc = check_stft_args(reinterpret_cast<const float*>(d->sig), d->B, d->N, d->frame_length, d->frame_step,
+                           d->fft_length);
+  if (rc) return rc;
+  LBX_CHECK_ARG(d->n_mel >= 1 && d->n_packed >= 0, "bad n_mel=%d n_packed=%d", d->n_mel, d->n_packed);
+  LBX_CHECK_ARG(d->log_mode == 0 || d->log_mode == 1, "log_mode must be 0 or 1");
+  LBX_CHECK_ARG(d->out_lo == nullptr || d->out_dtype == LBX_BF16, "out_lo needs a bf16 output");
+  const long long T = lbx_num_frames(d->N, d->frame_length, d->frame_step);
+  if (d->B == 0 || T == 0) return LBX_OK;
+  LBX_CHECK_ARG(d->out && d->band_start && d->band_len && d->band_off && d->band_w, "NULL pointer argument");
+  const int row_pitch = d->out_row_pitch > 0 ? d->out_row_pitch : d->n_mel;
+  const long long utt_pitch = d->out_utt_pitch > 0 ? d->out_utt_pitch : T * row_pitch;
+  LBX_CHECK_ARG(row_pitch >= d->n_mel && utt_pitch >= T * row_pitch, "output pitches too small (row %d, utterance %lld)",
+                row_pitch, utt_pitch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fused_ok(d->frame_length, d->frame_step, d->fft_length, d->n_mel, d->n_packed)) {
+    FusedParams p{};
+    if (d->sig_dtype == LBX_I16) p.sig_i16 = reinterpret_cast<const short*>(d->sig);
+    else p.sig = reinterpret_cast<const float*>(d->sig);
+    p.N = d->N; p.T = T;
+    p.frame_length = d->frame_length; p.frame_step = d->frame_step;
+    p.power = d->power;
+    p.n_mel = d->n_mel; p.band_start = d->band_start; p.band_len = d->band_len; p.band_off = d->band_off;
+    p.band_w = d->band_w; p.log_mode = d->log_mode; p.eps = d->eps;
+    p.out = d->out; p.out_lo = d->out_lo; p.out_bf16 = d->out_dtype == LBX_BF16;
+    p.utt_pitch = utt_pitch; p.row_pitch = row_pitch;
+    return launch_fused<1>(p, d->B, d->n_packed, st);
+  }
+  if (d->sig_dtype != LBX_F32 || d->out_dtype != LBX_F32 || row_pitch != d->n_mel || utt_pitch != T * row_pitch)
+    return set_error(LBX_EUNSUPPORTED, "16-bit PCM input, bf16 output and strided output are served by the fused "
+                                       "512-point configuration only");
+  const int K = d->fft_length / 2 + 1;
+  const size_t need = (size_t)d->B * (size_t)T * (size_t)K * sizeof(float);
+  if (d->workspace == nullptr || d->workspace_bytes < need)
+    return set_error(LBX_EWORKSPACE, "logmel needs a %zu-byte workspace for this configuration (got %zu)", need,
+                     d->workspace_bytes);
+  rc = launch_generic_stft(reinterpret_cast<const float*>(d->sig), d->B, d->N, T, d->frame_length, d->frame_step,
+                           d->fft_length, d->power, (float*)d->workspace, st);
+  if (rc) return rc;
+  return lbx_linear_to_mel_f32((const float*)d->workspace, d->B * T, K, d->n_mel, d->band_start, d->band_len, d->band_off,
+                               d->band_w, d->n_packed, d->log_mode, d->eps, (float*)d->out, stream);
+}
+
 int lbx_logmel_f32(const float* sig, long long B, long long N, int frame_length, int frame_step, int fft_length,
                    float power, int n_mel, const int* band_start, const int* band_len, const int* band_off,
                    const float* band_w, int n_packed, int log_mode, float eps, float* out, void* workspace,
                    size_t workspace_bytes, void* stream) {
-  int rc = check_stft_args(sig, B, N, frame_length, frame_step, fft_length);
-  if (rc) return rc;
-  LBX_CHECK_ARG(n_mel >= 1 && n_packed >= 0, "bad n_mel=%d n_packed=%d", n_mel, n_packed);
-  LBX_CHECK_ARG(log_mode == 0 || log_mode == 1, "log_mode must be 0 or 1");
-  const long long T = lbx_num_frames(N, frame_length, frame_step);
-  if (B == 0 || T == 0) return LBX_OK;
-  LBX_CHECK_ARG(out && band_start && band_len && band_off && band_w, "NULL pointer argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (fused_ok(frame_length, frame_step, fft_length, n_mel, n_packed)) {
-    FusedParams p{};
-    p.sig = sig; p.out = out; p.N = N; p.T = T;
-    p.frame_length = frame_length; p.frame_step = frame_step;
-    p.sig_smem = fused_sig_smem(frame_length, frame_step);
-    p.power = power;
-    p.n_mel = n_mel; p.band_start = band_start; p.band_len = band_len; p.band_off = band_off; p.band_w = band_w;
-    p.n_packed = n_packed; p.log_mode = log_mode; p.eps = eps;
-    return launch_fused<1>(p, B, fused_smem_bytes(frame_length, frame_step, n_mel, n_packed), st);
-  }
-  const int K = fft_length / 2 + 1;
-  const size_t need = (size_t)B * (size_t)T * (size_t)K * sizeof(float);
-  if (workspace == nullptr || workspace_bytes < need)
-    return set_error(LBX_EWORKSPACE, "logmel needs a %zu-byte workspace for this configuration (got %zu)", need,
-                     workspace_bytes);
-  rc = launch_generic_stft(sig, B, N, T, frame_length, frame_step, fft_length, power, (float*)workspace, st);
-  if (rc) return rc;
-  return lbx_linear_to_mel_f32((const float*)workspace, B * T, K, n_mel, band_start, band_len, band_off, band_w,
-                               n_packed, log_mode, eps, out, stream);
+  lbx_logmel_t d{};
+  d.sig = sig; d.sig_dtype = LBX_F32; d.B = B; d.N = N;
+  d.frame_length = frame_length; d.frame_step = frame_step; d.fft_length = fft_length; d.power = power;
+  d.n_mel = n_mel; d.band_start = band_start; d.band_len = band_len; d.band_off = band_off; d.band_w = band_w;
+  d.n_packed = n_packed; d.log_mode = log_mode; d.eps = eps;
+  d.out = out; d.out_dtype = LBX_F32; d.workspace = workspace; d.workspace_bytes = workspace_bytes;
+  return lbx_logmel_ex(&d, stream);
 }
 
 int lbx_logmel_i16(const short* pcm, long long B, long long N, int frame_length, int frame_step, int fft_length,
                    float power, int n_mel, const int* band_start, const int* band_len, const int* band_off,
                    const float* band_w, int n_packed, int log_mode, float eps, float* out, void* stream) {
-  int rc = check_stft_args(reinterpret_cast<const float*>(pcm), B, N, frame_length, frame_step, fft_length);
-  if (rc) return rc;
-  LBX_CHECK_ARG(n_mel >= 1 && n_packed >= 0, "bad n_mel=%d n_packed=%d", n_mel, n_packed);
-  LBX_CHECK_ARG(log_mode == 0 || log_mode == 1, "log_mode must be 0 or 1");
-  const long long T = lbx_num_frames(N, frame_length, frame_step);
-  if (B == 0 || T == 0) return LBX_OK;
-  LBX_CHECK_ARG(out && band_start && band_len && band_off && band_w, "NULL pointer argument");
-  if (!fused_ok(frame_length, frame_step, fft_length, n_mel, n_packed))
-    return set_error(LBX_EUNSUPPORTED, "16-bit PCM input is served by the fused 512-point configuration only");
-  FusedParams p{};
-  p.sig = nullptr; p.sig_i16 = pcm; p.out = out; p.N = N; p.T = T;
-  p.frame_length = frame_length; p.frame_step = frame_step;
-  p.sig_smem = fused_sig_smem(frame_length, frame_step);
-  p.power = power;
-  p.n_mel = n_mel; p.band_start = band_start; p.band_len = band_len; p.band_off = band_off; p.band_w = band_w;
-  p.n_packed = n_packed; p.log_mode = log_mode; p.eps = eps;
-  return launch_fused<1>(p, B, fused_smem_bytes(frame_length, frame_step, n_mel, n_packed), (cudaStream_t)stream);
+  lbx_logmel_t d{};
+  d.sig = pcm; d.sig_dtype = LBX_I16; d.B = B; d.N = N;
+  d.frame_length = frame_length; d.frame_step = frame_step; d.fft_length = fft_length; d.power = power;
+  d.n_mel = n_mel; d.band_start = band_start; d.band_len = band_len; d.band_off = band_off; d.band_w = band_w;
+  d.n_packed = n_packed; d.log_mode = log_mode; d.eps = eps;
+  d.out = out; d.out_dtype = LBX_F32;
+  return lbx_logmel_ex(&d, stream);
 }
 
 int lbx_power_to_db_f32(const float* S, long long numel, float amin, float top_db, float* out, void* workspace,

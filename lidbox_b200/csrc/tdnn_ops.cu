@@ -28,14 +28,22 @@ __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned 
   return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// advances a device-side call counter (SpatialDropout1D mask index): a kernel, so that CUDA-graph replays advance it too
+__global__ void counter_tick_kernel(unsigned long long* counter) {
+  LBX_PDL_SYNC();
+  *counter += 1ULL;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // features [B,T,F] f32 -> zero-left-padded bf16 activation rows (hi [+ lo]); optional SpatialDropout1D
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ x, long long B, int T, int F,
                                                        bf16* __restrict__ hi, bf16* __restrict__ lo, int rows_per_utt,
                                                        int row_off, int pitch, float drop_rate,
-                                                       unsigned long long seed) {
+                                                       unsigned long long seed,
+                                                       const unsigned long long* __restrict__ seed_counter) {
   LBX_PDL_SYNC();
+  if (seed_counter != nullptr) seed += 7919ULL * *seed_counter;
   const long long total = B * T * (long long)pitch;
   const float keep_scale = drop_rate > 0.0f ? 1.0f / (1.0f - drop_rate) : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -60,8 +68,11 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) pack_rows_vec_kernel(const float* __restrict__ x, long long B, int T, int F,
                                                            bf16* __restrict__ hi, bf16* __restrict__ lo,
                                                            int rows_per_utt, int row_off, int pitch, float drop_rate,
-                                                           unsigned long long seed, int x_vec) {
+                                                           unsigned long long seed,
+                                                           const unsigned long long* __restrict__ seed_counter,
+                                                           int x_vec) {
   LBX_PDL_SYNC();
+  if (seed_counter != nullptr) seed += 7919ULL * *seed_counter;
   const int gpr = pitch >> 3;                       // 8-feature groups per row
   const long long total = B * T * (long long)gpr;
   const float keep_scale = drop_rate > 0.0f ? 1.0f / (1.0f - drop_rate) : 1.0f;
@@ -200,11 +211,15 @@ __global__ void __launch_bounds__(128) logsoftmax_xent_kernel(const float* __res
   s = warp_sum(s);
   const float lse = mx + logf(s);
   const int label = y ? y[b] : -1;
+  // a label outside [0, n) raises in the reference (tf.gather / sparse cross-entropy); here the sample gets a NaN
+  // loss and a zero gradient instead of a silent wrong value
+  const bool bad_label = y != nullptr && (label < 0 || label >= n);
+  if (bad_label && loss && lane == 0) loss[b] = __int_as_float(0x7fc00000);
   for (int j = lane; j < n; j += 32) {
     const float lp = row[j] - lse;
     if (logp) logp[b * n + j] = lp;
     if (dlogits) {
-      const bf16 gq = __float2bfloat16_rn((expf(lp) - (j == label ? 1.0f : 0.0f)) * grad_scale);
+      const bf16 gq = __float2bfloat16_rn(bad_label ? 0.0f : (expf(lp) - (j == label ? 1.0f : 0.0f)) * grad_scale);
       dlogits[b * dl_pitch + j] = gq;
       if (dbias) atomicAdd(dbias + j, __bfloat162float(gq));
     }
@@ -374,7 +389,10 @@ __global__ void __launch_bounds__(128) ap_loss_kernel(const float* __restrict__ 
     ss = warp_sum(ss);
     inv_norm = rsqrtf(fmaxf(ss, 1e-12f));
   }
-  const int label = y[b];
+  int label = y[b];
+  // labels outside [0, N) raise in the reference (tf.gather); here: NaN loss, zero gradient, no out-of-bounds read
+  const bool bad_label = label < 0 || label >= N;
+  if (bad_label) label = 0;
   const float zy = row[label] * inv_norm;
   const float theta_y = acosf(zy);
   float l = 0.0f, dty = 0.0f, dot = 0.0f;     // dot = z . dz (for the normalisation backward)
@@ -400,11 +418,11 @@ __global__ void __launch_bounds__(128) ap_loss_kernel(const float* __restrict__ 
   }
   l = warp_sum(l);
   dty = warp_sum(dty);
-  if (loss && lane == 0) loss[b] = l;
+  if (loss && lane == 0) loss[b] = bad_label ? __int_as_float(0x7fc00000) : l;
   if (grad_f32 == nullptr && grad_bf16 == nullptr) return;
   const float dzy = -dty * rsqrtf(fmaxf(1.0f - zy * zy, 0.0f));
   dot = warp_sum(dot) + dzy * zy;
-  const float gl = (gloss ? gloss[b] : 1.0f) * grad_scale;
+  const float gl = bad_label ? 0.0f : (gloss ? gloss[b] : 1.0f) * grad_scale;
   for (int j = lane; j < D; j += 32) {
     const float z = row[j] * inv_norm;
     float dz = 0.0f;
@@ -989,8 +1007,15 @@ using namespace lbx;
 
 extern "C" {
 
+int lbx_counter_tick(unsigned long long* counter_dev, void* stream) {
+  LBX_CHECK_ARG(counter_dev != nullptr, "NULL counter");
+  LBX_LAUNCH_PDL(counter_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, counter_dev);
+  return LBX_OK;
+}
+
 int lbx_pack_rows_bf16(const float* x, long long B, int T, int F, void* hi, void* lo, int rows_per_utt, int row_off,
-                       int pitch, float drop_rate, unsigned long long seed, void* stream) {
+                       int pitch, float drop_rate, unsigned long long seed, const unsigned long long* seed_counter_dev,
+                       void* stream) {
   LBX_CHECK_ARG(B >= 0 && T >= 0 && F >= 1 && pitch >= F, "bad shape B=%lld T=%d F=%d pitch=%d", B, T, F, pitch);
   LBX_CHECK_ARG(row_off >= 0 && row_off + T <= rows_per_utt, "rows do not fit: off=%d T=%d rows_per_utt=%d", row_off, T,
                 rows_per_utt);
@@ -1001,11 +1026,11 @@ int lbx_pack_rows_bf16(const float* x, long long B, int T, int F, void* hi, void
     const int x_vec = F % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     LBX_LAUNCH_PDL(pack_rows_vec_kernel, dim3(grid_for(B * T * (long long)(pitch / 8), 256)), dim3(256), 0,
                    (cudaStream_t)stream, x, B, T, F, (bf16*)hi, (bf16*)lo, rows_per_utt, row_off, pitch, drop_rate, seed,
-                   x_vec);
+                   seed_counter_dev, x_vec);
     return LBX_OK;
   }
   LBX_LAUNCH_PDL(pack_rows_kernel, dim3(grid_for(B * T * (long long)pitch, 256)), dim3(256), 0, (cudaStream_t)stream, x, B,
-                 T, F, (bf16*)hi, (bf16*)lo, rows_per_utt, row_off, pitch, drop_rate, seed);
+                 T, F, (bf16*)hi, (bf16*)lo, rows_per_utt, row_off, pitch, drop_rate, seed, seed_counter_dev);
   return LBX_OK;
 }
 

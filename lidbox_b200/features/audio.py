@@ -5,6 +5,8 @@ scalars or torch tensors (as the reference's tests pass them, tests/test_feature
 results are float32 torch tensors on the CUDA device.  Everything numeric is one C-ABI call into hand-written
 sm_100a kernels (include/lidbox_b200.h).
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -74,11 +76,17 @@ def logmelspectrograms(signals, sample_rate, frame_length_ms=25, frame_step_ms=1
                        num_mel_bins=40, fmin=0.0, fmax=8000.0, log=True, eps=1e-6, out=None):
     """Fused spectrograms -> linear_to_mel -> ln(x + 1e-6) (the chain of lidbox/data/tf_utils.py:172-178) in one
     kernel: [B, N] -> [B, T, num_mel_bins].  Not a reference name: it is what the map stage calls.
-    An int16 torch tensor is taken as 16-bit PCM and decoded on the fly (x / 32768, as read_wav does)."""
+    An int16 torch tensor is taken as 16-bit PCM and decoded on the fly (x / 32768, as read_wav does).
+    `out` may be a float32 tensor [B, T, num_mel_bins], or the feature sink of a model
+    (`XVector.feature_sink(B, T)`): the rows are then written as bf16 straight into the zero-left-padded activation
+    buffer of the first frame layer (no fp32 round trip, no packing pass) and the sink is returned."""
+    dev = _lib.require_cuda()
     if isinstance(signals, torch.Tensor) and signals.dtype == torch.int16:
-        return _logmel_pcm16(signals, sample_rate, frame_length_ms, frame_step_ms, power, fft_length, num_mel_bins,
-                             fmin, fmax, log, eps, out)
-    sig = _as_device_f32(signals, 2, "signals")
+        if signals.dim() != 2:
+            raise ValueError("signals must have rank 2, got shape %s" % (tuple(signals.shape),))
+        sig, sig_dtype = signals.to(dev, non_blocking=True).contiguous(), _lib.I16
+    else:
+        sig, sig_dtype = _as_device_f32(signals, 2, "signals"), _lib.F32
     L = ms_to_frames(sample_rate, frame_length_ms)
     step = ms_to_frames(sample_rate, frame_step_ms)
     B, N = sig.shape
@@ -86,34 +94,28 @@ def logmelspectrograms(signals, sample_rate, frame_length_ms=25, frame_step_ms=1
     T = int(lib.lbx_num_frames(N, L, step)) if L >= 1 and step >= 1 else 0
     K = int(fft_length) // 2 + 1
     bands = mel_ops.mel_bands(num_mel_bins, K, sample_rate, fmin, fmax, sig.device)
-    if out is None:
-        out = torch.empty((B, T, int(num_mel_bins)), dtype=torch.float32, device=sig.device)
-    ws_bytes = int(lib.lbx_logmel_workspace_bytes(B, N, L, step, int(fft_length), bands.n_mel))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=sig.device) if ws_bytes else None
-    _lib.check(lib.lbx_logmel_f32(_lib.ptr(sig), B, N, L, step, int(fft_length), float(power), bands.n_mel,
-                                  _lib.ptr(bands.start), _lib.ptr(bands.len), _lib.ptr(bands.off), _lib.ptr(bands.w),
-                                  bands.n_packed, 1 if log else 0, float(eps), _lib.ptr(out), _lib.ptr(ws), ws_bytes,
-                                  _lib.stream_ptr(sig.device)))
-    return out
-
-
-def _logmel_pcm16(pcm, sample_rate, frame_length_ms, frame_step_ms, power, fft_length, num_mel_bins, fmin, fmax, log,
-                  eps, out):
-    if pcm.dim() != 2:
-        raise ValueError("signals must have rank 2, got shape %s" % (tuple(pcm.shape),))
-    pcm = pcm.to(_lib.require_cuda(), non_blocking=True).contiguous()
-    L = ms_to_frames(sample_rate, frame_length_ms)
-    step = ms_to_frames(sample_rate, frame_step_ms)
-    B, N = pcm.shape
-    lib = _lib.lib()
-    T = int(lib.lbx_num_frames(N, L, step)) if L >= 1 and step >= 1 else 0
-    bands = mel_ops.mel_bands(num_mel_bins, int(fft_length) // 2 + 1, sample_rate, fmin, fmax, pcm.device)
-    if out is None:
-        out = torch.empty((B, T, int(num_mel_bins)), dtype=torch.float32, device=pcm.device)
-    _lib.check(lib.lbx_logmel_i16(_lib.ptr(pcm), B, N, L, step, int(fft_length), float(power), bands.n_mel,
-                                  _lib.ptr(bands.start), _lib.ptr(bands.len), _lib.ptr(bands.off), _lib.ptr(bands.w),
-                                  bands.n_packed, 1 if log else 0, float(eps), _lib.ptr(out),
-                                  _lib.stream_ptr(pcm.device)))
+    d = _lib.LogmelDesc()
+    d.sig, d.sig_dtype, d.B, d.N = sig.data_ptr(), sig_dtype, B, N
+    d.frame_length, d.frame_step, d.fft_length, d.power = L, step, int(fft_length), float(power)
+    d.n_mel, d.n_packed = bands.n_mel, bands.n_packed
+    d.band_start, d.band_len, d.band_off, d.band_w = (bands.start.data_ptr(), bands.len.data_ptr(),
+                                                      bands.off.data_ptr(), bands.w.data_ptr())
+    d.log_mode, d.eps = 1 if log else 0, float(eps)
+    ws = None
+    if hasattr(out, "sink_spec"):
+        hi, lo, utt_pitch, row_pitch = out.sink_spec(B, T, bands.n_mel)
+        d.out, d.out_lo, d.out_dtype, d.out_utt_pitch, d.out_row_pitch = hi, lo, _lib.BF16, utt_pitch, row_pitch
+    else:
+        if out is None:
+            out = torch.empty((B, T, int(num_mel_bins)), dtype=torch.float32, device=sig.device)
+        elif tuple(out.shape) != (B, T, int(num_mel_bins)) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 tensor of shape %s" % ((B, T, int(num_mel_bins)),))
+        d.out, d.out_dtype = out.data_ptr(), _lib.F32
+        ws_bytes = int(lib.lbx_logmel_workspace_bytes(B, N, L, step, int(fft_length), bands.n_mel))
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=sig.device)
+            d.workspace, d.workspace_bytes = ws.data_ptr(), ws_bytes
+    _lib.check(lib.lbx_logmel_ex(ctypes.byref(d), _lib.stream_ptr(sig.device)))
     return out
 
 

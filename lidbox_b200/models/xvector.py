@@ -69,6 +69,27 @@ class GlobalMeanStddevPooling1D:
         return out
 
 
+class FeatureSink:
+    """Handle of the first frame layer's activation buffer for one (B, T): `features.audio.logmelspectrograms(...,
+    out=sink)` writes its bf16 rows straight into it (zero-left-padded NWC layout) and the model then
+    consumes the sink instead of a [B, T, F] tensor — the fp32 feature tensor and the packing pass never exist."""
+
+    def __init__(self, model, bufs, B, T, training):
+        self.model, self.bufs, self.B, self.T, self.training = model, bufs, B, T, training
+        self.shape = (B, T, model.F)
+
+    def sink_spec(self, B, T, n_feat):
+        """(hi pointer, lo pointer or None, utterance pitch, row pitch) in elements — see lbx_logmel_t."""
+        m, geo = self.model, self.bufs["geo"]
+        if (B, T, n_feat) != (self.B, self.T, m.F):
+            raise ValueError("feature sink was created for %s, got features of shape %s" %
+                             ((self.B, self.T, m.F), (B, T, n_feat)))
+        off = geo.pad[0] * m.Fp * 2                            # bytes: k-1 zero rows in front of every utterance
+        hi = self.bufs["X"][0].data_ptr() + off
+        lo = self.bufs["X_lo"][0].data_ptr() + off if self.bufs["X_lo"][0] is not None else None
+        return hi, lo, geo.Tpad[0] * m.Fp, m.Fp
+
+
 class _Geometry:
     """Row geometry shared by all activation buffers for one (T) — see DESIGN.md §Data layout."""
 
@@ -117,7 +138,7 @@ class XVector:
         self.output_name = output_name                     # "outputs" (xvector.py:64) / "output" (xvector_extended.py:40)
         self.device = _lib.require_cuda(device)
         self._dropout_seed = 0x5EED if seed is None else int(seed)
-        self._dropout_calls = 0
+        self._dropout_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._build_params(seed)
         self._bufs = {}
         self._adam = None
@@ -227,11 +248,14 @@ class XVector:
     # ------------------------------------------------------------------ buffers
     def _buffers(self, B, T, training):
         key = (B, T, self.precision, bool(training))
-        bufs = self._bufs.get(key)
+        bufs = self._bufs.pop(key, None)
         if bufs is not None:
+            self._bufs[key] = bufs                 # most recently used last
             return bufs
-        if len(self._bufs) > 4:
-            self._bufs.clear()
+        # least-recently-used eviction; sets captured by a CUDA graph (GraphedTrainStep) or handed out as a feature
+        # sink are pinned: their raw pointers live on outside this cache
+        for k in [k for k, v in self._bufs.items() if not v.get("pinned")][:max(0, len(self._bufs) - 4)]:
+            del self._bufs[k]
         geo = _Geometry(T, self.frames)
         dev, bf = self.device, torch.bfloat16
         split = self.precision == "fp32"
@@ -268,7 +292,19 @@ class XVector:
         return bufs
 
     # ------------------------------------------------------------------ forward
+    def feature_sink(self, B, T, training=False):
+        """Buffer handle for direct feature hand-off (see FeatureSink).  The buffer set stays allocated (pinned)."""
+        if training and self.channel_dropout_rate > 0:
+            raise NotImplementedError("SpatialDropout1D is applied by the packing pass; feed [B,T,F] tensors instead")
+        bufs = self._buffers(int(B), int(T), bool(training))
+        bufs["pinned"] = True
+        return FeatureSink(self, bufs, int(B), int(T), bool(training))
+
     def _prepare_input(self, x):
+        if isinstance(x, FeatureSink):
+            if x.model is not self:
+                raise ValueError("feature sink belongs to another model")
+            return x
         if not isinstance(x, torch.Tensor):
             x = torch.as_tensor(np.asarray(x))
         if x.dim() != 3 or x.shape[2] != self.F:
@@ -281,14 +317,21 @@ class XVector:
         lib, st = _lib.lib(), _lib.stream_ptr(self.device)
         geo = bufs["geo"]
         B, T, _ = x.shape
+        if isinstance(x, FeatureSink) and x.bufs is not bufs:
+            raise ValueError("feature sink was created with training=%s" % x.training)
         split = self.precision == "fp32"
         self._refresh(need_lo=split)
         n = len(self.frames)
         rate = self.channel_dropout_rate if training else 0.0
-        self._dropout_calls += 1
-        _lib.check(lib.lbx_pack_rows_bf16(_lib.ptr(x), B, T, self.F, _lib.ptr(bufs["X"][0]), _lib.ptr(bufs["X_lo"][0]),
-                                          geo.Tpad[0], geo.pad[0], self.Fp, rate,
-                                          self._dropout_seed + 7919 * self._dropout_calls, st))
+        if not isinstance(x, FeatureSink):
+            # the dropout mask is keyed on (seed, device-side call counter): the counter is advanced by a kernel, so
+            # replays of a captured CUDA graph draw a fresh mask every step (a host-side counter would be baked in)
+            _lib.check(lib.lbx_pack_rows_bf16(_lib.ptr(x), B, T, self.F, _lib.ptr(bufs["X"][0]),
+                                              _lib.ptr(bufs["X_lo"][0]), geo.Tpad[0], geo.pad[0], self.Fp, rate,
+                                              self._dropout_seed, _lib.ptr(self._dropout_counter) if rate > 0 else None,
+                                              st))
+            if rate > 0:
+                _lib.check(lib.lbx_counter_tick(_lib.ptr(self._dropout_counter), st))
         for L in range(n):
             ly = self.layers[L]
             last = L == n - 1
@@ -634,11 +677,12 @@ class XVector:
                 raise ValueError("the sharded optimizer was enabled for a different process group")
             losses = self.loss_and_grads(x, y, loss=loss, global_batch=B * world, process_group=None, **kw)
             self._apply_sharded()
-            return losses
-        losses = self.loss_and_grads(x, y, loss=loss, global_batch=B * world,
-                                     process_group=process_group if world > 1 else None, **kw)
-        self.apply_gradients()
-        return losses
+        else:
+            losses = self.loss_and_grads(x, y, loss=loss, global_batch=B * world,
+                                         process_group=process_group if world > 1 else None, **kw)
+            self.apply_gradients()
+        # the loss buffer is reused by the next step: hand out a copy (inside a graph capture the static buffer itself)
+        return losses if torch.cuda.is_current_stream_capturing() else losses.clone()
 
 
 class GraphedTrainStep:
@@ -678,6 +722,10 @@ class GraphedTrainStep:
                 body()
         torch.cuda.current_stream(model.device).wait_stream(side)
         torch.cuda.synchronize(model.device)
+        # the graph holds raw pointers into the activation / gradient buffers: keep every set alive and un-evictable
+        self._keep = list(model._bufs.values())
+        for bufs in self._keep:
+            bufs["pinned"] = True
         self.graph = torch.cuda.CUDAGraph()
         n0 = lib.lbx_launch_count()
         with torch.cuda.graph(self.graph):

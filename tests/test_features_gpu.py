@@ -311,3 +311,74 @@ def test_mfcc_map_stage(built_lib):
     lm = rng.standard_normal((2, 5, 40)).astype(np.float32)
     np.testing.assert_allclose(a.mfccs_from_log_mel_spectrograms(lm).cpu().numpy(),
                                O.mfccs_from_log_mel_spectrograms(lm), rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: persistent packed-fp32 kernel — staging paths, multi-pass CTAs, direct bf16 hand-off, host entry point
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N", [(3, 16000), (2, 16001), (5, 16002), (1, 16399), (700, 4000), (2, 400), (1, 559),
+                                 (1, 560)])
+def test_logmel_staging_paths_and_persistent_passes(audio, B, N):
+    """N % 4 == 0 takes the bulk-copy (TMA) prefetch path, other lengths the plain-load fallback; B = 700 x 0.25 s
+    gives every persistent CTA several runs (more items than 3 CTAs x 148 SMs); N = 400 / 559 / 560 are the
+    one-frame and two-frame edges."""
+    sig = _signals(B, N, seed=N)
+    ref = O.logmel(sig, 16000, dtype=np.float64)
+    out = audio.logmelspectrograms(sig, 16000).cpu().numpy()
+    assert out.shape == ref.shape
+    assert_logmel_close(out, ref)
+
+
+@pytest.mark.parametrize("N", [16000, 16008, 16004, 16001])
+def test_logmel_pcm16_staging_paths(audio, N):
+    """16-bit PCM: N % 8 == 0 -> bulk copy of the raw samples + in-place expansion; otherwise plain loads."""
+    pcm = np.clip(np.round(_signals(3, N, seed=7) * 32768.0), -32768, 32767).astype(np.int16)
+    ref = O.logmel(pcm.astype(np.float32) / 32768.0, 16000, dtype=np.float64)
+    out = audio.logmelspectrograms(torch.from_numpy(pcm), 16000).cpu().numpy()
+    assert_logmel_close(out, ref)
+
+
+def test_logmel_nonfinite_input_stays_in_its_utterance(audio):
+    """Persistent CTAs reuse the staging buffer: a NaN in one utterance must not leak into another one's frames."""
+    sig = _signals(40, 8000, seed=3)
+    sig[17, 4000] = np.nan
+    out = audio.logmelspectrograms(sig, 16000).cpu().numpy()
+    bad = ~np.isfinite(out).all(axis=(1, 2))
+    assert bad[17] and bad.sum() == 1
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_logmel_direct_handoff_equals_packing_pass(audio, precision):
+    """logmelspectrograms(out=model.feature_sink(B, T)) writes bf16 rows straight into the first frame layer's
+    buffer; the model output must be bit-identical to feeding the fp32 features through the packing pass."""
+    from lidbox_b200.models import xvector
+    sig = _signals(6, 16000, seed=11)
+    m = xvector.create((98, 40), 5, precision=precision, seed=1)
+    feats = audio.logmelspectrograms(sig, 16000)
+    ref = m(feats).cpu().numpy()
+    m._buffers(6, 98, False)["X"][0].zero_()
+    sink = audio.logmelspectrograms(sig, 16000, out=m.feature_sink(6, 98))
+    out = m(sink).cpu().numpy()
+    np.testing.assert_array_equal(out, ref)
+    pcm = torch.from_numpy(np.clip(np.round(sig * 32768.0), -32768, 32767).astype(np.int16))
+    out16 = m(audio.logmelspectrograms(pcm, 16000, out=m.feature_sink(6, 98))).cpu().numpy()
+    ref16 = m(audio.logmelspectrograms(pcm, 16000)).cpu().numpy()
+    np.testing.assert_array_equal(out16, ref16)
+
+
+def test_logmel_host_entry_point(audio, built_lib):
+    """lbx_logmel_f32_host: pageable host signals in, host log-mel out (the binding a non-torch caller uses)."""
+    import ctypes
+    from lidbox_b200 import _lib
+    sig = _signals(3, 16000, seed=5)
+    T = 98
+    out = np.empty((3, T, 40), np.float32)
+    d_sig = torch.empty((3, 16000), dtype=torch.float32, device="cuda")
+    d_out = torch.empty((3, T, 40), dtype=torch.float32, device="cuda")
+    d_tab = torch.empty(1 << 16, dtype=torch.uint8, device="cuda")
+    rc = _lib.lib().lbx_logmel_f32_host(sig.ctypes.data_as(ctypes.c_void_p), 3, 16000, 16000, 25, 10, 512, 2.0, 40, 0.0,
+                                        8000.0, 1, 1e-6, out.ctypes.data_as(ctypes.c_void_p), _lib.ptr(d_sig),
+                                        _lib.ptr(d_out), _lib.ptr(d_tab), d_tab.numel(),
+                                        _lib.stream_ptr(d_sig.device))
+    _lib.check(rc)
+    assert_logmel_close(out, O.logmel(sig, 16000, dtype=np.float64))

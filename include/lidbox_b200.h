@@ -117,6 +117,9 @@ int lbx_logmel_ex(const lbx_logmel_t* d, void* stream);
 int lbx_power_to_db_f32(const float* S, long long numel, float amin, float top_db, float* out, void* workspace,
                         void* stream);
 
+/* lidbox/features/audio.py:177-181  db_to_power(): pow(10, S / 20), elementwise */
+int lbx_db_to_power_f32(const float* S, long long numel, float* out, void* stream);
+
 /* tf.debugging.assert_all_finite (tf_utils.py:173-194): writes 1 to *flag_dev (int32, device) if any element is
  * NaN/Inf, leaves it untouched otherwise (caller zeroes it first). */
 int lbx_check_finite_f32(const float* x, long long numel, int* flag_dev, void* stream);

@@ -58,6 +58,7 @@ SIGNATURES = {
                                c_float, _P, _P]),
     "lbx_logmel_ex": (c_int, [ctypes.POINTER(LogmelDesc), _P]),
     "lbx_power_to_db_f32": (c_int, [_P, c_ll, c_float, c_float, _P, _P, _P]),
+    "lbx_db_to_power_f32": (c_int, [_P, c_ll, _P, _P]),
     "lbx_check_finite_f32": (c_int, [_P, c_ll, _P, _P]),
     "lbx_normalize_axis_f32": (c_int, [_P, _P, c_ll, c_ll, c_ll, c_int, c_float, c_float, _P]),
     "lbx_feature_scaling_all_f32": (c_int, [_P, _P, c_ll, c_float, c_float, _P, _P]),

@@ -658,6 +658,12 @@ __global__ void __launch_bounds__(256) ptdb_map_kernel(const float* __restrict__
   }
 }
 
+// db_to_power (audio.py:177-181): pow(10, S / 20)
+__global__ void __launch_bounds__(256) db_to_power_kernel(const float* __restrict__ S, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = powf(10.0f, __ldg(S + i) / 20.0f);
+}
+
 __global__ void __launch_bounds__(256) check_finite_kernel(const float* __restrict__ x, long long n, int* flag) {
   bool bad = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -895,6 +901,16 @@ int lbx_power_to_db_f32(const float* S, long long numel, float amin, float top_d
   ptdb_max_kernel<<<blocks, 256, 0, st>>>(S, numel, amin, ws);
   LBX_LAUNCH_CHECK();
   ptdb_map_kernel<<<blocks, 256, 0, st>>>(S, out, numel, amin, top_db, ws);
+  LBX_LAUNCH_CHECK();
+  return LBX_OK;
+}
+
+int lbx_db_to_power_f32(const float* S, long long numel, float* out, void* stream) {
+  LBX_CHECK_ARG(numel >= 0, "negative numel");
+  if (numel == 0) return LBX_OK;
+  LBX_CHECK_ARG(S && out, "NULL pointer argument");
+  const int blocks = (int)min((long long)148 * 8, ceil_div(numel, 256));
+  db_to_power_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(S, out, numel);
   LBX_LAUNCH_CHECK();
   return LBX_OK;
 }

@@ -28,8 +28,6 @@ def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_
     if feattype in ("melspectrogram", "logmelspectrogram"):
         X = audio_features.logmelspectrograms(sig, sample_rate, log=(feattype == "logmelspectrogram"), **spec_kwargs,
                                               **melspec_kwargs)
-    elif feattype == "spectrogram":
-        X = audio_features.spectrograms(sig, sample_rate, **spec_kwargs)
     elif feattype == "db_spectrogram":
         X = audio_features.spectrograms(sig, sample_rate, **spec_kwargs)
         if check_finite:
@@ -43,9 +41,11 @@ def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_
         X = audio_features.mfccs_from_log_mel_spectrograms(X, mfcc_kwargs.get("coef_begin", 1),
                                                            mfcc_kwargs.get("coef_end", 13))   # tf_utils.py:181-185
     else:
-        raise ValueError("unknown feature type " + repr(feattype))
+        # "spectrogram" and, exactly like the reference's if/elif chain (tf_utils.py:172-188), ANY other feature type
+        # string: the power spectrogram is returned unchanged, no error is raised
+        X = audio_features.spectrograms(sig, sample_rate, **spec_kwargs)
     if check_finite:
-        audio_features.assert_all_finite(X, feattype + " failed")
+        audio_features.assert_all_finite(X, str(feattype) + " failed")
     if feat_scale_kwargs:
         X = features.feature_scaling(X, **feat_scale_kwargs)                      # tf_utils.py:189-191
         if check_finite:

@@ -132,6 +132,14 @@ def mfccs_from_log_mel_spectrograms(log_mel, coef_begin=0, coef_end=None):
     return out
 
 
+def db_to_power(S):
+    """lidbox/features/audio.py:177-181: pow(10, S / 20) on a rank-3 float32 tensor."""
+    S = _as_device_f32(S, 3, "S")
+    out = torch.empty_like(S)
+    _lib.check(_lib.lib().lbx_db_to_power_f32(_lib.ptr(S), S.numel(), _lib.ptr(out), _lib.stream_ptr(S.device)))
+    return out
+
+
 def power_to_db(S, amin=1e-10, top_db=80.0):
     """lidbox/features/audio.py:167-174 (max over the whole tensor, batch included)."""
     S = _as_device_f32(S, 3, "S")

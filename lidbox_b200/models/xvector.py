@@ -74,9 +74,17 @@ class FeatureSink:
     out=sink)` writes its bf16 rows straight into it (zero-left-padded NWC layout) and the model then
     consumes the sink instead of a [B, T, F] tensor — the fp32 feature tensor and the packing pass never exist."""
 
-    def __init__(self, model, bufs, B, T, training):
-        self.model, self.bufs, self.B, self.T, self.training = model, bufs, B, T, training
+    def __init__(self, model, bufs, B, T, training, slot=0):
+        self.model, self.bufs, self.B, self.T, self.training, self.slot = model, bufs, B, T, training, slot
         self.shape = (B, T, model.F)
+        # slot 0 is the model's own input buffer; further slots are private copies of it, so that the features of
+        # batch i+1 can be produced while the step of batch i still reads its own (the weight gradient of the first
+        # frame layer reads the input at the very end of the backward pass)
+        if slot == 0:
+            self.x0, self.x0_lo = bufs["X0_own"], bufs["X0_lo_own"]
+        else:
+            self.x0 = torch.zeros_like(bufs["X0_own"])
+            self.x0_lo = torch.zeros_like(bufs["X0_lo_own"]) if bufs["X0_lo_own"] is not None else None
 
     def sink_spec(self, B, T, n_feat):
         """(hi pointer, lo pointer or None, utterance pitch, row pitch) in elements — see lbx_logmel_t."""
@@ -85,8 +93,8 @@ class FeatureSink:
             raise ValueError("feature sink was created for %s, got features of shape %s" %
                              ((self.B, self.T, m.F), (B, T, n_feat)))
         off = geo.pad[0] * m.Fp * 2                            # bytes: k-1 zero rows in front of every utterance
-        hi = self.bufs["X"][0].data_ptr() + off
-        lo = self.bufs["X_lo"][0].data_ptr() + off if self.bufs["X_lo"][0] is not None else None
+        hi = self.x0.data_ptr() + off
+        lo = self.x0_lo.data_ptr() + off if self.x0_lo is not None else None
         return hi, lo, geo.Tpad[0] * m.Fp, m.Fp
 
 
@@ -268,7 +276,7 @@ class XVector:
         cn = self.layers[n - 1]["N"]
         cnp = _ceil8(cn)
         Y = torch.zeros((B * geo.R[n - 1] + _SLACK_ROWS, cnp), dtype=torch.float32 if split else bf, device=dev)
-        bufs = dict(geo=geo, X=X, X_lo=X_lo, Y=Y, cn=cn, cnp=cnp,
+        bufs = dict(geo=geo, X=X, X_lo=X_lo, X0_own=X[0], X0_lo_own=X_lo[0], Y=Y, cn=cn, cnp=cnp,
                     pooled=torch.zeros((B, 2 * cn), dtype=torch.float32, device=dev),
                     var_raw=torch.zeros((B, cn), dtype=torch.float32, device=dev),
                     pooled_hi=torch.zeros((B, 2 * cn), dtype=bf, device=dev),
@@ -292,13 +300,14 @@ class XVector:
         return bufs
 
     # ------------------------------------------------------------------ forward
-    def feature_sink(self, B, T, training=False):
-        """Buffer handle for direct feature hand-off (see FeatureSink).  The buffer set stays allocated (pinned)."""
+    def feature_sink(self, B, T, training=False, slot=0):
+        """Buffer handle for direct feature hand-off (see FeatureSink).  The buffer set stays allocated (pinned).
+        slot > 0 gives an additional, independent input buffer (double buffering of the input pipeline)."""
         if training and self.channel_dropout_rate > 0:
             raise NotImplementedError("SpatialDropout1D is applied by the packing pass; feed [B,T,F] tensors instead")
         bufs = self._buffers(int(B), int(T), bool(training))
         bufs["pinned"] = True
-        return FeatureSink(self, bufs, int(B), int(T), bool(training))
+        return FeatureSink(self, bufs, int(B), int(T), bool(training), slot)
 
     def _prepare_input(self, x):
         if isinstance(x, FeatureSink):
@@ -317,8 +326,12 @@ class XVector:
         lib, st = _lib.lib(), _lib.stream_ptr(self.device)
         geo = bufs["geo"]
         B, T, _ = x.shape
-        if isinstance(x, FeatureSink) and x.bufs is not bufs:
-            raise ValueError("feature sink was created with training=%s" % x.training)
+        if isinstance(x, FeatureSink):
+            if x.bufs is not bufs:
+                raise ValueError("feature sink was created with training=%s" % x.training)
+            bufs["X"][0], bufs["X_lo"][0] = x.x0, x.x0_lo       # this call (and its backward) reads the sink's buffer
+        else:
+            bufs["X"][0], bufs["X_lo"][0] = bufs["X0_own"], bufs["X0_lo_own"]
         split = self.precision == "fp32"
         self._refresh(need_lo=split)
         n = len(self.frames)

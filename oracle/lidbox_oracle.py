@@ -177,6 +177,12 @@ def power_to_db(S, amin=1e-10, top_db=80.0):
     return np.maximum(db, db.max() - np.float32(top_db)).astype(np.float32)
 
 
+def db_to_power(S):
+    """lidbox/features/audio.py:177-181 — pow(10, S / 20)."""
+    S = np.asarray(S)
+    return np.power(S.dtype.type(10.0), S / S.dtype.type(20.0))
+
+
 def logmel(signals, sample_rate, frame_length_ms=25, frame_step_ms=10, power=2.0, fft_length=512,
            num_mel_bins=40, fmin=0.0, fmax=8000.0, dtype=np.float32):
     """The intended map-stage chain (tf_utils.py:172-178): spectrograms -> linear_to_mel -> ln(x+1e-6)."""
@@ -216,8 +222,8 @@ def extract_features(signals, sample_rates, feattype, spec_kwargs=None, melspec_
             X = mfccs_from_log_mel_spectrograms(X)[..., mk.get("coef_begin", 1):mk.get("coef_end", 13)]
     elif feattype == "db_spectrogram":
         X = power_to_db(X, **(db_spec_kwargs or {}))
-    elif feattype != "spectrogram":
-        raise NotImplementedError(feattype)
+    # any other feattype string (incl. "spectrogram") falls through the reference's if/elif chain: X stays the
+    # power spectrogram (tf_utils.py:172-188)
     if not np.isfinite(X).all():
         raise FloatingPointError(feattype + " failed")
     if feat_scale_kwargs:

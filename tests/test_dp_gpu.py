@@ -35,6 +35,39 @@ if rank == 0:
     w = (m.w16[:npar].float() - ref.w16.float()).abs().max().item()
     err = int(m._sharded["local"][3].item()) if m._sharded is not None else 0
     print("MEANDIFF", d, "STEP", s, "W16", w, "ERR", err, "NVLS", bool(m._sharded and m._sharded.get("mc_grads")))
+# ---- summed flat gradient BEFORE Adam, both exchange paths, vs the single-rank gradient of the concatenated batch
+B2 = 16
+x2 = rng.standard_normal((B2, 61, 40)).astype(np.float32); y2 = np.arange(B2) %% 4
+per2 = B2 // world
+def local_grads(model):
+    model.loss_and_grads(x2[rank*per2:(rank+1)*per2], y2[rank*per2:(rank+1)*per2], global_batch=B2)
+    return model.grads
+ma = xvector.create((61, 40), 4, precision="bf16", seed=5)
+g_nccl = local_grads(ma).clone()
+dist.all_reduce(g_nccl)                                   # the LBX_DP_SHARDED=0 exchange: one NCCL all-reduce
+mb = xvector.create((61, 40), 4, precision="bf16", seed=5)
+mb.configure_optimizer(lr=0.0)                            # lr = 0: the step leaves the weights alone and m = (1-beta1) * sum_r g_r
+mb.enable_sharded_optimizer(dist.group.WORLD)
+local_grads(mb)
+mb._apply_sharded()
+sh = mb._sharded
+shards = [torch.empty_like(sh["m"]) for _ in range(world)]
+dist.all_gather(shards, sh["m"])
+g_fused = torch.cat(shards) / (1.0 - 0.9)                 # the in-kernel reduce-scatter (NVLS multimem.ld_reduce or peer loads)
+terr = int(sh["local"][3].item())
+if rank == 0:
+    mr = xvector.create((61, 40), 4, precision="bf16", seed=5)
+    mr.loss_and_grads(x2, y2)
+    g_ref = mr.grads
+    n = g_ref.numel()
+    worst_n, worst_f = 0.0, 0.0
+    for ly in mr.layers:
+        lo, hi = ly["w_off"], ly["b_off"] + ly["ldw"]
+        den = g_ref[lo:hi].abs().max().item() + 1e-30
+        worst_n = max(worst_n, (g_nccl[lo:hi] - g_ref[lo:hi]).abs().max().item() / den)
+        worst_f = max(worst_f, (g_fused[lo:hi] - g_ref[lo:hi]).abs().max().item() / den)
+    print("GRADSUM nccl", worst_n, "fused", worst_f, "ERR", terr, "NVLS", bool(sh.get("mc_grads")))
+dist.barrier()
 dist.destroy_process_group()
 ''' % ROOT
 
@@ -59,3 +92,7 @@ def test_two_rank_step_matches_single_rank(tmp_path, sharded):
     # Adam's first step moves every weight by ~lr * sign(g); the two runs differ only by bf16 / atomic summation order,
     # which can flip the sign of near-zero gradients: compare the mean displacement
     assert step > 5e-4 and diff < 0.05 * step, (diff, step)
+    # summed gradients of the two ranks (before Adam) vs one rank with the whole batch: per-sample work is identical,
+    # only the fp32 summation order of the weight / bias gradient reductions differs (split-K atomics, exchange order)
+    gl = [l for l in out.stdout.splitlines() if l.startswith("GRADSUM")][0].split()
+    assert float(gl[2]) < 2e-4 and float(gl[4]) < 2e-4 and int(gl[6]) == 0, gl

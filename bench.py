@@ -391,6 +391,28 @@ class XVectorTrainWorkload:
         barrier()
         return e0.elapsed_time(e1) / steps, self.B * self.N * x_host.element_size(), self.B * 4
 
+    def measure_exchange(self, iters=20):
+        """Duration of the optimizer kernel (N = 1: Adam + bf16 refresh; N > 1: flag exchange + reduce-scatter + Adam on
+        the shard + all-gather) from CUDA events around it in eager steps — the part of the step that is exposed after
+        the backward pass."""
+        m = self.model
+        ts = []
+        for _ in range(iters + 3):
+            feats = self.audio.logmelspectrograms(self.x, SR, out=self.sinks[0])
+            m.loss_and_grads(feats, self.y, loss=self.loss, global_batch=self.B * self.world, **self.kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if m._sharded is not None:
+                m._apply_sharded()
+            else:
+                if self.pg is not None:
+                    self.dist.all_reduce(m.grads, group=self.pg)
+                m.apply_gradients()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return float(np.median(ts[3:]))
+
     def roofline_measure(self, peaks):
         """Dominant kernel = gemm_bf16_kernel.  Every GEMM descriptor of one training step is recorded, the launches
         are replayed back-to-back from a CUDA graph (same operands, same order, nothing else in between) and timed
@@ -645,7 +667,7 @@ WORKLOADS = {"logmel": LogmelWorkload, "xvector_train": XVectorTrainWorkload,
 DEFAULT_WORKLOAD = os.environ.get("LBX_BENCH_WORKLOAD", "xvector_train")
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's own CPU path (here: the oracle port, TensorFlow is not installable), all host
     threads.  Every step is ONE real step of the workload on the configured batch; if K steps of that size would not
     finish within ~2.5 minutes the per-step sample is shrunk (and the line says so)."""
@@ -683,7 +705,7 @@ def run_reference(args, rank, world):
             "config": cfg, "cpu_baseline": cb,
             "e2e": {"value": value, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -780,9 +802,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     if not torch.cuda.is_available():
@@ -801,7 +830,7 @@ def main():
     peaks = load_peaks()
     if args.workload == "fwd_sweep":
         if rank == 0:
-            print(json.dumps(bench_fwd_sweep(device)), flush=True)
+            emit(bench_fwd_sweep(device))
         return
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -845,14 +874,14 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     clocks = None
+    if ms < 250.0:
+        # a timed region shorter than a few NVML polls: keep the SAME workload running (untimed, the same number of
+        # steps on every rank: the steps contain cross-rank barriers) until the sampler has seen it under load, so that
+        # the clocks / throttle record describes this kernel mix
+        for _ in range(int(400.0 / max(ms_per_step, 1e-3)) + 1):
+            wl.step()
+        torch.cuda.synchronize()
     if rank == 0:
-        if ms < 250.0:
-            # a timed region shorter than a few NVML polls: keep the SAME workload running (untimed) until the sampler
-            # has seen it under load, so that the clocks / throttle record describes this kernel mix
-            t_end = time.time() + 0.4
-            while time.time() < t_end:
-                wl.step()
-            torch.cuda.synchronize()
         clocks = sampler.stop()
         clocks["timed_region_ms"] = ms
     if dist is not None:
@@ -862,6 +891,14 @@ def main():
     # dominant-kernel timing for the roofline (CUDA events on the launching stream)
     roof = wl.roofline_measure(peaks) if hasattr(wl, "roofline_measure") else wl.roofline(ms_per_step, peaks)
 
+    exch_us = None
+    if hasattr(wl, "measure_exchange"):
+        exch_us = wl.measure_exchange()
+        if dist is not None:
+            t = torch.tensor([exch_us], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            exch_us = float(t.item())
+            wl.model.dp_health()
     _log("roofline done")
     # end-to-end through the public API with pinned host buffers: 16-bit PCM batches (primary), float32 (secondary)
     e_steps = max(10, min(args.steps, 50))
@@ -902,11 +939,13 @@ def main():
                                "note": "same pipeline fed with float32 signals: PCIe-bound"}
         if dp_check is not None:
             line["dp_check"] = dp_check
+        if exch_us is not None:
+            line["dp_exchange_us"] = exch_us
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = wl.cpu_sample()
         if hasattr(wl, "extra"):
             line.update(wl.extra())
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         # ranks > 0 wait here while rank 0 measures the secondary lines; then leave without tearing NCCL down
         # (destroy_process_group can dead-lock while a captured CUDA graph still references the communicator)

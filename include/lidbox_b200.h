@@ -311,14 +311,20 @@ int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, 
 /* Data-parallel optimizer step fused with the gradient exchange over NVLink peer memory (one node, one process per
  * GPU; replaces "all-reduce + Adam").  The flat parameter / gradient / bf16-copy buffers are SYMMETRIC allocations:
  * params_ptrs / grads_ptrs / w16_ptrs / signal_ptrs are DEVICE arrays of `world` peer pointers (index = rank).
- * Every rank: waits until all ranks finished their backward pass (peer flag barrier), sums ITS shard
+ * Every rank: waits until all ranks finished their backward pass (ONE peer flag exchange), sums ITS shard
  * [rank*n/world, (rank+1)*n/world) of all ranks' gradients with peer loads (reduce-scatter), applies Adam to the shard
- * (m_shard / v_shard hold n/world elements), stores the updated fp32 parameters and bf16 copy into every rank's
- * buffers with peer stores (all-gather), waits for all ranks again, and zeroes its own gradient buffer.
- * signal pads: 2*world uint32 per rank, zero-initialised; epoch_dev / local_sync_dev (4 uint32): zero-initialised local
- * state advanced by every call, so the call can be replayed from a CUDA graph.  local_sync_dev[3] != 0 reports a
- * barrier time-out.  n must be a multiple of 4*world.  push_fp32 = 0 all-gathers only the bf16 operand copy (the fp32
- * master copy of a shard then lives on its owner only, ZeRO-1 style; gather it from the peers before exporting).
+ * (m_shard / v_shard hold n/world elements), stores the updated bf16 copy (and optionally the fp32 parameters) into
+ * every rank's buffers with peer stores (all-gather) and publishes "pushed" to every peer — it does NOT wait for the
+ * peers' pushes and does NOT touch the gradient buffer: the next step starts with lbx_dp_wait() (all peers have
+ * published <=> this rank's bf16 weights are complete and nobody reads its gradient any more), after which the caller
+ * clears its gradient buffer (off the critical path, e.g. on a side stream during the forward pass).
+ * signal pads: 2*world uint32 per rank, zero-initialised; epoch_dev (1 uint32) / local_sync_dev (16 uint32; [4..9] receive three 64-bit globaltimer stamps of the last call:
+ * start, barrier passed, last block done): zero-initialised local
+ * state advanced by every call, so the calls can be replayed from a CUDA graph.  local_sync_dev[3] != 0 reports a
+ * barrier time-out (lbx_set_dp_spin_limit polls of 64 ns, default 2^23 ~ 1 s): the update of that step is SKIPPED on
+ * the rank that timed out, never applied from a half-reduced gradient; the host must treat it as fatal.
+ * n must be a multiple of 4*world.  push_fp32 = 0 all-gathers only the bf16 operand copy (the fp32 master copy of a
+ * shard then lives on its owner only, ZeRO-1 style; gather it from the peers before exporting).
  * mc_grads / mc_w16 (optional, both or none): NVLS multicast mappings of the gradient and bf16 buffers; when given the
  * reduce-scatter is one multimem.ld_reduce per element (the sum is formed inside the NVSwitch) and the all-gather one
  * multimem.st per element instead of `world` peer accesses. */
@@ -327,6 +333,12 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
                           unsigned int* epoch_dev, unsigned int* local_sync_dev, float lr, float beta1, float beta2,
                           float eps, long long* step_dev, float* lr_t_dev, float grad_scale, int push_fp32,
                           const void* mc_grads, void* mc_w16, void* stream);
+/* see lbx_adam_step_sharded: spins until every peer has published the epoch in *epoch_dev into this rank's pad */
+int lbx_dp_wait(const void* signal_pad_local, int world, const unsigned int* epoch_dev, unsigned int* local_sync_dev,
+                void* stream);
+int lbx_set_dp_spin_limit(long long polls);
+/* resident blocks per SM of lbx_adam_step_sharded (1..8, default 4) */
+int lbx_set_dp_blocks_per_sm(int n);
 
 /* fp32 -> bf16 operand planes of the flat parameter buffer: hi = bf16(x), lo = bf16(x - hi) (lo optional; it feeds
  * the bf16x3 forward mode).  The buffers keep the Keras layouts ([k*C_in, C_out] per kernel, pitch padded to 8). */

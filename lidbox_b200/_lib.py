@@ -88,6 +88,9 @@ SIGNATURES = {
     "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P, c_int, _P]),
     "lbx_adam_step_sharded": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P, _P, c_float, c_float, c_float,
                                       c_float, _P, _P, c_float, c_int, _P, _P, _P]),
+    "lbx_dp_wait": (c_int, [_P, c_int, _P, _P, _P]),
+    "lbx_set_dp_spin_limit": (c_int, [c_ll]),
+    "lbx_set_dp_blocks_per_sm": (c_int, [c_int]),
     "lbx_split_bf16": (c_int, [_P, c_ll, _P, _P, _P]),
     "lbx_logmel_f32_host": (c_int, [_P, c_ll, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_float,
                                     c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),
@@ -117,6 +120,10 @@ def lib():
             handle.lbx_set_pdl(0)
         handle.lbx_set_gemm_pair(0 if os.environ.get("LBX_GEMM_PAIR", "1") == "0" else 1)
         handle.lbx_set_gemm_fast_epilogue(0 if os.environ.get("LBX_GEMM_FAST_EPI", "1") == "0" else 1)
+        if os.environ.get("LBX_DP_BLOCKS_PER_SM"):
+            handle.lbx_set_dp_blocks_per_sm(int(os.environ["LBX_DP_BLOCKS_PER_SM"]))
+        if os.environ.get("LBX_DP_SPIN_LIMIT"):
+            handle.lbx_set_dp_spin_limit(int(os.environ["LBX_DP_SPIN_LIMIT"]))
         _lib = handle
     return _lib
 

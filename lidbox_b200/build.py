@@ -37,21 +37,49 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
         return _compile(out, list(extra_flags), verbose)
     if not force and not is_stale():
         return LIB_PATH
+    if force:
+        shutil.rmtree(os.path.join(CSRC, "gen", "obj", "default"), ignore_errors=True)
     return _compile(LIB_PATH, [], verbose)
 
 
 def _compile(LIB_PATH, extra, verbose):
+    """One nvcc -c per translation unit, in parallel, objects cached under csrc/gen/obj (rebuilt when the source or any
+    header is newer), then one link step."""
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: lidbox_b200 has no CPU fallback and cannot run without its CUDA library")
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-o", LIB_PATH + ".tmp"] + sources()
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared",)] + extra
+    tag = "default" if not extra else "x%08x" % (hash(tuple(extra)) & 0xffffffff)
+    obj_dir = os.path.join(CSRC, "gen", "obj", tag)
+    os.makedirs(obj_dir, exist_ok=True)
+    hdr_time = max(os.path.getmtime(p) for p in _deps() if not p.endswith((".cu", ".cpp")))
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        objs.append(obj)
+        if not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            jobs.append([nvcc] + compile_flags + ["-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-c", "-o", obj, src])
+    log = []
+    with ThreadPoolExecutor(max_workers=max(1, len(jobs))) as ex:
+        procs = list(ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs))
+    failed = False
+    for cmd, proc in zip(jobs, procs):
+        log.append(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+        failed = failed or proc.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+            "-o", LIB_PATH + ".tmp"] + objs
+    proc = subprocess.run(link, capture_output=True, text=True)
+    log.append(" ".join(link) + "\n" + proc.stdout + proc.stderr)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed (exit %d)" % proc.returncode)
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("link failed (exit %d)" % proc.returncode)
     with open(os.path.join(PKG_DIR, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        f.write("\n".join(log))
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     return LIB_PATH
 

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace lbx {
 
@@ -833,6 +834,8 @@ struct ShardedAdamParams {
   int push_fp32;                 // 1: also all-gather the fp32 master copy (otherwise only the owner's shard is current)
   const float* mc_grads;         // optional NVLS multicast mapping of the gradient buffers (in-switch reduction)
   bf16* mc_w16;                  // optional NVLS multicast mapping of the bf16 operand copy (one store reaches all ranks)
+  long long spin_limit;          // polls (64 ns apart) before a barrier gives up and the step is skipped
+  int debug;                     // measurement only: 1 = no remote loads, 2 = no remote stores, 4 = no fence per thread
 };
 
 // NVLink SHARP: one load returns the sum over all ranks of the multicast group, reduced inside the NVSwitch
@@ -867,8 +870,9 @@ __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) 
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // bounded spin: a lost peer must not hang the GPU (error flag instead)
-__device__ __forceinline__ bool spin_until_ge(const unsigned int* p, unsigned int target, bool sys_scope) {
-  for (long long it = 0; it < (1LL << 23); ++it) {   // ~1 s
+__device__ __forceinline__ bool spin_until_ge(const unsigned int* p, unsigned int target, bool sys_scope,
+                                              long long limit = (1LL << 23)) {
+  for (long long it = 0; it < limit; ++it) {         // 2^23 polls ~ 1 s
     const unsigned int v = sys_scope ? ld_acquire_sys(p) : ld_acquire_gpu(p);
     if ((int)(v - target) >= 0) return true;
     __nanosleep(64);
@@ -880,67 +884,104 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned int* p, unsigned in
 __device__ __forceinline__ bool peer_barrier(const ShardedAdamParams& p, unsigned int e, int base) {
   for (int q = 0; q < p.world; ++q) st_release_sys(p.signals[q] + base + p.rank, e);
   bool ok = true;
-  for (int q = 0; q < p.world; ++q) ok = spin_until_ge(p.signals[p.rank] + base + q, e, true) && ok;
+  for (int q = 0; q < p.world; ++q) ok = spin_until_ge(p.signals[p.rank] + base + q, e, true, p.spin_limit) && ok;
   return ok;
 }
 
 // NVLS: gradients are reduced inside the NVSwitch (one multimem.ld_reduce per element), W is unused (1);
 // otherwise W = number of ranks whose gradient shard is read over NVLink peer mappings (2, 4 or 8).
+//
+// Critical path of a data-parallel step after the backward pass = ONE flag exchange (all ranks have finished their
+// gradients) + the shard update itself.  Nothing else waits inside this kernel: every block leaves as soon as its part
+// of the shard is pushed, the LAST block to finish publishes "rank r has pushed epoch e" to every peer, and the next
+// step's forward pass starts with dp_wait_kernel (weights complete on this rank <=> all peers have published), after
+// which the local gradient is cleared off the critical path.  A barrier time-out (a peer is more than spin_limit polls
+// late) sets local_sync[3] and SKIPS the update on this rank: no half-reduced gradient is ever applied.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <bool NVLS, int W>
 __global__ void __launch_bounds__(256) adam_sharded_kernel(const ShardedAdamParams p) {
   LBX_PDL_SYNC();
-  __shared__ unsigned int s_e;
+  __shared__ unsigned int s_abort;
   __shared__ float s_lr_t;
   const unsigned int nblk = gridDim.x;
-  // ---- barrier 1: every rank has finished its backward pass (its gradient buffer is complete) ----
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const unsigned int e = *p.epoch + 1;
-    const long long t = *p.step + 1;
-    *p.step = t;
-    *p.lr_t = (float)((double)p.lr * sqrt(1.0 - pow((double)p.beta2, (double)t)) / (1.0 - pow((double)p.beta1, (double)t)));
-    __threadfence_system();                     // this rank's gradient writes are visible to the peers
-    if (!peer_barrier(p, e, 0)) p.local_sync[3] = 1;
-    __threadfence();
-    st_release_gpu(p.local_sync + 0, e);
-  }
+  const unsigned int e = *p.epoch + 1;            // epoch is only advanced at the very end, by the last block
+  // optional phase timestamps (local_sync[4..9] as three 64-bit nanosecond stamps: start, barrier passed, last block done)
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(p.local_sync + 4);
+  // ---- barrier: every rank has finished its backward pass (its gradient buffer is complete).  Block 0 announces this
+  // rank to every peer; EVERY block polls this rank's own pad (local memory the peers write into): no relay hop ----
   if (threadIdx.x == 0) {
-    const unsigned int e = *p.epoch + 1;         // epoch is only advanced at the very end, by block 0
-    if (!spin_until_ge(p.local_sync + 0, e, false)) p.local_sync[3] = 1;
-    s_e = e;
-    s_lr_t = *reinterpret_cast<volatile float*>(p.lr_t);
+    if (blockIdx.x == 0) {
+      stamps[0] = global_timer_ns();
+      __threadfence_system();                     // this rank's gradient writes are visible to the peers
+      for (int q = 0; q < p.world; ++q) st_release_sys(p.signals[q] + p.rank, e);
+    }
+    bool ok = true;
+    for (int q = 0; q < p.world; ++q) ok = spin_until_ge(p.signals[p.rank] + q, e, true, p.spin_limit) && ok;
+    if (!ok) p.local_sync[3] = 1;
+    if (blockIdx.x == 0) {
+      stamps[1] = global_timer_ns();
+      if (ok) {
+        const long long t = *p.step + 1;
+        *p.step = t;
+      }
+    }
+    // bias-corrected rate of THIS step, computed by every block from the (not yet advanced or just advanced) counter
+    const long long t = e;                        // one optimizer step per epoch: step counter == epoch
+    s_lr_t = (float)((double)p.lr * sqrt(1.0 - pow((double)p.beta2, (double)t)) / (1.0 - pow((double)p.beta1, (double)t)));
+    if (blockIdx.x == 0) *p.lr_t = s_lr_t;
+    s_abort = ok ? 0u : 1u;
   }
   __syncthreads();
-  const unsigned int e = s_e;
   const float lr_t = s_lr_t;
 
   // ---- reduce-scatter + Adam + all-gather on this rank's shard ----
-  const long long shard4 = p.n / 4 / p.world;    // float4 groups per shard
-  const long long base4 = shard4 * p.rank;
+  const long long shard4 = s_abort ? 0 : p.n / 4 / p.world;    // float4 groups per shard (none after a time-out)
+  const long long base4 = (p.n / 4 / p.world) * p.rank;
   float4* m4 = reinterpret_cast<float4*>(p.m);
   float4* v4 = reinterpret_cast<float4*>(p.v);
   float4* my_params = reinterpret_cast<float4*>(p.params[p.rank]) + base4;
-  // peer loads have NVLink latency (microseconds): every thread issues all loads of UNROLL elements (gradient shards of
-  // every rank or one in-switch reduction, moments, master weights) before the first use
-  constexpr int UNROLL = NVLS ? 4 : (W <= 2 ? 4 : 2);
+  // Software pipeline: the NVLink loads (gradient shards of the peers, or one in-switch reduction) of iteration k+1 are
+  // in flight while iteration k does its local work (moments, master weights, bf16 push), so the link time and the HBM
+  // time overlap instead of adding up (measured on 2 GPUs: 17 us of exposed peer-load latency with a single wave).
+  constexpr int UNROLL = 2;
   const long long stride = (long long)nblk * blockDim.x;
-  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < shard4; i0 += stride * UNROLL) {
-    float4 t[UNROLL][W], mi[UNROLL], vi[UNROLL], pi[UNROLL];
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float4 tn[UNROLL][W];
+  auto fetch = [&](long long i0) {
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long i = i0 + u * stride;
       if (i < shard4) {
         if (NVLS) {
-          t[u][0] = multimem_ld_reduce_f32x4(p.mc_grads + 4 * (base4 + i));
+          tn[u][0] = multimem_ld_reduce_f32x4(p.mc_grads + 4 * (base4 + i));
         } else {
 #pragma unroll
           for (int q = 0; q < W; ++q)
-            t[u][q] = __ldcv(reinterpret_cast<const float4*>(p.grads[q]) + base4 + i);   // peer (NVLink) or local
+            tn[u][q] = __ldcv(reinterpret_cast<const float4*>(p.grads[(p.debug & 1) ? p.rank : q]) + base4 + i);
         }
+      }
+    }
+  };
+  fetch(first);
+  for (long long i0 = first; i0 < shard4; i0 += stride * UNROLL) {
+    float4 t[UNROLL][W], mi[UNROLL], vi[UNROLL], pi[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+      for (int q = 0; q < W; ++q) t[u][q] = tn[u][q];
+      const long long i = i0 + u * stride;
+      if (i < shard4) {
         mi[u] = __ldcs(m4 + i);
         vi[u] = __ldcs(v4 + i);
         pi[u] = my_params[i];
       }
     }
+    fetch(i0 + stride * UNROLL);                  // next iteration's link traffic, before this iteration's math / stores
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long i = i0 + u * stride;
@@ -968,33 +1009,40 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const ShardedAdamPara
         multimem_st_b32x2(p.mc_w16 + 4 * (base4 + i), packed);
       } else {
         for (int q = 0; q < p.world; ++q) {         // all-gather by peer stores
+          if ((p.debug & 2) && q != p.rank) continue;
           if (p.push_fp32 || q == p.rank) reinterpret_cast<float4*>(p.params[q])[base4 + i] = pi[u];
           reinterpret_cast<uint2*>(p.w16[q])[base4 + i] = packed;
         }
       }
     }
   }
-  // ---- barrier 2: all shards have been pushed everywhere and nobody reads this rank's gradient any more ----
-  __threadfence_system();
+  // ---- publish: the last block to finish tells every peer that this rank's shard has been pushed everywhere (and that
+  // this rank no longer reads anybody's gradient); nobody waits here.  bar.sync + one system fence by thread 0 orders
+  // the whole block's remote stores before the count (the cooperative-groups grid-sync pattern) ----
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(p.local_sync + 1, 1u);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (!spin_until_ge(p.local_sync + 1, e * nblk, false)) p.local_sync[3] = 1;
+  if (threadIdx.x == 0) {
     __threadfence_system();
-    if (!peer_barrier(p, e, p.world)) p.local_sync[3] = 1;
-    __threadfence();
-    st_release_gpu(p.local_sync + 2, e);
+    const unsigned int done = atomicAdd(p.local_sync + 1, 1u) + 1u;
+    if (done == e * nblk) {                       // counts accumulate over the epochs: e * nblk after epoch e
+      stamps[2] = global_timer_ns();
+      __threadfence_system();
+      for (int q = 0; q < p.world; ++q) st_release_sys(p.signals[q] + p.world + p.rank, e);
+      *p.epoch = e;                               // every block has read the old value (they all passed the start)
+    }
   }
-  if (threadIdx.x == 0 && !spin_until_ge(p.local_sync + 2, e, false)) p.local_sync[3] = 1;
-  __syncthreads();
-  // ---- reset the local gradient for the next step (measured: resetting shard by shard on every rank through the
-  // multicast mapping instead is slower, 0.485 -> 0.516 ms/step on 2 GPUs) ----
-  float4* g4 = reinterpret_cast<float4*>(p.grads[p.rank]);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n / 4; i += (long long)nblk * blockDim.x)
-    g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // the epoch is advanced once every block has read it (all blocks passed go2, which is after their read)
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.epoch = e;
 }
+
+// Start of the next step: all peers have published epoch *epoch  <=>  every shard of the bf16 weights has landed in
+// this rank's copy and nobody reads this rank's gradient buffer any more (it may be cleared).
+__global__ void dp_wait_kernel(const unsigned int* __restrict__ pad, int world, const unsigned int* __restrict__ epoch,
+                               unsigned int* __restrict__ local_sync, long long spin_limit) {
+  LBX_PDL_SYNC();
+  const unsigned int e = *epoch;
+  if ((int)threadIdx.x < world && !spin_until_ge(pad + world + threadIdx.x, e, true, spin_limit)) local_sync[3] = 1;
+}
+
+static long long g_dp_spin_limit = 1LL << 23;      // ~1 s of 64 ns polls
+static int g_dp_blocks_per_sm = 2;
 
 static inline int grid_for(long long n, int block, int cap = 148 * 16) {
   long long g = ceil_div(n, block);
@@ -1190,6 +1238,8 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
   p.lr = lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale;
   p.push_fp32 = push_fp32;
   p.mc_grads = (const float*)mc_grads; p.mc_w16 = (bf16*)mc_w16;
+  p.spin_limit = g_dp_spin_limit;
+  p.debug = getenv("LBX_DP_DEBUG") ? atoi(getenv("LBX_DP_DEBUG")) : 0;
   LBX_CHECK_ARG(world <= 8, "at most 8 ranks (one NVLink domain)");
   // every block must be able to be resident at once (grid-wide flags): occupancy-limited grid
   int dev = 0, sms = 0, per_sm = 0;
@@ -1211,9 +1261,30 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
     }
   }
   LBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > g_dp_blocks_per_sm) per_sm = g_dp_blocks_per_sm;
   if (per_sm < 1) per_sm = 1;
   LBX_LAUNCH_PDL(kernel, dim3((unsigned)(sms * per_sm)), dim3(256), 0, (cudaStream_t)stream, p);
+  return LBX_OK;
+}
+
+int lbx_dp_wait(const void* signal_pad_local, int world, const unsigned int* epoch_dev, unsigned int* local_sync_dev,
+                void* stream) {
+  LBX_CHECK_ARG(signal_pad_local && epoch_dev && local_sync_dev, "NULL pointer argument");
+  LBX_CHECK_ARG(world >= 1 && world <= 8, "at most 8 ranks (one NVLink domain)");
+  LBX_LAUNCH_PDL(dp_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (const unsigned int*)signal_pad_local, world,
+                 epoch_dev, local_sync_dev, g_dp_spin_limit);
+  return LBX_OK;
+}
+
+int lbx_set_dp_blocks_per_sm(int n) {
+  LBX_CHECK_ARG(n >= 1 && n <= 8, "blocks per SM must be in [1, 8]");
+  g_dp_blocks_per_sm = n;
+  return LBX_OK;
+}
+
+int lbx_set_dp_spin_limit(long long polls) {
+  LBX_CHECK_ARG(polls >= 1, "spin limit must be >= 1");
+  g_dp_spin_limit = polls;
   return LBX_OK;
 }
 

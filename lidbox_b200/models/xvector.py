@@ -439,11 +439,34 @@ class XVector:
         fused_head = (loss == "xent" and self.num_outputs <= 8 and n_seg >= 1 and out_ly["K"] <= 1024 and
                       out_ly["K"] * (4 * self.num_outputs + 20) + 256 <= 49152 and
                       os.environ.get("LBX_FUSED_HEAD", "0") == "1")
+        cur = torch.cuda.current_stream(self.device)
+        ev_zero = None
+        if self._sharded is not None:
+            # data-parallel step start: the previous lbx_adam_step_sharded did not wait for the peers' all-gather pushes
+            # nor clear the gradient.  A side stream waits for "every peer has published" (tiny kernel, normally already
+            # true), which the forward pass needs (complete weights); after it the gradient buffer is cleared while
+            # the forward pass runs (first written by the loss kernel).
+            sh = self._sharded
+            ev0 = torch.cuda.Event()
+            ev0.record(cur)
+            self._side_stream.wait_event(ev0)
+            with torch.cuda.stream(self._side_stream):
+                _lib.check(lib.lbx_dp_wait(_lib.ptr(sh["sig"]), sh["world"], _lib.ptr(sh["epoch"]), _lib.ptr(sh["local"]),
+                                           _lib.stream_ptr(self.device)))
+                ev_w = torch.cuda.Event()
+                ev_w.record(self._side_stream)
+                self.grads.zero_()
+                ev_zero = torch.cuda.Event()
+                ev_zero.record(self._side_stream)
+            cur.wait_event(ev_w)
+            self._grads_clean = True
         logits = self._forward(x, bufs, True, skip_outputs=fused_head)
         scale = 1.0 / float(global_batch or B)
         npad = bufs["dlogits"].shape[1]
         if not self._grads_clean:
             self.grads.zero_()
+        if ev_zero is not None:
+            cur.wait_event(ev_zero)
         self._grads_clean = False
         g = self.grads
         if fused_head:
@@ -468,7 +491,6 @@ class XVector:
 
         # weight gradients are leaves of the backward graph (only the optimizer reads them): they run on a side
         # stream, concurrently with the latency-bound chain of data-gradient kernels, and are joined before Adam
-        cur = torch.cuda.current_stream(self.device)
         side = self._side_stream if self.overlap_wgrad else None
 
         def wgrad(a, a_rows, a_cols, lda, dz, dz_cols, dz_pitch, ly, a_off=0, dz_off=0):
@@ -637,7 +659,7 @@ class XVector:
                              m=torch.zeros(n_pad // world, dtype=torch.float32, device=dev),
                              v=torch.zeros(n_pad // world, dtype=torch.float32, device=dev),
                              epoch=torch.zeros(1, dtype=torch.int32, device=dev),
-                             local=torch.zeros(4, dtype=torch.int32, device=dev))
+                             local=torch.zeros(16, dtype=torch.int32, device=dev))
         a["m"] = a["v"] = None                              # full-size moments are not needed any more
         self._weights_dirty = self._lo_dirty = True
         self._grads_clean = True
@@ -653,10 +675,17 @@ class XVector:
                                                     1.0, 0, ctypes.c_void_p(sh["mc_grads"] or None),
                                                     ctypes.c_void_p(sh["mc_w16"] or None),
                                                     _lib.stream_ptr(self.device)))
-        self._grads_clean = True
+        self._grads_clean = False          # cleared at the start of the next step, after lbx_dp_wait
         self._weights_dirty = False
         self._lo_dirty = True
         sh["master_stale"] = True
+
+    def dp_health(self):
+        """Raises if a cross-GPU barrier of the sharded optimizer ever timed out on this rank (the update of that step
+        was skipped here, so the replicas have diverged: fatal).  Synchronises the device."""
+        if self._sharded is not None and int(self._sharded["local"][3].item()) != 0:
+            raise _lib.LidboxB200Error("data-parallel barrier time-out: a peer rank was more than the spin budget late "
+                                       "(LBX_DP_SPIN_LIMIT polls of 64 ns); the optimizer step was skipped on this rank")
 
     def _sync_master_from_peers(self):
         """The sharded optimizer keeps the fp32 master copy of a shard current on its owner only; pull the other
@@ -667,6 +696,7 @@ class XVector:
             return
         import torch.distributed as dist
         torch.cuda.synchronize(self.device)
+        self.dp_health()
         dist.barrier()
         shard = sh["n"] // sh["world"]
         h = sh["handles"][0]

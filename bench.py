@@ -426,7 +426,10 @@ class XVectorTrainWorkload:
         self._eager_step()
         torch.cuda.synchronize()
         rec, ops.GEMM_RECORD = ops.GEMM_RECORD, None
-        issued = sum(2.0 * M * N * K * nt for (_d, _k, (M, N, K, nt, _l)) in rec)
+        issued = 0.0
+        for (_d, _k, shape) in rec:        # one (M, N, K, n_terms, layout) per GEMM, a list of (M, N, K) per grouped launch
+            issued += (sum(2.0 * M * N * K for (M, N, K) in shape) if isinstance(shape, list)
+                       else 2.0 * shape[0] * shape[1] * shape[2] * shape[3])
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -455,8 +458,8 @@ class XVectorTrainWorkload:
                 traffic_src = "profiles/r2_gemm_traffic.json (ncu --set full capture of this step; not measured live)"
         except Exception:
             pass
-        return {"bound": "tensor", "kernel": "gemm_bf16_kernel (all %d launches of one training step, replayed "
-                                             "back-to-back from a CUDA graph)" % len(rec),
+        return {"bound": "tensor", "kernel": "gemm_bf16_kernel + wgrad_grouped_kernel (all %d tensor-core launches of one "
+                                             "training step, replayed back-to-back from a CUDA graph)" % len(rec),
                 "achieved": ach, "peak": peaks["bf16_tflops"],
                 "peak_source": peaks["source"] + " (burst: the GEMM replay lasts %.0f ms at boost clock)" % (ms * 53),
                 "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "frac_burst": ach / peaks["bf16_tflops"],

@@ -238,6 +238,18 @@ typedef struct lbx_gemm_t {
   int colsum_mod;
 } lbx_gemm_t;
 int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream);
+/* Grouped weight gradients: out_p[a_cols, b_cols] += A_p^T . B_p for up to 8 problems in ONE persistent launch
+ * (replaces the Keras-computed kernel gradients of the Conv1D frame layers, lidbox/models/xvector.py:38-43 under
+ * keras_utils.py:135-147 `fit`).  A_p = layer input [rows, a_cols] bf16 through its (possibly overlapping-row) view of
+ * pitch lda, B_p = gradient w.r.t. the layer's pre-activation [rows, b_cols] bf16 (pitch ldb), out_p fp32 with pitch
+ * ldo, accumulated with vector atomics (the caller zeroes it once per step).  The k-blocks of all problems are cut into
+ * equal contiguous ranges, one per CTA pair (stream-K), so no problem pays its own pipeline fill / tail. */
+typedef struct {
+  const void* a; long long rows; int a_cols; long long lda;
+  const void* b; int b_cols; long long ldb;
+  float* out; long long ldo;
+} lbx_wgrad_t;
+int lbx_wgrad_grouped(const lbx_wgrad_t* problems, int n, void* stream);
 /* GEMMs are launched with programmatic dependent launch (prologue overlaps the previous kernel's tail); 0 disables. */
 int lbx_set_pdl(int enabled);
 /* 1: the 256-wide GEMM tiles run on CTA pairs (clusters of 2, tcgen05 cta_group::2: a 256x256 tile per pair, every
@@ -289,6 +301,21 @@ int lbx_logsoftmax_xent(const float* logits, const int* labels, long long B, int
 int lbx_dense_xent_head(const void* h_bf16, const void* w_bf16, const float* bias, const int* labels, long long B, int K,
                         int N, int ldh, int ldw, float grad_scale, int relu_mask, float* logits_out, float* loss,
                         void* dh_bf16, float* dW, float* dbias, float* dbias_below, void* stream);
+
+/* Fused dense head (lidbox/models/xvector.py:61-63: segment1 = Dense(K1 -> N1) + ReLU, segment2 = Dense(N1 -> N2) +
+ * ReLU) in ONE persistent launch: h1 = bf16(relu(pooled . W1 + b1)), h2 = bf16(relu(h1 . W2 + b2)).  pooled [B, K1],
+ * h1 [B, N1], h2 [B, N2] dense bf16; W1 [K1, ldw1], W2 [N1, ldw2] bf16 copies of the Keras kernels; scratch = B*N1
+ * floats that are zero on entry and left zero; sync_ws = 512 zero-initialised uint32 owned by the caller (grid-barrier
+ * state: sync_ws[2] != 0 reports a barrier time-out).  All widths / pitches multiples of 8. */
+int lbx_head_fwd(const void* pooled_bf16, long long B, int K1, const void* w1_bf16, int ldw1, const float* b1, int N1,
+                 const void* w2_bf16, int ldw2, const float* b2, int N2, void* h1_bf16, void* h2_bf16, float* scratch,
+                 unsigned int* sync_ws, void* stream);
+/* Backward of the same two layers in ONE launch, from dh2 = d loss / d (segment2 pre-activation) [B, N2] bf16:
+ * dh1 = (dh2 . W2^T) * (h1 > 0) [B, N1] bf16, db1 += column sums of dh1, dW2 += h1^T . dh2, then
+ * gpool = dh1 . W1^T [B, K1] fp32 (overwritten) and dW1 += pooled^T . dh1.  dW1 / dW2 have pitches ldw1 / ldw2. */
+int lbx_head_bwd(const void* dh2_bf16, const void* pooled_bf16, const void* h1_bf16, long long B, int K1, int N1, int N2,
+                 const void* w1_bf16, int ldw1, const void* w2_bf16, int ldw2, void* dh1_bf16, float* gpool, float* dw1,
+                 float* db1, float* dw2, unsigned int* sync_ws, void* stream);
 
 /* lidbox/losses.py:12-52 SparseAngularProximity(N, D, delta_weight): theta = acos(z[:, :N]),
  * loss[b] = sum_{l != y_b} sigmoid(delta_weight * (theta[b,y_b] - theta[b,l])).  normalize = 1 first maps

@@ -27,6 +27,15 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class WgradDesc(ctypes.Structure):
+    """lbx_wgrad_t (include/lidbox_b200.h)."""
+    _fields_ = [
+        ("a", c_void_p), ("rows", c_ll), ("a_cols", c_int), ("lda", c_ll),
+        ("b", c_void_p), ("b_cols", c_int), ("ldb", c_ll),
+        ("out", c_void_p), ("ldo", c_ll),
+    ]
+
+
 class LogmelDesc(ctypes.Structure):
     """lbx_logmel_t (include/lidbox_b200.h)."""
     _fields_ = [
@@ -85,6 +94,9 @@ SIGNATURES = {
     "lbx_stats_pool_bwd": (c_int, [_P, c_ll, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, c_int, _P]),
     "lbx_logsoftmax_xent": (c_int, [_P, _P, c_ll, c_int, _P, _P, _P, c_int, c_float, _P, _P]),
     "lbx_ap_loss": (c_int, [_P, _P, c_ll, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_int, _P, c_float, _P, _P]),
+    "lbx_wgrad_grouped": (c_int, [_P, c_int, _P]),
+    "lbx_head_fwd": (c_int, [_P, c_ll, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, _P]),
+    "lbx_head_bwd": (c_int, [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P, c_int, _P]),
     "lbx_adam_step_sharded": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P, _P, c_float, c_float, c_float,
                                       c_float, _P, _P, c_float, c_int, _P, _P, _P]),

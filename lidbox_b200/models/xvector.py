@@ -154,6 +154,20 @@ class XVector:
         self._grads_clean = True
         self.overlap_wgrad = True
         self._side_stream = torch.cuda.Stream(device=self.device)
+        self._head_sync = torch.zeros(512, dtype=torch.int32, device=self.device)   # grid-barrier state of the fused head
+
+    def _head_fused(self):
+        """The two segment layers run as one persistent launch each way (lbx_head_fwd / lbx_head_bwd) in bf16 precision;
+        LBX_HEAD_FUSED=0 restores one tcgen05 GEMM launch per layer and direction."""
+        n = len(self.frames)
+        return (self.precision == "bf16" and len(self.segments) == 2 and os.environ.get("LBX_HEAD_FUSED", "1") != "0" and
+                all(self.layers[n + i]["relu"] and self.layers[n + i]["N"] % 8 == 0 and self.layers[n + i]["K"] % 8 == 0
+                    for i in range(2)))
+
+    def head_health(self):
+        """Raises if a grid barrier of the fused head ever timed out (synchronises the device)."""
+        if int(self._head_sync[2].item()) != 0:
+            raise _lib.LidboxB200Error("fused head: grid barrier time-out")
 
     # ------------------------------------------------------------------ parameters
     def _build_params(self, seed):
@@ -284,6 +298,8 @@ class XVector:
                     H=[], H_lo=[], emb=torch.zeros((B, self.segments[0].units), dtype=torch.float32, device=dev),
                     logits=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev),
                     out=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev))
+        if not split and self.segments:
+            bufs["head_scratch"] = torch.zeros((B, self.segments[0].units), dtype=torch.float32, device=dev)
         for sgm in self.segments:
             bufs["H"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev))
             bufs["H_lo"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev) if split else None)
@@ -361,7 +377,18 @@ class XVector:
                                           _lib.ptr(bufs["pooled"]), _lib.ptr(bufs["var_raw"]),
                                           _lib.ptr(bufs["pooled_hi"]), _lib.ptr(bufs["pooled_lo"]), st))
         a, a_lo = bufs["pooled_hi"], bufs["pooled_lo"]
+        fused = self._head_fused() and not upto_embedding
+        if fused:
+            l1, l2 = self.layers[n], self.layers[n + 1]
+            _lib.check(lib.lbx_head_fwd(_lib.ptr(a), B, l1["K"], ops._addr(self.w16, l1["w_off"]), l1["ldw"],
+                                        ops._addr(self.params, l1["b_off"]), l1["N"],
+                                        ops._addr(self.w16, l2["w_off"]), l2["ldw"], ops._addr(self.params, l2["b_off"]),
+                                        l2["N"], _lib.ptr(bufs["H"][0]), _lib.ptr(bufs["H"][1]),
+                                        _lib.ptr(bufs["head_scratch"]), _lib.ptr(self._head_sync), st))
+            a, a_lo = bufs["H"][1], None
         for i, sgm in enumerate(self.segments):
+            if fused:
+                break
             ly = self.layers[n + i]
             if i == 0 and upto_embedding:
                 self._dense(bufs, a, a_lo, B, ly, relu=False, out_f32=bufs["emb"])
@@ -432,13 +459,12 @@ class XVector:
         n = len(self.frames)
         out_ly = self.layers[-1]
         n_seg = len(self.segments)
-        # few classes + cross-entropy: output layer, loss and the layer's whole backward can run as ONE launch
-        # (lbx_dense_xent_head) instead of GEMM + loss + 2 GEMMs.  Opt-in (LBX_FUSED_HEAD=1): measured on B200 it removes
-        # three launches but no time (0.4396 vs 0.4391 ms/step) — the dense head is bound by the serial latency of its
-        # kernels, not by their work.
+        # few classes + cross-entropy: output layer, loss and the layer's whole backward run as ONE launch
+        # (lbx_dense_xent_head) instead of GEMM + loss + 2 GEMMs (LBX_FUSED_HEAD=0 disables).  Together with the fused
+        # segment layers (lbx_head_fwd / lbx_head_bwd) the dense head is 3 launches instead of 11.
         fused_head = (loss == "xent" and self.num_outputs <= 8 and n_seg >= 1 and out_ly["K"] <= 1024 and
                       out_ly["K"] * (4 * self.num_outputs + 20) + 256 <= 49152 and
-                      os.environ.get("LBX_FUSED_HEAD", "0") == "1")
+                      os.environ.get("LBX_FUSED_HEAD", "1") != "0")
         cur = torch.cuda.current_stream(self.device)
         ev_zero = None
         if self._sharded is not None:
@@ -492,11 +518,23 @@ class XVector:
         # weight gradients are leaves of the backward graph (only the optimizer reads them): they run on a side
         # stream, concurrently with the latency-bound chain of data-gradient kernels, and are joined before Adam
         side = self._side_stream if self.overlap_wgrad else None
+        side_used = [False]
 
-        def wgrad(a, a_rows, a_cols, lda, dz, dz_cols, dz_pitch, ly, a_off=0, dz_off=0):
+        # frame-layer weight gradients: collected and issued as ONE grouped launch after the data-gradient chain
+        # (lbx_wgrad_grouped: the k-blocks of all layers cut into equal ranges, one per CTA pair); LBX_WGRAD_GROUPED=0
+        # restores one split-K GEMM per layer on the side stream
+        dp_mode = os.environ.get("LBX_DP_MODE", "single")      # single | buckets | none (measurement only)
+        grouped = [] if (os.environ.get("LBX_WGRAD_GROUPED", "1") != "0" and dp_mode != "buckets") else None
+
+        def wgrad(a, a_rows, a_cols, lda, dz, dz_cols, dz_pitch, ly, a_off=0, dz_off=0, group=False):
+            if group and grouped is not None:
+                grouped.append(dict(a=a, rows=a_rows, a_cols=a_cols, lda=lda, a_off=a_off, b=dz, b_cols=dz_cols,
+                                    ldb=dz_pitch, b_off=dz_off, out=g, ldo=ly["ldw"], out_off=ly["w_off"]))
+                return
             tiles = -(-a_cols // 128) * -(-dz_cols // 256)
             ks = max(1, min(-(-a_rows // 64), 148 // tiles))
             if side is not None:
+                side_used[0] = True
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 side.wait_event(ev)
@@ -511,7 +549,6 @@ class XVector:
         # "buckets" all-reduces three buckets on the side stream as soon as each is complete; measured on 2 x B200 it is
         # SLOWER (0.712 vs 0.619 ms/step; no exchange: 0.572): the NCCL kernels take SMs away from the persistent
         # one-CTA-per-SM GEMMs they overlap with.  Kept for experiments (LBX_DP_MODE=buckets).
-        dp_mode = os.environ.get("LBX_DP_MODE", "single")      # single | buckets | none (measurement only)
 
         def reduce_bucket(first_layer, last_layer):
             if process_group is None or dp_mode != "buckets":
@@ -520,6 +557,7 @@ class XVector:
             lo = self.layers[first_layer]["w_off"]
             hi = self.layers[last_layer]["b_off"] + self.layers[last_layer]["ldw"]
             if side is not None:
+                side_used[0] = True
                 ev = torch.cuda.Event()
                 ev.record(cur)                     # bias gradients of the bucket come from main-stream kernels
                 side.wait_event(ev)
@@ -536,7 +574,17 @@ class XVector:
         if fused_head:             # the output layer is done: continue from the gradient w.r.t. the last segment layer
             first = n_seg - 1
             dz, dz_cols, dz_pitch = bufs["dH"][-1], out_ly["K"], out_ly["K"]
+        head_fused = self._head_fused()
         for i in range(first, -1, -1):
+            if head_fused and i == 1:
+                # both segment layers' backward in one persistent launch: dH1 (+ its bias gradient), dW2, d pooled, dW1
+                l1, l2 = self.layers[n], self.layers[n + 1]
+                _lib.check(lib.lbx_head_bwd(_lib.ptr(dz), _lib.ptr(bufs["pooled_hi"]), _lib.ptr(bufs["H"][0]), B, l1["K"],
+                                            l1["N"], l2["N"], ops._addr(self.w16, l1["w_off"]), l1["ldw"],
+                                            ops._addr(self.w16, l2["w_off"]), l2["ldw"], _lib.ptr(bufs["dH"][0]),
+                                            _lib.ptr(bufs["gpool"]), ops._addr(g, l1["w_off"]), ops._addr(g, l1["b_off"]),
+                                            ops._addr(g, l2["w_off"]), _lib.ptr(self._head_sync), st))
+                break
             ly = self.layers[n + i]
             wgrad(acts[i], B, ly["K"], ly["K"], dz, dz_cols, dz_pitch, ly)
             if i > 0:      # d hidden = (dz . W^T) masked by the ReLU of the layer below (+ its bias gradient), one launch
@@ -562,7 +610,7 @@ class XVector:
             dZ = bufs["dZ"][L]
             dz_pitch = bufs["cnp"] if L == n - 1 else ly["N"]
             dz_off = 0 if L == n - 1 else geo.pad[L + 1] * ly["N"]
-            wgrad(bufs["X"][L], rows, ly["K"], ly["s"] * ly["c_in"], dZ, ly["N"], dz_pitch, ly, dz_off=dz_off)
+            wgrad(bufs["X"][L], rows, ly["K"], ly["s"] * ly["c_in"], dZ, ly["N"], dz_pitch, ly, dz_off=dz_off, group=True)
             if L == mid and mid > 0:
                 reduce_bucket(mid, n - 1)
             if L == 0:
@@ -598,7 +646,12 @@ class XVector:
                              b1_off=ly["w_off"] + taps[-1] * c * ly["ldw"], terms=terms, out_off=rho * c,
                              mask_src=bufs["X"][L], mask_off=rho * c, colsum=g, colsum_off=below["b_off"],
                              colsum_mod=c)
-        if side is not None:
+        if grouped:
+            # largest problems first: the ranges of the line that end up shortest in wall time come last
+            grouped.sort(key=lambda q: -q["rows"] * q["a_cols"] * q["b_cols"])
+            for i in range(0, len(grouped), 8):
+                ops.wgrad_grouped(grouped[i:i + 8], self.device)
+        if side is not None and side_used[0]:
             ev = torch.cuda.Event()
             ev.record(side)
             cur.wait_event(ev)

@@ -16,11 +16,33 @@ GEMM_RECORD = None
 
 
 def replay(descs, device):
-    """Re-issue recorded GEMM descriptors on the current stream."""
+    """Re-issue recorded GEMM launches (single descriptors and grouped weight-gradient launches) on the current stream."""
     st = _lib.stream_ptr(device)
-    fn = _lib.lib().lbx_gemm_bf16
+    lib = _lib.lib()
     for d, _keep, _shape in descs:
-        _lib.check(fn(ctypes.byref(d), st))
+        if isinstance(d, tuple):
+            _lib.check(lib.lbx_wgrad_grouped(d[0], d[1], st))
+        else:
+            _lib.check(lib.lbx_gemm_bf16(ctypes.byref(d), st))
+
+
+def wgrad_grouped(problems, device):
+    """lbx_wgrad_grouped: out += a^T . b for every problem (dicts with a, rows, a_cols, lda, a_off, b, b_cols, ldb, b_off,
+    out, ldo, out_off; offsets in elements) in one persistent launch on the current stream."""
+    if not problems:
+        return
+    arr = (_lib.WgradDesc * len(problems))()
+    keep, shapes = [], []
+    for d, q in zip(arr, problems):
+        assert q["a"].dtype == torch.bfloat16 and q["b"].dtype == torch.bfloat16 and q["out"].dtype == torch.float32
+        d.a, d.rows, d.a_cols, d.lda = _addr(q["a"], q.get("a_off", 0)), q["rows"], q["a_cols"], q["lda"]
+        d.b, d.b_cols, d.ldb = _addr(q["b"], q.get("b_off", 0)), q["b_cols"], q["ldb"]
+        d.out, d.ldo = _addr(q["out"], q.get("out_off", 0)), q["ldo"]
+        keep.append((q["a"], q["b"], q["out"]))
+        shapes.append((q["a_cols"], q["b_cols"], q["rows"]))
+    if GEMM_RECORD is not None:
+        GEMM_RECORD.append(((arr, len(problems)), keep, shapes))
+    _lib.check(_lib.lib().lbx_wgrad_grouped(arr, len(problems), _lib.stream_ptr(device)))
 
 
 def _addr(t, offset_elems=0):

@@ -158,3 +158,64 @@ def test_colsum_epilogue(ops):
     ref = torch.where(y.double() > 0, dz.double() @ w.double().T, torch.zeros((), device="cuda", dtype=torch.double))
     ref_cs = ref.sum(dim=0).view(2, C).sum(dim=0)
     assert float((cs.double() - ref_cs).abs().max()) < 1e-3 * float(ref.abs().sum(dim=0).max())
+
+
+def _wgrad_problem(rows, a_cols, b_cols, seed, lda=None, ldo=None):
+    """One weight-gradient problem: A [rows, a_cols] read through a view of pitch lda (lda < a_cols: overlapping rows,
+    the implicit im2col of a Conv1D with kernel_size > strides), B [rows, b_cols], out fp32 [a_cols, ldo]."""
+    lda = lda or a_cols
+    ldo = ldo or -(-b_cols // 8) * 8
+    flat = _rand(((rows - 1) * lda + a_cols + 64,), seed).bfloat16()
+    ldb = -(-b_cols // 8) * 8
+    b_full = _rand((rows, ldb), seed + 1, 0.05).bfloat16()
+    b = b_full[:, :b_cols]
+    out = _rand((a_cols, ldo), seed + 2)                       # the launch ACCUMULATES into whatever is there
+    a_view = torch.as_strided(flat, (rows, a_cols), (lda, 1))
+    ref = out[:, :b_cols].double() + a_view.double().T @ b.double()
+    absref = out[:, :b_cols].double().abs() + a_view.double().abs().T @ b.double().abs()
+    q = dict(a=flat, rows=rows, a_cols=a_cols, lda=lda, b=b_full, b_cols=b_cols, ldb=ldb, out=out, ldo=ldo)
+    return q, ref, absref
+
+
+@pytest.mark.parametrize("shapes", [
+    [(1000, 128, 256)],                                        # one tile, one problem
+    [(70, 200, 512, 40)],                                      # overlapping rows (frame1: k=5, C=40, stride 1), 2 k-blocks
+    [(26112, 1536, 512), (8704, 1536, 512), (8704, 512, 1500), (8704, 512, 512), (52224, 200, 512, 40)],   # config 3
+    [(5000, 512, 1500), (64, 64, 4), (3, 8, 8), (777, 264, 72), (12800, 1536, 512, 1024), (1, 512, 512)],
+])
+def test_wgrad_grouped(ops, shapes):
+    """lbx_wgrad_grouped (all problems in one stream-K launch) vs fp64 A^T.B of the same bf16 operands; the pitch-padding
+    columns of the outputs must stay untouched."""
+    probs, refs = [], []
+    for i, sh in enumerate(shapes):
+        rows, a_cols, b_cols = sh[:3]
+        q, ref, absref = _wgrad_problem(rows, a_cols, b_cols, 100 + 10 * i, lda=sh[3] if len(sh) > 3 else None)
+        probs.append(q)
+        refs.append((ref, absref, q["out"][:, b_cols:].clone()))
+    ops.wgrad_grouped(probs, torch.device("cuda"))
+    torch.cuda.synchronize()
+    for q, (ref, absref, pad) in zip(probs, refs):
+        _check(q["out"][:, :q["b_cols"]], ref, absref, tol=2e-5)
+        assert torch.equal(q["out"][:, q["b_cols"]:], pad)
+
+
+def test_wgrad_grouped_matches_per_layer_launches(ops):
+    """Same problems through lbx_gemm_bf16 (layout TN, split-K, atomic epilogue): both paths sum the same products in
+    fp32, only the order differs."""
+    shapes = [(8704, 1536, 512), (8704, 512, 1500), (17408, 200, 512)]
+    probs = []
+    for i, (rows, a_cols, b_cols) in enumerate(shapes):
+        q, _, _ = _wgrad_problem(rows, a_cols, b_cols, 300 + 10 * i, lda=40 if a_cols == 200 else None)
+        q["out"].zero_()
+        probs.append(q)
+    singles = []
+    for q in probs:
+        o = torch.zeros_like(q["out"])
+        ops.gemm(q["a"], q["rows"], q["a_cols"], q["lda"], q["b"], q["rows"], q["b_cols"], q["ldb"], o, q["ldo"],
+                 layout=1, k_splits=9, epi_atomic=True)
+        singles.append(o)
+    ops.wgrad_grouped(probs, torch.device("cuda"))
+    torch.cuda.synchronize()
+    for q, o in zip(probs, singles):
+        den = float(o.abs().max())
+        assert float((q["out"] - o).abs().max()) < 2e-5 * den + 1e-6

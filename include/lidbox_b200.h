@@ -206,8 +206,11 @@ int lbx_vad_compact_f32(const float* sig, long long B, long long N, int frame_le
  * A/B are bf16 views: `rows` x `cols` with row pitch ld (elements, multiple of 8; may be SMALLER than cols: a causal
  * Conv1D with kernel k and stride s over NWC activations is the NT GEMM whose A view has cols = k*C_in and
  * lda = s*C_in on the zero-left-padded activation buffer — no im2col).
- * n_terms (1..3) accumulating passes over the contraction; pass t reads A plane term_a[t] (0: a0, 1: a1) shifted by
- * term_a_row[t] rows, and B plane term_b[t] (0: b0, 1: b1).  Two uses:
+ * n_terms (1..LBX_GEMM_MAX_TERMS) accumulating passes over the contraction; pass t reads A plane term_a[t] (0: a0,
+ * 1: a1) shifted by term_a_row[t] rows, and B plane term_b[t] (0: b0, 1: b1) shifted by term_b_row[t] rows of the B view
+ * (whose full extent is then b_map_rows >= term_b_row[t] + b_rows).  Three uses:
+ *   dilated causal Conv1D (dilation_rate d, stride 1): tap j is the pass that reads the activations j*d rows further
+ *   down against rows [j*C_in, (j+1)*C_in) of the Keras kernel (and the mirror image in its data gradient);
  *   "bf16x3": a1/b1 = bf16 residual planes (x - bf16(x)), passes (a0,b0) (a0,b1) (a1,b0): fp32-grade forward results;
  *   gather-form data gradient of a strided conv (k > stride): output time tau = t*stride + j receives tap j of row t,
  *   so every residue class of tau is ONE GEMM whose passes read dZ shifted by -i rows against the weights of tap
@@ -216,6 +219,7 @@ int lbx_vad_compact_f32(const float* sig, long long B, long long N, int frame_le
  * then either atomicAdd into fp32 out (epi_atomic, required for k_splits > 1), or out (+)= x as fp32 / bf16
  * (plus out_lo = bf16 residual).  Rows with (m % rows_per_utt) >= valid_rows are stored as ZERO when rows_per_utt > 0 (they land on
  * destination rows that must stay zero: junk rows and the next utterance's causal padding). */
+#define LBX_GEMM_MAX_TERMS 5
 typedef struct lbx_gemm_t {
   const void* a0; const void* a1;
   long long a_rows; int a_cols; long long lda;
@@ -223,13 +227,17 @@ typedef struct lbx_gemm_t {
   long long b_rows; int b_cols; long long ldb;
   int layout;
   int n_terms;
-  int term_a[3]; int term_b[3]; int term_a_row[3];
+  int term_a[LBX_GEMM_MAX_TERMS]; int term_b[LBX_GEMM_MAX_TERMS]; int term_a_row[LBX_GEMM_MAX_TERMS];
+  int term_b_row[LBX_GEMM_MAX_TERMS];
+  long long b_map_rows;     /* 0 = b_rows */
   int k_splits;
   int epi_atomic;
   int out_dtype;            /* LBX_F32 | LBX_BF16 */
   void* out; void* out_lo; long long ldo;
   const float* bias;
   int relu;
+  const float* post_scale;  /* optional [N]: x = x * post_scale[n] + post_shift[n] AFTER the activation (inference-time */
+  const float* post_shift;  /* BatchNormalization behind a frame layer: conv -> ReLU -> BN, lidbox/models/xvector_2d.py:41-43) */
   int rows_per_utt; int valid_rows;
   const void* mask_src;     /* bf16, indexed like out */
   int accumulate;
@@ -304,12 +312,13 @@ int lbx_dense_xent_head(const void* h_bf16, const void* w_bf16, const float* bia
 
 /* Fused dense head (lidbox/models/xvector.py:61-63: segment1 = Dense(K1 -> N1) + ReLU, segment2 = Dense(N1 -> N2) +
  * ReLU) in ONE persistent launch: h1 = bf16(relu(pooled . W1 + b1)), h2 = bf16(relu(h1 . W2 + b2)).  pooled [B, K1],
- * h1 [B, N1], h2 [B, N2] dense bf16; W1 [K1, ldw1], W2 [N1, ldw2] bf16 copies of the Keras kernels; scratch = B*N1
- * floats that are zero on entry and left zero; sync_ws = 512 zero-initialised uint32 owned by the caller (grid-barrier
+ * h1 [B, N1], h2 [B, N2] dense bf16; W1 [K1, ldw1], W2 [N1, ldw2] bf16 copies of the Keras kernels; scratch = scratch_floats
+ * (>= B*N1, ideally 8*B*N1) floats of workspace — the split-K partial sums of segment1 go to one slab per split and are
+ * added in a fixed order, so the result is bit-reproducible; sync_ws = 512 zero-initialised uint32 owned by the caller (grid-barrier
  * state: sync_ws[2] != 0 reports a barrier time-out).  All widths / pitches multiples of 8. */
 int lbx_head_fwd(const void* pooled_bf16, long long B, int K1, const void* w1_bf16, int ldw1, const float* b1, int N1,
                  const void* w2_bf16, int ldw2, const float* b2, int N2, void* h1_bf16, void* h2_bf16, float* scratch,
-                 unsigned int* sync_ws, void* stream);
+                 long long scratch_floats, unsigned int* sync_ws, void* stream);
 /* Backward of the same two layers in ONE launch, from dh2 = d loss / d (segment2 pre-activation) [B, N2] bf16:
  * dh1 = (dh2 . W2^T) * (h1 > 0) [B, N1] bf16, db1 += column sums of dh1, dW2 += h1^T . dh2, then
  * gpool = dh1 . W1^T [B, K1] fp32 (overwritten) and dW1 += pooled^T . dh1.  dW1 / dW2 have pitches ldw1 / ldw2. */

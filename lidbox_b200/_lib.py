@@ -19,9 +19,11 @@ class GemmDesc(ctypes.Structure):
     _fields_ = [
         ("a0", c_void_p), ("a1", c_void_p), ("a_rows", c_ll), ("a_cols", c_int), ("lda", c_ll),
         ("b0", c_void_p), ("b1", c_void_p), ("b_rows", c_ll), ("b_cols", c_int), ("ldb", c_ll),
-        ("layout", c_int), ("n_terms", c_int), ("term_a", c_int * 3), ("term_b", c_int * 3), ("term_a_row", c_int * 3),
+        ("layout", c_int), ("n_terms", c_int), ("term_a", c_int * 5), ("term_b", c_int * 5), ("term_a_row", c_int * 5),
+        ("term_b_row", c_int * 5), ("b_map_rows", c_ll),
         ("k_splits", c_int), ("epi_atomic", c_int), ("out_dtype", c_int),
         ("out", c_void_p), ("out_lo", c_void_p), ("ldo", c_ll), ("bias", c_void_p), ("relu", c_int),
+        ("post_scale", c_void_p), ("post_shift", c_void_p),
         ("rows_per_utt", c_int), ("valid_rows", c_int), ("mask_src", c_void_p), ("accumulate", c_int),
         ("tile_n", c_int), ("colsum", c_void_p), ("colsum_mod", c_int),
     ]
@@ -95,7 +97,7 @@ SIGNATURES = {
     "lbx_logsoftmax_xent": (c_int, [_P, _P, c_ll, c_int, _P, _P, _P, c_int, c_float, _P, _P]),
     "lbx_ap_loss": (c_int, [_P, _P, c_ll, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_int, _P, c_float, _P, _P]),
     "lbx_wgrad_grouped": (c_int, [_P, c_int, _P]),
-    "lbx_head_fwd": (c_int, [_P, c_ll, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, _P]),
+    "lbx_head_fwd": (c_int, [_P, c_ll, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_ll, _P, _P]),
     "lbx_head_bwd": (c_int, [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P, c_int, _P]),
     "lbx_adam_step_sharded": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P, _P, c_float, c_float, c_float,

@@ -56,9 +56,10 @@ struct Cfg {
 struct GemmParams {
   int M, N, K;             // output rows, output cols, contraction length
   int layout;              // 0 NT, 1 TN
-  int n_terms;             // accumulating passes over the contraction (1..3)
-  int term_a[3], term_b[3];   // which A / B tensor map each pass reads (0 or 1)
-  int term_arow[3];        // row offset added to the A coordinate of each pass (NT / NN layouts)
+  int n_terms;             // accumulating passes over the contraction (1..LBX_GEMM_MAX_TERMS)
+  int term_a[LBX_GEMM_MAX_TERMS], term_b[LBX_GEMM_MAX_TERMS];   // which A / B tensor map each pass reads (0 or 1)
+  int term_arow[LBX_GEMM_MAX_TERMS];   // row offset added to the A coordinate of each pass (NT / NN layouts)
+  int term_brow[LBX_GEMM_MAX_TERMS];   // row offset added to the B row coordinate of each pass (NT: N index, NN: K index)
   int k_splits;            // split-K partitions (>= 1)
   int epi_atomic;          // 1: atomicAdd fp32 into out (split-K / gradient accumulation)
   int out_dtype;           // LBX_F32 / LBX_BF16
@@ -67,6 +68,8 @@ struct GemmParams {
   long long ldo;           // output row pitch in elements (may be < N for the overlapping dgrad view)
   const float* bias;       // [N] or NULL
   int relu;
+  const float* post_scale; // optional per-column affine AFTER the activation (inference-time BatchNormalization)
+  const float* post_shift;
   int rows_per_utt;        // > 0: rows with (m % rows_per_utt) >= valid_rows are not stored
   int valid_rows;
   const __nv_bfloat16* mask_src;   // optional: keep x only where mask_src[m*ldo + n] > 0 (ReLU backward)
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int term = 0; term < p.n_terms; ++term) {
           const CUtensorMap* mA = p.term_a[term] ? &mapA1 : &mapA0;
           const CUtensorMap* mB = p.term_b[term] ? &mapB1 : &mapB0;
-          const int arow = p.term_arow[term];
+          const int arow = p.term_arow[term], brow = p.term_brow[term];
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             unsigned char* sA = smem + (size_t)stage * STAGE_BYTES;
@@ -206,11 +209,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                   tma_load_2d(mA, full_bar + stage, sA + i * 8192, m_blk * BM + i * 64, kb * BK);
               }
               if (!B_MN) {
-                tma_load_2d(mB, full_bar + stage, sB, kb * BK, n_blk * BN);
+                tma_load_2d(mB, full_bar + stage, sB, kb * BK, n_blk * BN + brow);
               } else {
 #pragma unroll
                 for (int i = 0; i < BN / 64; ++i)
-                  tma_load_2d(mB, full_bar + stage, sB + i * 8192, n_blk * BN + i * 64, kb * BK);
+                  tma_load_2d(mB, full_bar + stage, sB + i * 8192, n_blk * BN + i * 64, kb * BK + brow);
               }
             } else {
               // all bytes of both CTAs are counted on the LEADER's full barrier (the MMA issuer waits there)
@@ -225,11 +228,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                   tma_load_2d_pair(mA, lead_full, sA + i * 8192, m_blk * BM + i * 64, kb * BK);
               }
               if (!B_MN) {
-                tma_load_2d_pair(mB, lead_full, sB, kb * BK, n_col0);
+                tma_load_2d_pair(mB, lead_full, sB, kb * BK, n_col0 + brow);
               } else {
 #pragma unroll
                 for (int i = 0; i < BN_LOCAL / 64; ++i)
-                  tma_load_2d_pair(mB, lead_full, sB + i * 8192, n_col0 + i * 64, kb * BK);
+                  tma_load_2d_pair(mB, lead_full, sB + i * 8192, n_col0 + i * 64, kb * BK + brow);
               }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -395,7 +398,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             for (int j = 0; j < 32; ++j) x[j] = 0.0f;
           }
           uint32_t pk[16];
-          if (p.relu) {
+          if (p.post_scale != nullptr) {          // activation, then the per-column affine (zero rows stay zero)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = p.relu ? fmaxf(x[j], 0.0f) : x[j];
+              const int nn = n0 + j < p.N ? n0 + j : p.N - 1;
+              v = fmaf(v, __ldg(p.post_scale + nn), __ldg(p.post_shift + nn));
+              x[j] = kill_row ? 0.0f : v;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = cvt_bf16x2(x[2 * j], x[2 * j + 1]);
+          } else if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = cvt_bf16x2_relu(x[2 * j], x[2 * j + 1]);
           } else {
@@ -498,6 +511,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+        }
+        if (p.post_scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) x[j] = fmaf(x[j], __ldg(p.post_scale + n0 + j), __ldg(p.post_shift + n0 + j));
         }
         if (row_zero || !in_range) {
 #pragma unroll
@@ -710,7 +728,7 @@ using namespace lbx;
 extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   LBX_CHECK_ARG(g != nullptr, "NULL gemm descriptor");
   LBX_CHECK_ARG(g->layout >= 0 && g->layout <= 2, "layout must be 0 (NT), 1 (TN) or 2 (NN)");
-  LBX_CHECK_ARG(g->n_terms >= 1 && g->n_terms <= 3, "n_terms must be 1, 2 or 3");
+  LBX_CHECK_ARG(g->n_terms >= 1 && g->n_terms <= LBX_GEMM_MAX_TERMS, "n_terms must be in [1, %d]", LBX_GEMM_MAX_TERMS);
   LBX_CHECK_ARG(g->a_rows >= 0 && g->a_cols >= 0 && g->b_rows >= 0 && g->b_cols >= 0, "negative extent");
   GemmParams p{};
   p.layout = g->layout;
@@ -737,7 +755,11 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
     LBX_CHECK_ARG((g->term_a[t] == 0 || (g->term_a[t] == 1 && g->a1)) && (g->term_b[t] == 0 || (g->term_b[t] == 1 && g->b1)),
                   "term %d selects an operand plane that was not given", t);
     LBX_CHECK_ARG(g->term_a_row[t] == 0 || g->layout != 1, "row offsets are not available in the TN layout");
+    LBX_CHECK_ARG(g->term_b_row[t] == 0 || g->layout != 1, "row offsets are not available in the TN layout");
+    LBX_CHECK_ARG(g->term_b_row[t] >= 0 && g->term_b_row[t] + g->b_rows <= (g->b_map_rows > 0 ? g->b_map_rows : g->b_rows),
+                  "term %d: B row offset %d + %lld rows exceeds the B view", t, g->term_b_row[t], g->b_rows);
     p.term_a[t] = g->term_a[t]; p.term_b[t] = g->term_b[t]; p.term_arow[t] = g->term_a_row[t];
+    p.term_brow[t] = g->term_b_row[t];
   }
   LBX_CHECK_ARG(g->lda % 8 == 0 && g->ldb % 8 == 0, "operand pitches must be multiples of 8 elements (16 bytes)");
   LBX_CHECK_ARG((reinterpret_cast<uintptr_t>(g->a0) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->b0) & 15) == 0,
@@ -757,6 +779,10 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   p.out_dtype = g->out_dtype;
   p.out = g->out; p.out_lo = g->out_lo; p.ldo = g->ldo;
   p.bias = g->bias; p.relu = g->relu;
+  LBX_CHECK_ARG((g->post_scale == nullptr) == (g->post_shift == nullptr), "post_scale and post_shift come together");
+  LBX_CHECK_ARG(g->post_scale == nullptr || (!g->epi_atomic && !g->accumulate && g->mask_src == nullptr && g->colsum == nullptr),
+                "the post-activation affine is a forward-pass epilogue (no atomics / accumulate / mask / colsum)");
+  p.post_scale = g->post_scale; p.post_shift = g->post_shift;
   p.rows_per_utt = g->rows_per_utt; p.valid_rows = g->valid_rows;
   p.mask_src = reinterpret_cast<const __nv_bfloat16*>(g->mask_src);
   p.accumulate = g->accumulate;
@@ -777,10 +803,11 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   const bool pair = g_use_pair && bn == 256;
   const int boxA_rows = g->layout == 1 ? 64 : BM, boxB_rows = g->layout == 0 ? (pair ? bn / 2 : bn) : 64;
   if ((rc = make_map(&mA0, g->a0, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
-  if ((rc = make_map(&mB0, g->b0, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
+  const long long b_map_rows = g->b_map_rows > 0 ? g->b_map_rows : g->b_rows;
+  if ((rc = make_map(&mB0, g->b0, b_map_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
   mA1 = mA0; mB1 = mB0;
   if (g->a1 && (rc = make_map(&mA1, g->a1, g->a_rows, g->a_cols, g->lda, 64, boxA_rows))) return rc;
-  if (g->b1 && (rc = make_map(&mB1, g->b1, g->b_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
+  if (g->b1 && (rc = make_map(&mB1, g->b1, b_map_rows, g->b_cols, g->ldb, 64, boxB_rows))) return rc;
   mOut = mA0; mMask = mA0;
   if (p.fast) {
     if ((rc = make_map(&mOut, g->out, p.M, p.N, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;

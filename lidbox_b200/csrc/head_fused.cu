@@ -48,6 +48,7 @@ struct HeadGemm {
   float* out_f32;
   bf16* out_bf16;
   long long ldo;
+  long long split_stride;  // HEPI_STORE_F32 with k_splits > 1: split i stores its partial tile into slab i (deterministic)
   const float* bias;
   int relu;
   const bf16* mask;        // HEPI_MASK_BF16_COLSUM: keep x where mask[m, n] > 0 (pitch ldo)
@@ -58,8 +59,10 @@ struct HeadStep {
   int kind;
   int n_gemms;
   HeadGemm g[2];
-  // HSTEP_FINALIZE: out[m, n] = bf16(act(z[m, n] + bias[n])), z = 0     (z dense [M, N], N % 4 == 0)
+  // HSTEP_FINALIZE: out[m, n] = bf16(act(sum_i z[i][m, n] + bias[n]))   (n_slabs dense [M, N] slabs, summed in order;
+  // N % 4 == 0)
   float* z;
+  int n_slabs;
   const float* bias;
   bf16* out;
   int M, N, relu;
@@ -151,7 +154,7 @@ struct HeadPipe {
 // One 64 x 128 output tile over the k-chunks [kc0, kc1) of HT_K.
 template <int AT, int BT>
 __device__ __forceinline__ void gemm_tile(const HeadGemm& g, const CUtensorMap* mapA, const CUtensorMap* mapB, int m_tile,
-                                          int n_tile, int kc0, int kc1, unsigned char* smem, HeadPipe& pipe) {
+                                          int n_tile, int split, int kc0, int kc1, unsigned char* smem, HeadPipe& pipe) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3;                 // 2 x 4 warps, 32 x 32 outputs each
   const int m0 = m_tile * HT_M, n0 = n_tile * HT_N;
@@ -265,7 +268,7 @@ __device__ __forceinline__ void gemm_tile(const HeadGemm& g, const CUtensorMap* 
   const int gq = lane >> 2, tq = lane & 3;
   const int epi = g.epi, relu = g.relu;
   const long long ldo = g.ldo;
-  float* const out_f32 = g.out_f32;
+  float* const out_f32 = g.out_f32 + split * g.split_stride;
   bf16* const out_bf16 = g.out_bf16;
   const float* const bias = g.bias;
   const bf16* const mask = g.mask;
@@ -385,18 +388,20 @@ __global__ void __launch_bounds__(HT_THREADS, 1) head_chain_kernel(const __grid_
         const int nkc = (g.K + HT_K - 1) / HT_K;
         const int per = (nkc + g.k_splits - 1) / g.k_splits;
         const int kc0 = split * per, kc1 = min(nkc, kc0 + per);
-        if (kc0 >= kc1) continue;
-        if (g.a_trans == 0 && g.b_trans == 1) gemm_tile<0, 1>(g, &P.maps[g.map_a], &P.maps[g.map_b], m_tile, n_tile, kc0, kc1, smem, pipe);
-        else if (g.a_trans == 0 && g.b_trans == 0) gemm_tile<0, 0>(g, &P.maps[g.map_a], &P.maps[g.map_b], m_tile, n_tile, kc0, kc1, smem, pipe);
-        else if (g.a_trans == 1 && g.b_trans == 1) gemm_tile<1, 1>(g, &P.maps[g.map_a], &P.maps[g.map_b], m_tile, n_tile, kc0, kc1, smem, pipe);
-        else gemm_tile<1, 0>(g, &P.maps[g.map_a], &P.maps[g.map_b], m_tile, n_tile, kc0, kc1, smem, pipe);
+        if (kc0 >= kc1) continue;               // host: every split is non-empty
+        if (g.a_trans == 0 && g.b_trans == 1) gemm_tile<0, 1>(g, &P.maps[g.map_a], &P.maps[g.map_b], m_tile, n_tile, split, kc0, kc1, smem, pipe);
+        else if (g.a_trans == 0 && g.b_trans == 0) gemm_tile<0, 0>(g, &P.maps[g.map_a], &P.maps[g.map_b], m_tile, n_tile, split, kc0, kc1, smem, pipe);
+        else if (g.a_trans == 1 && g.b_trans == 1) gemm_tile<1, 1>(g, &P.maps[g.map_a], &P.maps[g.map_b], m_tile, n_tile, split, kc0, kc1, smem, pipe);
+        else gemm_tile<1, 0>(g, &P.maps[g.map_a], &P.maps[g.map_b], m_tile, n_tile, split, kc0, kc1, smem, pipe);
       }
     } else if (st.kind == HSTEP_FINALIZE) {
       const long long n4 = (long long)st.M * st.N / 4;
       for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4* zp = reinterpret_cast<float4*>(st.z) + i;
-        float4 z = *zp;
-        *zp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 z = reinterpret_cast<const float4*>(st.z)[i];
+        for (int sl = 1; sl < st.n_slabs; ++sl) {
+          const float4 zs = reinterpret_cast<const float4*>(st.z)[(long long)sl * n4 + i];
+          z.x += zs.x; z.y += zs.y; z.z += zs.z; z.w += zs.w;
+        }
         const long long e = 4 * i;
         const int m = (int)(e / st.N), n = (int)(e - (long long)m * st.N);
         if (st.bias) {
@@ -453,7 +458,9 @@ static void set_tiles(HeadGemm& g, int k_splits) {
   g.m_tiles = (g.M + HT_M - 1) / HT_M;
   g.n_tiles = (g.N + HT_N - 1) / HT_N;
   const int nkc = (g.K + HT_K - 1) / HT_K;
-  g.k_splits = k_splits < 1 ? 1 : (k_splits > nkc ? nkc : k_splits);
+  int ks = k_splits < 1 ? 1 : (k_splits > nkc ? nkc : k_splits);
+  const int per = (nkc + ks - 1) / ks;
+  g.k_splits = (nkc + per - 1) / per;            // no empty split
 }
 
 // tensor maps of one GEMM's operands (see gemm_tile for the box shapes)
@@ -478,7 +485,8 @@ using namespace lbx;
 
 extern "C" int lbx_head_fwd(const void* pooled_bf16, long long B, int K1, const void* w1_bf16, int ldw1, const float* b1,
                             int N1, const void* w2_bf16, int ldw2, const float* b2, int N2, void* h1_bf16,
-                            void* h2_bf16, float* scratch, unsigned int* sync_ws, void* stream) {
+                            void* h2_bf16, float* scratch, long long scratch_floats, unsigned int* sync_ws,
+                            void* stream) {
   LBX_CHECK_ARG(B >= 0 && B <= 1 << 20 && K1 >= 8 && N1 >= 8 && N2 >= 8, "bad head shape");
   LBX_CHECK_ARG(K1 % 8 == 0 && N1 % 8 == 0 && N2 % 8 == 0 && ldw1 % 8 == 0 && ldw2 % 8 == 0,
                 "layer widths and pitches must be multiples of 8");
@@ -499,15 +507,21 @@ extern "C" int lbx_head_fwd(const void* pooled_bf16, long long B, int K1, const 
   int n_maps = 0;
   g0.M = (int)B; g0.N = N1; g0.K = K1;
   if ((rc = set_operands(P, n_maps, g0, pooled_bf16, K1, 0, w1_bf16, ldw1, 1))) return rc;
-  g0.epi = HEPI_ATOMIC; g0.out_f32 = scratch; g0.ldo = N1;
+  // every split stores its partial sums into its own slab of the scratch buffer; the finalize step adds the slabs in
+  // a fixed order: the forward pass is bit-reproducible (no floating-point atomics)
+  g0.epi = HEPI_STORE_F32; g0.out_f32 = scratch; g0.ldo = N1; g0.split_stride = B * N1;
   set_tiles(g0, 1);
   {
     const int tiles = g0.m_tiles * g0.n_tiles;
-    set_tiles(g0, tiles >= g_head_grid ? 1 : g_head_grid / tiles);
+    long long want = tiles >= g_head_grid ? 1 : g_head_grid / tiles;
+    const long long room = scratch_floats / (B * N1);
+    LBX_CHECK_ARG(room >= 1, "scratch must hold at least B * N1 floats");
+    set_tiles(g0, (int)(want < room ? want : room));
   }
-  // step 1: H1 = bf16(relu(Z1 + b1)); Z1 = 0
+  // step 1: H1 = bf16(relu(sum of the slabs + b1))
   HeadStep& s1 = P.step[1];
-  s1.kind = HSTEP_FINALIZE; s1.z = scratch; s1.bias = b1; s1.out = (bf16*)h1_bf16; s1.M = (int)B; s1.N = N1; s1.relu = 1;
+  s1.kind = HSTEP_FINALIZE; s1.z = scratch; s1.n_slabs = g0.k_splits; s1.bias = b1; s1.out = (bf16*)h1_bf16;
+  s1.M = (int)B; s1.N = N1; s1.relu = 1;
   s1.ldo = N1;
   // step 2: H2 = bf16(relu(H1 . W2 + b2))
   HeadStep& s2 = P.step[2];

@@ -33,17 +33,35 @@ def _ceil8(n):
     return (n + 7) // 8 * 8
 
 
+BN_MOMENTUM, BN_EPSILON = 0.99, 1e-3       # Keras BatchNormalization defaults (xvector_2d.py:36)
+
+
 class _LayerSpec:
-    def __init__(self, kind, name, units, kernel_size=1, strides=1, activation="relu"):
+    def __init__(self, kind, name, units, kernel_size=1, strides=1, activation="relu", dilation_rate=1,
+                 batch_norm=False):
         self.kind, self.name, self.units = kind, name, units
         self.kernel_size, self.strides, self.activation = kernel_size, strides, activation
+        self.dilation_rate, self.batch_norm = dilation_rate, batch_norm
 
 
-def frame_layer(filters, kernel_size, strides, padding="causal", activation="relu", name="frame"):
-    """xvector.py:38-39 — Conv1D(filters, kernel_size, strides, padding="causal", activation="relu")."""
+def frame_layer(filters, kernel_size, strides, padding="causal", activation="relu", name="frame", dilation_rate=1,
+                batch_norm=False):
+    """xvector.py:38-39 — Conv1D(filters, kernel_size, strides, padding="causal", activation="relu").
+
+    Two extensions beyond the reference's x-vector (both default off; the reference code has neither, its prose has):
+    dilation_rate > 1 gives the dilated TDNN layer (Keras Conv1D semantics: causal left padding dilation*(k-1), tap j
+    reads time t + j*dilation; like Keras, dilation needs strides == 1), and batch_norm=True appends an inference-time
+    BatchNormalization AFTER the activation, the order of the only Conv+BN frame layer of the reference
+    (xvector_2d.py:41-43: conv -> ReLU -> BN), with the Keras defaults momentum 0.99 / epsilon 1e-3."""
     if padding != "causal":
         raise NotImplementedError("only padding='causal' is implemented (the only mode the reference uses)")
-    return _LayerSpec("frame", name, filters, kernel_size, strides, activation)
+    if int(dilation_rate) < 1:
+        raise ValueError("dilation_rate must be >= 1")
+    if int(dilation_rate) > 1 and int(strides) != 1:
+        raise ValueError("`strides > 1` not supported in conjunction with `dilation_rate > 1`")     # Keras' own check
+    if int(dilation_rate) > 1 and int(kernel_size) > 5:
+        raise NotImplementedError("dilated layers support kernel_size <= 5 (one accumulating GEMM pass per tap)")
+    return _LayerSpec("frame", name, filters, kernel_size, strides, activation, int(dilation_rate), bool(batch_norm))
 
 
 def segment_layer(units, activation="relu", name="segment"):
@@ -111,12 +129,13 @@ class _Geometry:
             prod[L] = prod[L + 1] * frames[L].strides
         P = self.T[n]
         for L in range(n):
-            need = self.T[L] + frames[L].kernel_size - 1
+            need = self.T[L] + (frames[L].kernel_size - 1) * getattr(frames[L], "dilation_rate", 1)
             P = max(P, -(-need // prod[L]))
         self.P = P
         self.Tpad = [P * prod[L] for L in range(n)]            # padded input length of layer L
         self.R = [self.Tpad[L] // frames[L].strides for L in range(n)]   # GEMM rows per utterance of layer L
-        self.pad = [f.kernel_size - 1 for f in frames]         # data row offset inside layer L's input buffer
+        # data row offset inside layer L's input buffer = causal padding dilation * (k - 1)
+        self.pad = [(f.kernel_size - 1) * getattr(f, "dilation_rate", 1) for f in frames]
         for L in range(n - 1):
             assert self.R[L] == self.Tpad[L + 1]
 
@@ -176,7 +195,17 @@ class XVector:
         c_in, c_in_real = self.Fp, self.F
         for f in self.frames:
             self.layers.append(dict(name=f.name, kind="frame", K=f.kernel_size * c_in, N=f.units, k=f.kernel_size,
-                                    s=f.strides, c_in=c_in, c_in_real=c_in_real, relu=f.activation == "relu"))
+                                    s=f.strides, c_in=c_in, c_in_real=c_in_real, relu=f.activation == "relu",
+                                    d=getattr(f, "dilation_rate", 1), bn=None))
+            if getattr(f, "batch_norm", False):
+                # Keras BatchNormalization state (gamma, beta, moving_mean, moving_variance) and the folded inference
+                # affine y = x * scale + shift applied by the GEMM epilogue after the activation
+                dev = self.device
+                self.layers[-1]["bn"] = dict(gamma=torch.ones(f.units, device=dev), beta=torch.zeros(f.units, device=dev),
+                                             moving_mean=torch.zeros(f.units, device=dev),
+                                             moving_variance=torch.ones(f.units, device=dev),
+                                             scale=torch.ones(f.units, device=dev), shift=torch.zeros(f.units, device=dev))
+                self._fold_bn(self.layers[-1])
             c_in = c_in_real = f.units
         d_in = 2 * c_in
         for sgm in self.segments:
@@ -213,6 +242,12 @@ class XVector:
                 self._w_view(ly)[:, :ly["N"]].copy_((torch.rand((ly["K"], ly["N"]), generator=gen) * 2 - 1) * limit)
         self._weights_dirty, self._lo_dirty = True, True
 
+    @staticmethod
+    def _fold_bn(ly):
+        bn = ly["bn"]
+        bn["scale"].copy_(bn["gamma"] / torch.sqrt(bn["moving_variance"] + BN_EPSILON))
+        bn["shift"].copy_(bn["beta"] - bn["moving_mean"] * bn["scale"])
+
     def _w_view(self, ly, buf=None):
         buf = self.params if buf is None else buf
         return buf[ly["w_off"]:ly["w_off"] + ly["K"] * ly["ldw"]].view(ly["K"], ly["ldw"])
@@ -234,6 +269,9 @@ class XVector:
                 w = w.view(ly["k"], ly["c_in"], ly["N"])[:, :ly["c_in_real"]]
             out[ly["name"] + "/kernel"] = w.numpy().copy()
             out[ly["name"] + "/bias"] = self._b_view(ly).cpu().numpy().copy()
+            if ly.get("bn"):
+                for key in ("gamma", "beta", "moving_mean", "moving_variance"):
+                    out[ly["name"] + "_bn/" + key] = ly["bn"][key].cpu().numpy().copy()
         return out
 
     def set_weights(self, weights):
@@ -250,6 +288,12 @@ class XVector:
                 raise ValueError("bad kernel shape for %s: %s" % (ly["name"], tuple(w.shape)))
             self._w_view(ly)[:, :ly["N"]].copy_(w)
             self._b_view(ly).copy_(torch.as_tensor(np.asarray(weights[ly["name"] + "/bias"]), dtype=torch.float32))
+            if ly.get("bn"):
+                for key in ("gamma", "beta", "moving_mean", "moving_variance"):
+                    if ly["name"] + "_bn/" + key in weights:
+                        ly["bn"][key].copy_(torch.as_tensor(np.asarray(weights[ly["name"] + "_bn/" + key]),
+                                                            dtype=torch.float32))
+                self._fold_bn(ly)
         self._weights_dirty = self._lo_dirty = True
 
     def _refresh(self, need_lo):
@@ -279,17 +323,18 @@ class XVector:
         for k in [k for k, v in self._bufs.items() if not v.get("pinned")][:max(0, len(self._bufs) - 4)]:
             del self._bufs[k]
         geo = _Geometry(T, self.frames)
+        slack = max([_SLACK_ROWS] + geo.pad)         # shifted views (dilated taps) read up to pad rows past the last utterance
         dev, bf = self.device, torch.bfloat16
         split = self.precision == "fp32"
         n = len(self.frames)
         X, X_lo = [], []
         for L in range(n):
             c = self.layers[L]["c_in"]
-            X.append(torch.zeros((B * geo.Tpad[L] + _SLACK_ROWS, c), dtype=bf, device=dev))
+            X.append(torch.zeros((B * geo.Tpad[L] + slack, c), dtype=bf, device=dev))
             X_lo.append(torch.zeros_like(X[-1]) if split else None)
         cn = self.layers[n - 1]["N"]
         cnp = _ceil8(cn)
-        Y = torch.zeros((B * geo.R[n - 1] + _SLACK_ROWS, cnp), dtype=torch.float32 if split else bf, device=dev)
+        Y = torch.zeros((B * geo.R[n - 1] + slack, cnp), dtype=torch.float32 if split else bf, device=dev)
         bufs = dict(geo=geo, X=X, X_lo=X_lo, X0_own=X[0], X0_lo_own=X_lo[0], Y=Y, cn=cn, cnp=cnp,
                     pooled=torch.zeros((B, 2 * cn), dtype=torch.float32, device=dev),
                     var_raw=torch.zeros((B, cn), dtype=torch.float32, device=dev),
@@ -299,7 +344,7 @@ class XVector:
                     logits=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev),
                     out=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev))
         if not split and self.segments:
-            bufs["head_scratch"] = torch.zeros((B, self.segments[0].units), dtype=torch.float32, device=dev)
+            bufs["head_scratch"] = torch.zeros((8, B, self.segments[0].units), dtype=torch.float32, device=dev)
         for sgm in self.segments:
             bufs["H"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev))
             bufs["H_lo"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev) if split else None)
@@ -368,10 +413,26 @@ class XVector:
             out_lo = None if (last or not split) else bufs["X_lo"][L + 1]
             ldo = bufs["cnp"] if last else ly["N"]
             out_off = 0 if last else geo.pad[L + 1] * ly["N"]
+            bn = ly.get("bn")
+            post = dict(post_scale=bn["scale"], post_shift=bn["shift"]) if bn else {}
+            if bn and training:
+                raise NotImplementedError("batch_norm frame layers are inference-only (moving statistics)")
+            if ly["d"] > 1:
+                # dilated taps do not form one contiguous row of the padded input: one accumulating pass per tap, tap j
+                # reads the rows j*d further down against rows [j*C_in, (j+1)*C_in) of the kernel
+                if split:
+                    raise NotImplementedError("dilated frame layers run in precision='bf16' (the bf16x3 mode already "
+                                              "uses its accumulating passes for the residual planes)")
+                c = ly["c_in"]
+                ops.gemm(bufs["X"][L], B * geo.R[L], c, c, self.w16, c, ly["N"], ly["ldw"], out, ldo, layout=2,
+                         b_off=ly["w_off"], b_map_rows=ly["K"], terms=[(0, 0, j * ly["d"], j * c) for j in range(ly["k"])],
+                         out_off=out_off, bias=self._b_view(ly), relu=ly["relu"], rows_per_utt=geo.R[L],
+                         valid_rows=geo.T[L + 1], **post)
+                continue
             ops.gemm(bufs["X"][L], B * geo.R[L], ly["K"], ly["s"] * ly["c_in"], self.w16, ly["K"], ly["N"], ly["ldw"],
                      out, ldo, layout=2, a_lo=bufs["X_lo"][L], b_lo=self.w16_lo if split else None, b_off=ly["w_off"],
                      out_lo=out_lo, out_off=out_off, bias=self._b_view(ly), relu=ly["relu"], rows_per_utt=geo.R[L],
-                     valid_rows=geo.T[L + 1])
+                     valid_rows=geo.T[L + 1], **post)
         _lib.check(lib.lbx_stats_pool_fwd(_lib.ptr(bufs["Y"]), ops.F32 if split else ops.BF16, B, geo.R[n - 1],
                                           geo.T[n], bufs["cn"], bufs["cnp"], STDDEV_SQRT_MIN_CLIP,
                                           _lib.ptr(bufs["pooled"]), _lib.ptr(bufs["var_raw"]),
@@ -384,7 +445,8 @@ class XVector:
                                         ops._addr(self.params, l1["b_off"]), l1["N"],
                                         ops._addr(self.w16, l2["w_off"]), l2["ldw"], ops._addr(self.params, l2["b_off"]),
                                         l2["N"], _lib.ptr(bufs["H"][0]), _lib.ptr(bufs["H"][1]),
-                                        _lib.ptr(bufs["head_scratch"]), _lib.ptr(self._head_sync), st))
+                                        _lib.ptr(bufs["head_scratch"]), bufs["head_scratch"].numel(),
+                                        _lib.ptr(self._head_sync), st))
             a, a_lo = bufs["H"][1], None
         for i, sgm in enumerate(self.segments):
             if fused:
@@ -610,7 +672,16 @@ class XVector:
             dZ = bufs["dZ"][L]
             dz_pitch = bufs["cnp"] if L == n - 1 else ly["N"]
             dz_off = 0 if L == n - 1 else geo.pad[L + 1] * ly["N"]
-            wgrad(bufs["X"][L], rows, ly["K"], ly["s"] * ly["c_in"], dZ, ly["N"], dz_pitch, ly, dz_off=dz_off, group=True)
+            if ly["d"] > 1:
+                # one weight-gradient problem per tap: dW_j += X[t + j*d]^T . dZ[t]  (rows shifted by j*d, kernel rows j*C_in..)
+                c = ly["c_in"]
+                for j in range(ly["k"]):
+                    wgrad(bufs["X"][L], rows, c, c, dZ, ly["N"], dz_pitch,
+                          dict(ldw=ly["ldw"], w_off=ly["w_off"] + j * c * ly["ldw"]), a_off=j * ly["d"] * c, dz_off=dz_off,
+                          group=True)
+            else:
+                wgrad(bufs["X"][L], rows, ly["K"], ly["s"] * ly["c_in"], dZ, ly["N"], dz_pitch, ly, dz_off=dz_off,
+                      group=True)
             if L == mid and mid > 0:
                 reduce_bucket(mid, n - 1)
             if L == 0:
@@ -623,7 +694,14 @@ class XVector:
             below = self.layers[L - 1]
             if not below["relu"]:
                 raise NotImplementedError("linear frame layers are not supported in the backward pass")
-            if k <= s:
+            if ly["d"] > 1:
+                # dilated, stride 1: padded input time tau receives tap j of output time tau - j*d: ONE GEMM whose k
+                # accumulating passes read dZ shifted by -j*d rows against kernel rows [j*C_in, (j+1)*C_in)
+                ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], c,
+                         a_off=dz_off, b_off=ly["w_off"], b_map_rows=k * c,
+                         terms=[(0, 0, -j * ly["d"], j * c) for j in range(k)], mask_src=bufs["X"][L], colsum=g,
+                         colsum_off=below["b_off"], colsum_mod=c)
+            elif k <= s:
                 # taps tile the time axis without overlap: one GEMM writes all k*C_in columns of every view row
                 ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, k * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
                          a_off=dz_off, b_off=ly["w_off"], mask_src=bufs["X"][L], colsum=g, colsum_off=below["b_off"],

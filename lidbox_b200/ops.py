@@ -54,7 +54,7 @@ def _addr(t, offset_elems=0):
 def gemm(a, a_rows, a_cols, lda, b, b_rows, b_cols, ldb, out, ldo, *, layout=0, a_lo=None, b_lo=None, out_lo=None,
          a_off=0, b_off=0, out_off=0, k_splits=1, epi_atomic=False, bias=None, relu=False, rows_per_utt=0,
          valid_rows=0, mask_src=None, mask_off=0, accumulate=False, tile_n=0, colsum=None, colsum_off=0, colsum_mod=0,
-         b1=None, b1_off=0, terms=None):
+         b1=None, b1_off=0, terms=None, b_map_rows=0, post_scale=None, post_shift=None):
     """lbx_gemm_bf16: see lbx_gemm_t.  `a`, `b` are bf16 buffers; offsets are in elements from their data_ptr."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     d = _lib.GemmDesc()
@@ -66,8 +66,11 @@ def gemm(a, a_rows, a_cols, lda, b, b_rows, b_cols, ldb, out, ldo, *, layout=0, 
     if terms is None:        # bf16x3 when residual planes are given: (a0,b0) + (a0,b1) + (a1,b0)
         terms = [(0, 0, 0), (0, 1, 0), (1, 0, 0)] if a_lo is not None else [(0, 0, 0)]
     d.n_terms = len(terms)
-    for i, (ta, tb, trow) in enumerate(terms):
-        d.term_a[i], d.term_b[i], d.term_a_row[i] = ta, tb, trow
+    for i, term in enumerate(terms):        # (A plane, B plane, A row offset[, B row offset])
+        d.term_a[i], d.term_b[i], d.term_a_row[i] = term[0], term[1], term[2]
+        d.term_b_row[i] = term[3] if len(term) > 3 else 0
+    d.b_map_rows = b_map_rows
+    d.post_scale, d.post_shift = _addr(post_scale), _addr(post_shift)
     d.k_splits = k_splits
     d.epi_atomic = int(epi_atomic)
     d.out_dtype = BF16 if out.dtype == torch.bfloat16 else F32

@@ -13,12 +13,12 @@ w1 = (torch.randn(K1, N1, device=dev) * 0.02).bfloat16(); w2 = (torch.randn(N1, 
 b1 = torch.zeros(N1, device=dev); b2 = torch.zeros(N2, device=dev)
 h1 = torch.zeros(B, N1, device=dev, dtype=torch.bfloat16); h2 = torch.zeros(B, N2, device=dev, dtype=torch.bfloat16)
 dh2 = (torch.randn(B, N2, device=dev) * 0.01).bfloat16(); dh1 = torch.zeros_like(h1)
-scratch = torch.zeros(B, N1, device=dev); gpool = torch.zeros(B, K1, device=dev)
+scratch = torch.zeros(8, B, N1, device=dev); gpool = torch.zeros(B, K1, device=dev)
 dw1 = torch.zeros(K1, N1, device=dev); dw2 = torch.zeros(N1, N2, device=dev); db1 = torch.zeros(N1, device=dev)
 sync = torch.zeros(512, dtype=torch.int32, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def fwd():
-    _lib.check(L.lbx_head_fwd(p(pooled), B, K1, p(w1), N1, p(b1), N1, p(w2), N2, p(b2), N2, p(h1), p(h2), p(scratch), p(sync), st))
+    _lib.check(L.lbx_head_fwd(p(pooled), B, K1, p(w1), N1, p(b1), N1, p(w2), N2, p(b2), N2, p(h1), p(h2), p(scratch), scratch.numel(), p(sync), st))
 def bwd():
     _lib.check(L.lbx_head_bwd(p(dh2), p(pooled), p(h1), B, K1, N1, N2, p(w1), N1, p(w2), N2, p(dh1), p(gpool), p(dw1), p(db1), p(dw2), p(sync), st))
 res = {}

@@ -267,6 +267,9 @@ class XVectorTrainWorkload:
                                "(lbx_logmel_ex), no fp32 feature tensor / packing pass",
             "feature_prefetch": "log-mel of batch i+1 runs on a second stream during step i (one log-mel + one "
                                 "training step per replay)" if self.pipelined else "inline",
+            "tensor_launches": "5 forward + 5 data-gradient tcgen05 GEMMs, all frame-layer weight gradients in ONE "
+                               "grouped stream-K launch (lbx_wgrad_grouped); dense head = lbx_head_fwd + fused "
+                               "output/loss kernel + lbx_head_bwd (mma.sync, persistent)",
             "dp_exchange": getattr(self, "dp_exchange", None)})
         return cfg
 

@@ -783,7 +783,10 @@ class XVector:
         torch.cuda.synchronize(dev)
         dist.barrier(group=process_group)                   # every rank has zeroed its pads before anyone signals
         a = self._adam
-        use_nvls = os.environ.get("LBX_DP_NVLS", "1") != "0" and mc_ptrs[1] != 0 and mc_ptrs[2] != 0
+        # in-switch reduction (multimem.ld_reduce / multimem.st) pays from 4 ranks on; at 2 ranks plain peer loads are
+        # faster (measured on 2 x B200: optimizer kernel 46 us vs 64 us), so it is the default only for world > 2
+        nvls_default = "1" if world > 2 else "0"
+        use_nvls = os.environ.get("LBX_DP_NVLS", nvls_default) != "0" and mc_ptrs[1] != 0 and mc_ptrs[2] != 0
         self._sharded = dict(world=world, rank=rank, n=n_pad, p_ptrs=p_ptrs, g_ptrs=g_ptrs, w_ptrs=w_ptrs,
                              mc_grads=mc_ptrs[1] if use_nvls else 0, mc_w16=mc_ptrs[2] if use_nvls else 0,
                              s_ptrs=s_ptrs, sig=sig, handles=handles,

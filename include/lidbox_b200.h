@@ -354,7 +354,7 @@ int lbx_adam_step(float* params, float* grads, float* m, float* v, long long n, 
  * peers' pushes and does NOT touch the gradient buffer: the next step starts with lbx_dp_wait() (all peers have
  * published <=> this rank's bf16 weights are complete and nobody reads its gradient any more), after which the caller
  * clears its gradient buffer (off the critical path, e.g. on a side stream during the forward pass).
- * signal pads: 2*world uint32 per rank, zero-initialised; epoch_dev (1 uint32) / local_sync_dev (16 uint32; [4..9] receive three 64-bit globaltimer stamps of the last call:
+ * signal pads: 3*world uint32 per rank, zero-initialised; epoch_dev (1 uint32) / local_sync_dev (16 uint32; [4..9] receive three 64-bit globaltimer stamps of the last call:
  * start, barrier passed, last block done): zero-initialised local
  * state advanced by every call, so the calls can be replayed from a CUDA graph.  local_sync_dev[3] != 0 reports a
  * barrier time-out (lbx_set_dp_spin_limit polls of 64 ns, default 2^23 ~ 1 s): the update of that step is SKIPPED on
@@ -368,7 +368,18 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
                           void* const* signal_ptrs, float* m_shard, float* v_shard, long long n, int rank, int world,
                           unsigned int* epoch_dev, unsigned int* local_sync_dev, float lr, float beta1, float beta2,
                           float eps, long long* step_dev, float* lr_t_dev, float grad_scale, int push_fp32,
-                          const void* mc_grads, void* mc_w16, void* stream);
+                          const void* mc_grads, void* mc_w16, const float* staging, long long early_begin, void* stream);
+/* Early part of the exchange, off the critical path: gradients at flat index >= early_begin (the later layers) are
+ * complete long before the backward pass ends.  A rank announces that with lbx_dp_signal (slot_base = 2*world, epoch_add =
+ * 1), a side stream waits for every peer's announcement with lbx_dp_wait_slot and then lets the COPY ENGINE pull the
+ * peers' copies of this rank's shard (indices >= early_begin) into `staging` ((world-1) slabs of n/world floats, slab s
+ * = peer (rank+1+s) % world) while the tensor cores finish the backward pass; lbx_adam_step_sharded then sums those
+ * slabs locally and reads only the late part of the shard over NVLink.  staging = NULL: everything is read from the
+ * peers inside the kernel. */
+int lbx_dp_signal(void* const* signal_ptrs, int world, int rank, int slot_base, const unsigned int* epoch_dev,
+                  unsigned int epoch_add, void* stream);
+int lbx_dp_wait_slot(const void* signal_pad_local, int world, int slot_base, const unsigned int* epoch_dev,
+                     unsigned int epoch_add, unsigned int* local_sync_dev, void* stream);
 /* see lbx_adam_step_sharded: spins until every peer has published the epoch in *epoch_dev into this rank's pad */
 int lbx_dp_wait(const void* signal_pad_local, int world, const unsigned int* epoch_dev, unsigned int* local_sync_dev,
                 void* stream);

@@ -101,7 +101,9 @@ SIGNATURES = {
     "lbx_head_bwd": (c_int, [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P, c_int, _P]),
     "lbx_adam_step_sharded": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P, _P, c_float, c_float, c_float,
-                                      c_float, _P, _P, c_float, c_int, _P, _P, _P]),
+                                      c_float, _P, _P, c_float, c_int, _P, _P, _P, c_ll, _P]),
+    "lbx_dp_signal": (c_int, [_P, c_int, c_int, c_int, _P, ctypes.c_uint, _P]),
+    "lbx_dp_wait_slot": (c_int, [_P, c_int, c_int, _P, ctypes.c_uint, _P, _P]),
     "lbx_dp_wait": (c_int, [_P, c_int, _P, _P, _P]),
     "lbx_set_dp_spin_limit": (c_int, [c_ll]),
     "lbx_set_dp_blocks_per_sm": (c_int, [c_int]),

@@ -834,6 +834,8 @@ struct ShardedAdamParams {
   int push_fp32;                 // 1: also all-gather the fp32 master copy (otherwise only the owner's shard is current)
   const float* mc_grads;         // optional NVLS multicast mapping of the gradient buffers (in-switch reduction)
   bf16* mc_w16;                  // optional NVLS multicast mapping of the bf16 operand copy (one store reaches all ranks)
+  const float* staging;          // optional: (world-1) slabs of n/world floats = the peers' copies of this rank's shard for
+  long long early_begin;         //   flat indices >= early_begin, pulled by the copy engine during the backward pass
   long long spin_limit;          // polls (64 ns apart) before a barrier gives up and the step is skipped
   int debug;                     // measurement only: 1 = no remote loads, 2 = no remote stores, 4 = no fence per thread
 };
@@ -952,12 +954,28 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const ShardedAdamPara
   const long long stride = (long long)nblk * blockDim.x;
   const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float4 tn[UNROLL][W];
+  // elements of the shard at flat index >= early_begin: their gradients were complete long before the end of the
+  // backward pass and the copy engine has already pulled the peers' copies into the local staging slabs, so they need
+  // no NVLink round trip here — only the late part of the shard (the first frame layers) is read from the peers
+  const long long shard4_full = p.n / 4 / p.world;
+  const long long early4 = p.staging != nullptr ? p.early_begin / 4 : (1LL << 60);
+  const float4* stg4 = reinterpret_cast<const float4*>(p.staging);
+  const float4* my_grads4 = reinterpret_cast<const float4*>(p.grads[p.rank]);
   auto fetch = [&](long long i0) {
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long i = i0 + u * stride;
       if (i < shard4) {
-        if (NVLS) {
+        if (base4 + i >= early4) {
+          float4 acc = __ldcv(my_grads4 + base4 + i);
+          for (int sl = 0; sl < p.world - 1; ++sl) {
+            const float4 v = __ldcs(stg4 + sl * shard4_full + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          tn[u][0] = acc;
+#pragma unroll
+          for (int q = 1; q < W; ++q) tn[u][q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        } else if (NVLS) {
           tn[u][0] = multimem_ld_reduce_f32x4(p.mc_grads + 4 * (base4 + i));
         } else {
 #pragma unroll
@@ -1039,6 +1057,24 @@ __global__ void dp_wait_kernel(const unsigned int* __restrict__ pad, int world, 
   LBX_PDL_SYNC();
   const unsigned int e = *epoch;
   if ((int)threadIdx.x < world && !spin_until_ge(pad + world + threadIdx.x, e, true, spin_limit)) local_sync[3] = 1;
+}
+
+// "rank r has reached point X of epoch *epoch + add": one flag per peer pad, slot_base + rank
+__global__ void dp_signal_kernel(unsigned int* const* __restrict__ signals, int world, int rank, int slot_base,
+                                 const unsigned int* __restrict__ epoch, unsigned int add) {
+  LBX_PDL_SYNC();
+  const unsigned int e = *epoch + add;
+  if ((int)threadIdx.x < world) {
+    __threadfence_system();                      // the gradients written by the kernels before this one are visible
+    st_release_sys(signals[threadIdx.x] + slot_base + rank, e);
+  }
+}
+__global__ void dp_wait_slot_kernel(const unsigned int* __restrict__ pad, int world, int slot_base,
+                                    const unsigned int* __restrict__ epoch, unsigned int add,
+                                    unsigned int* __restrict__ local_sync, long long spin_limit) {
+  LBX_PDL_SYNC();
+  const unsigned int e = *epoch + add;
+  if ((int)threadIdx.x < world && !spin_until_ge(pad + slot_base + threadIdx.x, e, true, spin_limit)) local_sync[3] = 1;
 }
 
 static long long g_dp_spin_limit = 1LL << 23;      // ~1 s of 64 ns polls
@@ -1224,7 +1260,7 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
                           void* const* signal_ptrs, float* m_shard, float* v_shard, long long n, int rank, int world,
                           unsigned int* epoch_dev, unsigned int* local_sync_dev, float lr, float beta1, float beta2,
                           float eps, long long* step_dev, float* lr_t_dev, float grad_scale, int push_fp32,
-                          const void* mc_grads, void* mc_w16, void* stream) {
+                          const void* mc_grads, void* mc_w16, const float* staging, long long early_begin, void* stream) {
   LBX_CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
   LBX_CHECK_ARG(n > 0 && n % (4LL * world) == 0, "the flat length must be a multiple of 4*world (pad the buffers)");
   LBX_CHECK_ARG(params_ptrs && grads_ptrs && w16_ptrs && signal_ptrs && m_shard && v_shard && epoch_dev &&
@@ -1238,6 +1274,10 @@ int lbx_adam_step_sharded(void* const* params_ptrs, void* const* grads_ptrs, voi
   p.lr = lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale;
   p.push_fp32 = push_fp32;
   p.mc_grads = (const float*)mc_grads; p.mc_w16 = (bf16*)mc_w16;
+  LBX_CHECK_ARG(staging == nullptr || (early_begin >= 0 && early_begin % 4 == 0 &&
+                                       (reinterpret_cast<uintptr_t>(staging) & 15) == 0),
+                "staging needs a 16-byte aligned buffer and early_begin % 4 == 0");
+  p.staging = staging; p.early_begin = early_begin;
   p.spin_limit = g_dp_spin_limit;
   p.debug = getenv("LBX_DP_DEBUG") ? atoi(getenv("LBX_DP_DEBUG")) : 0;
   LBX_CHECK_ARG(world <= 8, "at most 8 ranks (one NVLink domain)");
@@ -1273,6 +1313,24 @@ int lbx_dp_wait(const void* signal_pad_local, int world, const unsigned int* epo
   LBX_CHECK_ARG(world >= 1 && world <= 8, "at most 8 ranks (one NVLink domain)");
   LBX_LAUNCH_PDL(dp_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (const unsigned int*)signal_pad_local, world,
                  epoch_dev, local_sync_dev, g_dp_spin_limit);
+  return LBX_OK;
+}
+
+int lbx_dp_signal(void* const* signal_ptrs, int world, int rank, int slot_base, const unsigned int* epoch_dev,
+                  unsigned int epoch_add, void* stream) {
+  LBX_CHECK_ARG(signal_ptrs && epoch_dev, "NULL pointer argument");
+  LBX_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world && slot_base >= 0, "bad rank / world / slot");
+  LBX_LAUNCH_PDL(dp_signal_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (unsigned int* const*)signal_ptrs, world,
+                 rank, slot_base, epoch_dev, epoch_add);
+  return LBX_OK;
+}
+
+int lbx_dp_wait_slot(const void* signal_pad_local, int world, int slot_base, const unsigned int* epoch_dev,
+                     unsigned int epoch_add, unsigned int* local_sync_dev, void* stream) {
+  LBX_CHECK_ARG(signal_pad_local && epoch_dev && local_sync_dev, "NULL pointer argument");
+  LBX_CHECK_ARG(world >= 1 && world <= 8 && slot_base >= 0, "bad world / slot");
+  LBX_LAUNCH_PDL(dp_wait_slot_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (const unsigned int*)signal_pad_local,
+                 world, slot_base, epoch_dev, epoch_add, local_sync_dev, g_dp_spin_limit);
   return LBX_OK;
 }
 

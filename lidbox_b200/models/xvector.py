@@ -588,6 +588,14 @@ class XVector:
         dp_mode = os.environ.get("LBX_DP_MODE", "single")      # single | buckets | none (measurement only)
         grouped = [] if (os.environ.get("LBX_WGRAD_GROUPED", "1") != "0" and dp_mode != "buckets") else None
 
+        def flush_grouped():
+            if grouped:
+                # largest problems first: the ranges of the line that end up shortest in wall time come last
+                grouped.sort(key=lambda q: -q["rows"] * q["a_cols"] * q["b_cols"])
+                for i in range(0, len(grouped), 8):
+                    ops.wgrad_grouped(grouped[i:i + 8], self.device)
+                del grouped[:]
+
         def wgrad(a, a_rows, a_cols, lda, dz, dz_cols, dz_pitch, ly, a_off=0, dz_off=0, group=False):
             if group and grouped is not None:
                 grouped.append(dict(a=a, rows=a_rows, a_cols=a_cols, lda=lda, a_off=a_off, b=dz, b_cols=dz_cols,
@@ -724,11 +732,16 @@ class XVector:
                              b1_off=ly["w_off"] + taps[-1] * c * ly["ldw"], terms=terms, out_off=rho * c,
                              mask_src=bufs["X"][L], mask_off=rho * c, colsum=g, colsum_off=below["b_off"],
                              colsum_mod=c)
-        if grouped:
-            # largest problems first: the ranges of the line that end up shortest in wall time come last
-            grouped.sort(key=lambda q: -q["rows"] * q["a_cols"] * q["b_cols"])
-            for i in range(0, len(grouped), 8):
-                ops.wgrad_grouped(grouped[i:i + 8], self.device)
+            if self._sharded is not None and self._sharded["early_on"] and L == self._sharded["early_layer"]:
+                # every gradient at flat index >= early_begin is now final on this rank (weights of layers >= L: issue
+                # them now; their biases came out of the data-gradient epilogues / pooling / head kernels above)
+                flush_grouped()
+                if side is not None and side_used[0]:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    cur.wait_event(ev)
+                self._dp_early_exchange(cur)
+        flush_grouped()
         if side is not None and side_used[0]:
             ev = torch.cuda.Event()
             ev.record(side)
@@ -794,20 +807,70 @@ class XVector:
                              v=torch.zeros(n_pad // world, dtype=torch.float32, device=dev),
                              epoch=torch.zeros(1, dtype=torch.int32, device=dev),
                              local=torch.zeros(16, dtype=torch.int32, device=dev))
+        # early exchange (opt-in, LBX_DP_EARLY=1): the gradients of the later layers (second half of the frame layers,
+        # pooling-side bias, dense head: ~80 % of the parameters) are complete when the data-gradient chain has passed
+        # the middle frame layer.  From then on the copy engine pulls the peers' copies of this rank's shard into local
+        # staging slabs while the tensor cores finish the backward pass (lbx_dp_signal / lbx_dp_wait_slot + D2D copies
+        # on a side stream); the optimizer kernel reads only the late part of its shard over NVLink.
+        # Measured on 2 x B200 it is correct but SLOWER (0.461 vs 0.447 ms/step): the optimizer kernel gains 6 us, and
+        # cutting the grouped weight-gradient launch in two plus the extra signal kernel / stream joins cost 11 us.
+        nfr = len(self.frames)
+        sh = self._sharded
+        sh["early_layer"] = nfr // 2
+        sh["early_begin"] = self.layers[nfr // 2]["w_off"] if nfr // 2 > 0 else n_pad
+        sh["early_on"] = os.environ.get("LBX_DP_EARLY", "0") == "1" and world > 1 and sh["early_begin"] < n_pad
+        if sh["early_on"]:
+            shard = n_pad // world
+            sh["staging"] = torch.zeros((world - 1, shard), dtype=torch.float32, device=dev)
+            sh["peer_grads"] = {q: handles[1].get_buffer(q, (n_pad,), torch.float32) for q in range(world) if q != rank}
+            sh["dp_stream"] = torch.cuda.Stream(device=dev)
+        sh["early_ev"] = None
         a["m"] = a["v"] = None                              # full-size moments are not needed any more
         self._weights_dirty = self._lo_dirty = True
         self._grads_clean = True
         self.w16_lo = None
 
+    def _dp_early_exchange(self, cur):
+        """Announce "my gradients at flat index >= early_begin are complete" and start pulling the peers' copies of this
+        rank's shard with the copy engine on a side stream (see enable_sharded_optimizer)."""
+        sh = self._sharded
+        lib = _lib.lib()
+        world, rank = sh["world"], sh["rank"]
+        _lib.check(lib.lbx_dp_signal(_lib.ptr(sh["s_ptrs"]), world, rank, 2 * world, _lib.ptr(sh["epoch"]), 1,
+                                     _lib.stream_ptr(self.device)))
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        s2 = sh["dp_stream"]
+        s2.wait_event(ev)
+        shard = sh["n"] // world
+        lo, hi = max(sh["early_begin"], rank * shard), (rank + 1) * shard
+        dbg = int(os.environ.get("LBX_DP_EARLY_DEBUG", "0"))      # measurement only: 1 = no copies, 2 = no wait kernel either
+        with torch.cuda.stream(s2):
+            if dbg < 2:
+                _lib.check(lib.lbx_dp_wait_slot(_lib.ptr(sh["sig"]), world, 2 * world, _lib.ptr(sh["epoch"]), 1,
+                                                _lib.ptr(sh["local"]), _lib.stream_ptr(self.device)))
+            if hi > lo and dbg == 0:
+                for sl in range(world - 1):
+                    q = (rank + 1 + sl) % world
+                    sh["staging"][sl, lo - rank * shard:hi - rank * shard].copy_(sh["peer_grads"][q][lo:hi],
+                                                                                non_blocking=True)
+            sh["early_ev"] = torch.cuda.Event()
+            sh["early_ev"].record(s2)
+
     def _apply_sharded(self):
         a, sh = self._adam, self._sharded
+        staging = None
+        if sh.get("early_ev") is not None:          # this step's early part sits in the staging slabs
+            torch.cuda.current_stream(self.device).wait_event(sh["early_ev"])
+            sh["early_ev"] = None
+            staging = _lib.ptr(sh["staging"])
         _lib.check(_lib.lib().lbx_adam_step_sharded(_lib.ptr(sh["p_ptrs"]), _lib.ptr(sh["g_ptrs"]),
                                                     _lib.ptr(sh["w_ptrs"]), _lib.ptr(sh["s_ptrs"]), _lib.ptr(sh["m"]),
                                                     _lib.ptr(sh["v"]), sh["n"], sh["rank"], sh["world"],
                                                     _lib.ptr(sh["epoch"]), _lib.ptr(sh["local"]), a["lr"], a["beta1"],
                                                     a["beta2"], a["eps"], _lib.ptr(a["step"]), _lib.ptr(a["lr_t"]),
                                                     1.0, 0, ctypes.c_void_p(sh["mc_grads"] or None),
-                                                    ctypes.c_void_p(sh["mc_w16"] or None),
+                                                    ctypes.c_void_p(sh["mc_w16"] or None), staging, sh["early_begin"],
                                                     _lib.stream_ptr(self.device)))
         self._grads_clean = False          # cleared at the start of the next step, after lbx_dp_wait
         self._weights_dirty = False

@@ -170,4 +170,15 @@ def stream_ptr(device=None):
 def require_cuda(device=None):
     if not torch.cuda.is_available():
         raise LidboxB200Error("lidbox_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    cur = torch.device("cuda", torch.cuda.current_device())
+    if device is None:
+        return cur
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise LidboxB200Error("lidbox_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if dev.index is not None and dev.index != cur.index:
+        # the library launches on the CURRENT device and keeps its per-kernel attributes / SM counts per process (one
+        # process per GPU): a model on another ordinal would launch on the wrong GPU
+        raise LidboxB200Error("device %s is not the current CUDA device (%s): call torch.cuda.set_device() first "
+                              "(one process per GPU)" % (dev, cur))
+    return cur

@@ -669,6 +669,9 @@ class XVector:
         reduce_bucket(n, len(self.layers) - 1)
         # ---- statistics pooling (+ ReLU mask and bias gradient of the last frame layer) ----
         last = self.layers[n - 1]
+        if not last["relu"]:
+            raise NotImplementedError("the pooling backward pass applies the ReLU mask of the last frame layer: a linear "
+                                      "last frame layer is not supported in training")
         _lib.check(lib.lbx_stats_pool_bwd(_lib.ptr(bufs["Y"]), B, geo.R[n - 1], geo.T[n], bufs["cn"], bufs["cnp"],
                                           STDDEV_SQRT_MIN_CLIP, _lib.ptr(bufs["pooled"]), _lib.ptr(bufs["var_raw"]),
                                           _lib.ptr(bufs["gpool"]), _lib.ptr(bufs["dZ"][n - 1]),

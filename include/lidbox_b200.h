@@ -213,8 +213,9 @@ int lbx_vad_compact_f32(const float* sig, long long B, long long N, int frame_le
  *   down against rows [j*C_in, (j+1)*C_in) of the Keras kernel (and the mirror image in its data gradient);
  *   "bf16x3": a1/b1 = bf16 residual planes (x - bf16(x)), passes (a0,b0) (a0,b1) (a1,b0): fp32-grade forward results;
  *   gather-form data gradient of a strided conv (k > stride): output time tau = t*stride + j receives tap j of row t,
- *   so every residue class of tau is ONE GEMM whose passes read dZ shifted by -i rows against the weights of tap
- *   rho + i*stride (no read-modify-write pass).
+ *   so pass i reads dZ shifted by -i rows against the kernel rows of taps [i*stride, (i+1)*stride) — ONE GEMM with
+ *   N = stride*C_in and ceil(k/stride) passes; kernel rows past k*C_in (b_map_rows) read as zeros (no read-modify-write
+ *   pass, no second launch).
  * Epilogue, per output element (m, n), in this order: + bias[n]; ReLU; zero unless mask_src[m*ldo+n] > 0;
  * then either atomicAdd into fp32 out (epi_atomic, required for k_splits > 1), or out (+)= x as fp32 / bf16
  * (plus out_lo = bf16 residual).  Rows with (m % rows_per_utt) >= valid_rows are stored as ZERO when rows_per_utt > 0 (they land on

@@ -718,23 +718,28 @@ class XVector:
                          a_off=dz_off, b_off=ly["w_off"], mask_src=bufs["X"][L], colsum=g, colsum_off=below["b_off"],
                          colsum_mod=c)
             else:
-                # gather form: padded output time tau = t*s + j.  For every residue rho = tau mod s one GEMM whose
-                # accumulating passes read dZ shifted by -i rows against the weights of tap rho + i*s
-                if -(-k // s) > 3:
-                    raise NotImplementedError("kernel_size > 3 * strides in the backward pass")
-                for rho in range(s):
-                    taps = list(range(rho, k, s))
-                    if not taps:
-                        continue
-                    terms = [(0, min(i, 1), -i) for i in range(len(taps))]
-                    if len(taps) == 3:
-                        raise NotImplementedError("three overlapping taps per residue class")
-                    b1 = self.w16 if len(taps) > 1 else None
-                    ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
-                             a_off=dz_off, b_off=ly["w_off"] + taps[0] * c * ly["ldw"], b1=b1,
-                             b1_off=ly["w_off"] + taps[-1] * c * ly["ldw"], terms=terms, out_off=rho * c,
-                             mask_src=bufs["X"][L], mask_off=rho * c, colsum=g, colsum_off=below["b_off"],
-                             colsum_mod=c)
+                # gather form: padded output time tau = t*s + j receives tap j of output row t.  View row m of the
+                # destination holds the s*C_in values of times m*s .. m*s + s - 1; accumulating pass i reads dZ shifted
+                # by -i rows against the kernel rows of taps i*s .. i*s + s - 1 (rows past k*C_in read as zeros), so the
+                # whole data gradient is ONE GEMM with N = s*C_in (round 1: one launch per residue class of tau)
+                passes = -(-k // s)
+                if passes > 5:
+                    raise NotImplementedError("kernel_size > 5 * strides in the backward pass")
+                if os.environ.get("LBX_DGRAD_MERGED", "1") != "0":
+                    ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, s * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
+                             a_off=dz_off, b_off=ly["w_off"], b_map_rows=k * c,
+                             terms=[(0, 0, -i, i * s * c) for i in range(passes)], mask_src=bufs["X"][L], colsum=g,
+                             colsum_off=below["b_off"], colsum_mod=c)
+                else:
+                    for rho in range(s):
+                        taps = list(range(rho, k, s))
+                        if not taps:
+                            continue
+                        ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
+                                 a_off=dz_off, b_off=ly["w_off"], b_map_rows=k * c,
+                                 terms=[(0, 0, -i, t * c) for i, t in enumerate(taps)], out_off=rho * c,
+                                 mask_src=bufs["X"][L], mask_off=rho * c, colsum=g, colsum_off=below["b_off"],
+                                 colsum_mod=c)
             if self._sharded is not None and self._sharded["early_on"] and L == self._sharded["early_layer"]:
                 # every gradient at flat index >= early_begin is now final on this rank (weights of layers >= L: issue
                 # them now; their biases came out of the data-gradient epilogues / pooling / head kernels above)

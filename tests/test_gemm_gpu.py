@@ -219,3 +219,21 @@ def test_wgrad_grouped_matches_per_layer_launches(ops):
     for q, o in zip(probs, singles):
         den = float(o.abs().max())
         assert float((q["out"] - o).abs().max()) < 2e-5 * den + 1e-6
+
+
+def test_nt_passes_with_b_row_offsets_and_zero_fill_past_the_view(ops):
+    """Accumulating passes with per-pass A / B row offsets: out[m, :] = sum_i A[m - i, :] . B[i*N : (i+1)*N, :]^T where
+    rows of B past b_map_rows read as zeros — the one-GEMM gather form of a strided Conv1D's data gradient
+    (k = 3 taps, stride 2: N = 2*C, pass 1 hangs over the end of the kernel)."""
+    M, C, K = 700, 64, 128                       # C = C_in, K = C_out
+    dz = _rand((M, K), 21).bfloat16()
+    w = _rand((3 * C, K), 22, 0.05).bfloat16()   # Keras kernel rows [tap*C_in + c, C_out]
+    junk = _rand((C, K), 23).bfloat16()          # memory behind the view: must NOT be read as data
+    wbuf = torch.cat([w, junk]).contiguous()
+    out = torch.full((M, 2 * C), float("nan"), device="cuda")
+    ops.gemm(dz, M, K, K, wbuf, 2 * C, K, K, out, 2 * C, b_map_rows=3 * C, terms=[(0, 0, 0, 0), (0, 0, -1, 2 * C)])
+    dzd, wd = dz.double(), w.double()
+    prev = torch.cat([torch.zeros((1, K), device="cuda", dtype=torch.float64), dzd[:-1]])      # row m - 1 (zero before row 0)
+    ref = torch.cat([dzd @ wd[:C].T + prev @ wd[2 * C:].T, dzd @ wd[C:2 * C].T], dim=1)
+    absref = torch.cat([dzd.abs() @ wd[:C].abs().T + prev.abs() @ wd[2 * C:].abs().T, dzd.abs() @ wd[C:2 * C].abs().T], dim=1)
+    _check(out, ref, absref)

@@ -174,6 +174,7 @@ class XVector:
         self.overlap_wgrad = True
         self._side_stream = torch.cuda.Stream(device=self.device)
         self._head_sync = torch.zeros(512, dtype=torch.int32, device=self.device)   # grid-barrier state of the fused head
+        self._num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
     def _head_fused(self):
         """The two segment layers run as one persistent launch each way (lbx_head_fwd / lbx_head_bwd) in bf16 precision;
@@ -429,10 +430,15 @@ class XVector:
                          out_off=out_off, bias=self._b_view(ly), relu=ly["relu"], rows_per_utt=geo.R[L],
                          valid_rows=geo.T[L + 1], **post)
                 continue
+            # small batches: when the 256 x 256 CTA-pair tiles would occupy less than half of the SMs (e.g. frame3 / frame4
+            # at 64 x 2 s: 18 pair tiles on 74 pairs), 128 x 128 single-CTA tiles put four times as many CTAs to work
+            m_tiles = -(-(B * geo.R[L]) // 128)
+            pair_units = -(-m_tiles // 2) * -(-ly["N"] // 256)
+            tile_n = 128 if 4 * pair_units <= self._num_sms else 0
             ops.gemm(bufs["X"][L], B * geo.R[L], ly["K"], ly["s"] * ly["c_in"], self.w16, ly["K"], ly["N"], ly["ldw"],
                      out, ldo, layout=2, a_lo=bufs["X_lo"][L], b_lo=self.w16_lo if split else None, b_off=ly["w_off"],
                      out_lo=out_lo, out_off=out_off, bias=self._b_view(ly), relu=ly["relu"], rows_per_utt=geo.R[L],
-                     valid_rows=geo.T[L + 1], **post)
+                     valid_rows=geo.T[L + 1], tile_n=tile_n, **post)
         _lib.check(lib.lbx_stats_pool_fwd(_lib.ptr(bufs["Y"]), ops.F32 if split else ops.BF16, B, geo.R[n - 1],
                                           geo.T[n], bufs["cn"], bufs["cnp"], STDDEV_SQRT_MIN_CLIP,
                                           _lib.ptr(bufs["pooled"]), _lib.ptr(bufs["var_raw"]),

@@ -237,3 +237,18 @@ def test_nt_passes_with_b_row_offsets_and_zero_fill_past_the_view(ops):
     ref = torch.cat([dzd @ wd[:C].T + prev @ wd[2 * C:].T, dzd @ wd[C:2 * C].T], dim=1)
     absref = torch.cat([dzd.abs() @ wd[:C].abs().T + prev.abs() @ wd[2 * C:].abs().T, dzd.abs() @ wd[C:2 * C].abs().T], dim=1)
     _check(out, ref, absref)
+
+
+@pytest.mark.parametrize("tile_n", [64, 128, 256])
+def test_nn_forward_layout_all_tile_widths(ops, tile_n):
+    """Forward layout (A K-major, B = Keras kernel [K, N] read as an MN-major operand) with bias + ReLU + bf16 output
+    for every tile width the host may pick (256: CTA pairs; 128: small batches; 64: dense layers)."""
+    M, N, K = 2176, 512, 1536
+    a = _rand((M, K), 31).bfloat16()
+    b = _rand((K, N), 32, 0.03).bfloat16()
+    bias = _rand((N,), 33, 0.1)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, M, K, K, b, K, N, N, out, N, layout=2, bias=bias, relu=True, tile_n=tile_n)
+    ref = torch.relu(a.double() @ b.double() + bias.double())
+    absref = a.double().abs() @ b.double().abs() + bias.double().abs()
+    assert bool(((out.double() - ref).abs() <= 2e-5 * absref + 2.0 ** -8 * ref.abs() + 1e-30).all())

@@ -202,6 +202,9 @@ class LogmelWorkload:
                           "TensorFlow is not installable)" % (n, Bs, self.sec), "ms_per_step": dt / n * 1e3}
 
 
+E2E_LOSS_RING = 8      # end-to-end loop: per-step D2H loss copies land in a ring; the host synchronises once per ring
+
+
 def tdnn_forward_flops(T, n_out=4, F=40):
     """Algorithmic forward FLOPs of one utterance: frames 1-5 + segments (+ output layer)."""
     T2 = -(-T // 2)
@@ -343,7 +346,7 @@ class XVectorTrainWorkload:
         dev = self.device
         e = {"copy": torch.cuda.Stream(device=dev),
              "h2d_done": [torch.cuda.Event(), torch.cuda.Event()], "step_done": torch.cuda.Event(),
-             "loss_host": [torch.empty((self.B,), dtype=torch.float32).pin_memory() for _ in range(2)]}
+             "loss_host": [torch.empty((self.B,), dtype=torch.float32).pin_memory() for _ in range(E2E_LOSS_RING)]}
         cur = torch.cuda.current_stream(dev)
         torch.cuda.synchronize(dev)
         # prime: batch 0 -> xs[k0] + its features, batch 1 -> xs[1-k0]
@@ -376,9 +379,10 @@ class XVectorTrainWorkload:
             e["copy"].wait_event(prev_done)                    # buffer k was last read by the previous replay
             pipe["xs"][k].copy_(pipe["x_host"], non_blocking=True)
             e["h2d_done"][k].record(e["copy"])
-        e["loss_host"][k].copy_(losses, non_blocking=True)
-        if k == 1:
-            cur.synchronize()                                  # host reads the losses of the last two steps
+        slot = (pipe["i"] - 1) % E2E_LOSS_RING                 # pipe["i"] was advanced by self.step()
+        e["loss_host"][slot].copy_(losses, non_blocking=True)  # every step's losses are copied to the host
+        if slot == E2E_LOSS_RING - 1:
+            cur.synchronize()                                  # the host reads the losses of the last ring of steps
 
     def e2e_run(self, x_host, steps, barrier):
         """Times `steps` end-to-end steps fed from the pinned host tensor x_host (int16 PCM or float32)."""

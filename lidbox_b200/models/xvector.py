@@ -345,7 +345,10 @@ class XVector:
                     logits=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev),
                     out=torch.zeros((B, self.num_outputs), dtype=torch.float32, device=dev))
         if not split and self.segments:
-            bufs["head_scratch"] = torch.zeros((8, B, self.segments[0].units), dtype=torch.float32, device=dev)
+            # split-K slabs of the fused head's first layer: as many as lbx_head_fwd can use (one 64 x 128 tile per SM)
+            head_tiles = -(-B // 64) * -(-self.segments[0].units // 128)
+            slabs = max(1, min(16, self._num_sms // head_tiles))
+            bufs["head_scratch"] = torch.zeros((slabs, B, self.segments[0].units), dtype=torch.float32, device=dev)
         for sgm in self.segments:
             bufs["H"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev))
             bufs["H_lo"].append(torch.zeros((B, sgm.units), dtype=bf, device=dev) if split else None)

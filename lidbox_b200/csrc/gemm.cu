@@ -298,6 +298,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint32_t mphase = 0;                         // parity of this warp's mask barrier (fast epilogue)
     for (int tile = worker; tile < total_tiles; tile += n_workers) {
       const int rem = tile % mn_tiles;
+      // split-K partial tiles are summed atomically: the bias is added by the first split only
+      const bool add_bias = !p.epi_atomic || tile < mn_tiles;
       const int m_unit = rem / n_tiles, n_blk = rem - m_unit * n_tiles;
       const int m_blk = PAIR ? 2 * m_unit + cta_rank : m_unit;
       const int m = m_blk * BM + sub * 32 + lane;
@@ -488,7 +490,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[c][j]);
-        if (bias_smem) {
+        if (!add_bias) {
+          // (a later split of an atomically accumulated tile)
+        } else if (bias_smem) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             if (4 * q < ncols) {                 // N is a multiple of 4 for every biased layer that takes this path
@@ -772,6 +776,7 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   LBX_CHECK_ARG(g->out_lo == nullptr || g->out_dtype == LBX_BF16, "out_lo needs a bf16 output");
   LBX_CHECK_ARG(g->k_splits >= 1, "k_splits must be >= 1");
   LBX_CHECK_ARG(g->k_splits == 1 || g->epi_atomic, "split-K needs the atomic epilogue");
+  LBX_CHECK_ARG(!(g->epi_atomic && g->relu), "an activation cannot be applied to atomically accumulated partial sums");
   p.n_terms = g->n_terms;
   const int kb_total = (p.K + BK - 1) / BK;
   int ks = g->k_splits < kb_total ? g->k_splits : kb_total;

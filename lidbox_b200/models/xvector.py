@@ -434,10 +434,11 @@ class XVector:
                          valid_rows=geo.T[L + 1], **post)
                 continue
             # small batches: when the 256 x 256 CTA-pair tiles would occupy less than half of the SMs (e.g. frame3 / frame4
-            # at 64 x 2 s: 18 pair tiles on 74 pairs), 128 x 128 single-CTA tiles put four times as many CTAs to work
+            # at 64 x 2 s: 18 pair tiles on 74 pairs), 128 x 128 or 128 x 64 single-CTA tiles put 4 or 8 times as many CTAs
+            # to work
             m_tiles = -(-(B * geo.R[L]) // 128)
             pair_units = -(-m_tiles // 2) * -(-ly["N"] // 256)
-            tile_n = 128 if 4 * pair_units <= self._num_sms else 0
+            tile_n = 64 if 8 * pair_units <= self._num_sms else (128 if 4 * pair_units <= self._num_sms else 0)
             ops.gemm(bufs["X"][L], B * geo.R[L], ly["K"], ly["s"] * ly["c_in"], self.w16, ly["K"], ly["N"], ly["ldw"],
                      out, ldo, layout=2, a_lo=bufs["X_lo"][L], b_lo=self.w16_lo if split else None, b_off=ly["w_off"],
                      out_lo=out_lo, out_off=out_off, bias=self._b_view(ly), relu=ly["relu"], rows_per_utt=geo.R[L],
@@ -481,9 +482,21 @@ class XVector:
                      b_lo=self.w16_lo if split else None, b_off=ly["w_off"], out_lo=out_lo, bias=self._b_view(ly),
                      relu=relu, tile_n=64)
         if out_f32 is not None:
-            ops.gemm(a, B, ly["K"], ly["K"], self.w16, ly["K"], ly["N"], ly["ldw"], out_f32, ly["N"], layout=2, a_lo=a_lo,
-                     b_lo=self.w16_lo if split else None, b_off=ly["w_off"], bias=self._b_view(ly), relu=relu,
-                     tile_n=64)
+            # a long contraction over few rows (the embedding layer: K = 3000, x3 passes in the fp32 mode, on 8 tiles
+            # took 42 us of the 195 us of BASELINE config 2): split-K over the idle SMs, fp32 partial sums added
+            # atomically into the zeroed output, the bias carried by the first split
+            tiles = -(-B // 128) * -(-ly["N"] // 64)
+            kb = -(-ly["K"] // 64)
+            ks = min(kb // 4, self._num_sms // tiles) if not relu else 1
+            if ks >= 2:
+                out_f32.zero_()
+                ops.gemm(a, B, ly["K"], ly["K"], self.w16, ly["K"], ly["N"], ly["ldw"], out_f32, ly["N"], layout=2,
+                         a_lo=a_lo, b_lo=self.w16_lo if split else None, b_off=ly["w_off"], bias=self._b_view(ly),
+                         tile_n=64, k_splits=ks, epi_atomic=True)
+            else:
+                ops.gemm(a, B, ly["K"], ly["K"], self.w16, ly["K"], ly["N"], ly["ldw"], out_f32, ly["N"], layout=2,
+                         a_lo=a_lo, b_lo=self.w16_lo if split else None, b_off=ly["w_off"], bias=self._b_view(ly),
+                         relu=relu, tile_n=64)
 
     def __call__(self, x, training=False):
         x = self._prepare_input(x)

@@ -252,3 +252,16 @@ def test_nn_forward_layout_all_tile_widths(ops, tile_n):
     ref = torch.relu(a.double() @ b.double() + bias.double())
     absref = a.double().abs() @ b.double().abs() + bias.double().abs()
     assert bool(((out.double() - ref).abs() <= 2e-5 * absref + 2.0 ** -8 * ref.abs() + 1e-30).all())
+
+
+def test_split_k_atomic_adds_the_bias_once(ops):
+    """Split-K with the atomic epilogue into a zeroed fp32 output: every split adds its partial sums, the bias is added
+    by the first split only (the embedding layer of the fp32 mode: 64 rows, K = 3000)."""
+    M, N, K = 64, 512, 3000
+    a = _rand((M, K), 41).bfloat16()
+    b = _rand((K, N), 42, 0.02).bfloat16()
+    bias = _rand((N,), 43)
+    out = torch.zeros((M, N), device="cuda")
+    ops.gemm(a, M, K, K, b, K, N, N, out, N, layout=2, bias=bias, tile_n=64, k_splits=11, epi_atomic=True)
+    ref = a.double() @ b.double() + bias.double()
+    _check(out, ref, a.double().abs() @ b.double().abs() + bias.double().abs(), tol=2e-5)

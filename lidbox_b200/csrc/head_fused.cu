@@ -5,14 +5,17 @@
 // step's FLOPs, but as separate tcgen05 launches (prologue -> TMA pipeline -> epilogue -> teardown, 6-17 us apiece) they
 // were 18 % of the training step.  Here one grid of co-resident CTAs (one per SM) walks a short list of STEPS separated
 // by grid-wide barriers:
-//   forward :  Z1 += pooled . W1 (split-K over the CTAs, fp32 reductions)  |  H1 = bf16(relu(Z1 + b1)), Z1 = 0  |
+//   forward :  slab[s] = pooled[:, K-range s] . W1[K-range s, :]  (split-K over the CTAs, one fp32 slab per split)  |
+//              H1 = bf16(relu(sum_s slab[s] + b1))  (fixed summation order: bit-reproducible)  |
 //              H2 = bf16(relu(H1 . W2 + b2))
 //   backward:  dH1 = (dH2 . W2^T) * (H1 > 0), db1 += colsum(dH1), dW2 += H1^T . dH2  |
 //              gpool = dH1 . W1^T, dW1 += pooled^T . dH1
-// Tiles are 64 x 128 x 32 per CTA on mma.sync.m16n8k16 (bf16 in, fp32 accumulate) fed by a 4-stage cp.async pipeline;
-// operands are read in place in whatever orientation the buffers have (K-contiguous or M/N-contiguous: ldmatrix /
-// ldmatrix.trans), so no transposed copy of weights or activations exists.  These problems are latency-bound, not
-// tensor-bound: what matters is that all 148 SMs work on every step and that nothing is launched in between.
+// Tiles are 64 x 128 x 64 per CTA on mma.sync.m16n8k16 (bf16 in, fp32 accumulate: a 256-row problem cannot fill
+// tcgen05's 128-row tiles on 148 SMs).  Operands arrive by TMA tensor maps into 128B-swizzled shared-memory tiles in
+// whatever orientation the buffers have (K-contiguous or M/N-contiguous: ldmatrix / ldmatrix.trans, conflict-free), so
+// no transposed copy of weights or activations exists; stages are handed over with mbarriers (no bar.sync in the loop);
+// every warp turns its 32 x 32 accumulator block around in shared memory so that results leave in 16-byte,
+// row-contiguous accesses.  LBX_HEAD_PROFILE / LBX_HEAD_NO_MMA are measurement builds (tools/head_probe.py).
 #include "tc_ptx.cuh"
 
 namespace lbx {

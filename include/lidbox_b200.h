@@ -230,6 +230,8 @@ typedef struct lbx_gemm_t {
   int n_terms;
   int term_a[LBX_GEMM_MAX_TERMS]; int term_b[LBX_GEMM_MAX_TERMS]; int term_a_row[LBX_GEMM_MAX_TERMS];
   int term_b_row[LBX_GEMM_MAX_TERMS];
+  int term_col_limit[LBX_GEMM_MAX_TERMS];   /* > 0: pass t only contributes to output columns < limit (multiple of 256): */
+                                            /* tiles beyond it skip the pass instead of multiplying by zero-filled rows  */
   long long b_map_rows;     /* 0 = b_rows */
   int k_splits;
   int epi_atomic;

@@ -20,7 +20,7 @@ class GemmDesc(ctypes.Structure):
         ("a0", c_void_p), ("a1", c_void_p), ("a_rows", c_ll), ("a_cols", c_int), ("lda", c_ll),
         ("b0", c_void_p), ("b1", c_void_p), ("b_rows", c_ll), ("b_cols", c_int), ("ldb", c_ll),
         ("layout", c_int), ("n_terms", c_int), ("term_a", c_int * 5), ("term_b", c_int * 5), ("term_a_row", c_int * 5),
-        ("term_b_row", c_int * 5), ("b_map_rows", c_ll),
+        ("term_b_row", c_int * 5), ("term_col_limit", c_int * 5), ("b_map_rows", c_ll),
         ("k_splits", c_int), ("epi_atomic", c_int), ("out_dtype", c_int),
         ("out", c_void_p), ("out_lo", c_void_p), ("ldo", c_ll), ("bias", c_void_p), ("relu", c_int),
         ("post_scale", c_void_p), ("post_shift", c_void_p),

@@ -60,6 +60,7 @@ struct GemmParams {
   int term_a[LBX_GEMM_MAX_TERMS], term_b[LBX_GEMM_MAX_TERMS];   // which A / B tensor map each pass reads (0 or 1)
   int term_arow[LBX_GEMM_MAX_TERMS];   // row offset added to the A coordinate of each pass (NT / NN layouts)
   int term_brow[LBX_GEMM_MAX_TERMS];   // row offset added to the B row coordinate of each pass (NT: N index, NN: K index)
+  int term_ncol[LBX_GEMM_MAX_TERMS];   // > 0: the pass only contributes to output columns < this (a multiple of the tile width)
   int k_splits;            // split-K partitions (>= 1)
   int epi_atomic;          // 1: atomicAdd fp32 into out (split-K / gradient accumulation)
   int out_dtype;           // LBX_F32 / LBX_BF16
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int term = 0; term < p.n_terms; ++term) {
           const CUtensorMap* mA = p.term_a[term] ? &mapA1 : &mapA0;
           const CUtensorMap* mB = p.term_b[term] ? &mapB1 : &mapB0;
+          if (p.term_ncol[term] > 0 && n_blk * BN >= p.term_ncol[term]) continue;   // pass does not reach these columns
           const int arow = p.term_arow[term], brow = p.term_brow[term];
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(empty_bar + stage, phase ^ 1);
@@ -251,7 +253,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int tile = worker; tile < total_tiles; tile += n_workers) {
         const int split = tile / mn_tiles;
         const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
-        const int iters = (kb1 - kb0) * p.n_terms;
+        const int n_blk_t = (tile - split * mn_tiles) % n_tiles;
+        int terms_here = 0;                         // passes that reach this tile's columns (same test as the producer)
+        for (int term = 0; term < p.n_terms; ++term)
+          terms_here += (p.term_ncol[term] <= 0 || n_blk_t * BN < p.term_ncol[term]) ? 1 : 0;
+        const int iters = (kb1 - kb0) * terms_here;
         mbar_wait(tempty_bar + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
@@ -443,6 +449,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 x[i] = (up ? x[i + off] : x[i]) + recv;
               }
             }
+            // (also tried: per-warp shared-memory accumulators over all tiles of the CTA and ONE global atomic per column
+            // and CTA at the end — no gain: the cost of this block is the transpose, not the atomics; tools/dgrad_probe.py)
             if (lane < ncols) atomicAdd(p.colsum + (n0 + lane) % p.colsum_mod, x[0]);
           }
         }
@@ -767,6 +775,9 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
                   "term %d: B row offset %d is outside the B view", t, g->term_b_row[t]);
     p.term_a[t] = g->term_a[t]; p.term_b[t] = g->term_b[t]; p.term_arow[t] = g->term_a_row[t];
     p.term_brow[t] = g->term_b_row[t];
+    LBX_CHECK_ARG(g->term_col_limit[t] >= 0 && g->term_col_limit[t] % 256 == 0 && (t > 0 || g->term_col_limit[t] == 0),
+                  "term_col_limit must be a multiple of 256 (the widest tile) and 0 for the first pass");
+    p.term_ncol[t] = g->term_col_limit[t];
   }
   LBX_CHECK_ARG(g->lda % 8 == 0 && g->ldb % 8 == 0, "operand pitches must be multiples of 8 elements (16 bytes)");
   LBX_CHECK_ARG((reinterpret_cast<uintptr_t>(g->a0) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->b0) & 15) == 0,

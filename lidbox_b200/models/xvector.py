@@ -747,10 +747,16 @@ class XVector:
                 passes = -(-k // s)
                 if passes > 5:
                     raise NotImplementedError("kernel_size > 5 * strides in the backward pass")
+                def limit(i):
+                    # pass i covers taps i*s .. min(k, (i+1)*s) - 1 = output columns [0, (that many) * C_in): tiles to
+                    # the right of it would only multiply by the zero fill — skip them when tile-aligned
+                    cols = (min(k, (i + 1) * s) - i * s) * c
+                    return cols if (i > 0 and cols < s * c and cols % 256 == 0) else 0
+
                 if os.environ.get("LBX_DGRAD_MERGED", "1") != "0":
                     ops.gemm(dZ, rows, ly["N"], dz_pitch, self.w16, s * c, ly["N"], ly["ldw"], bufs["dZ"][L - 1], s * c,
                              a_off=dz_off, b_off=ly["w_off"], b_map_rows=k * c,
-                             terms=[(0, 0, -i, i * s * c) for i in range(passes)], mask_src=bufs["X"][L], colsum=g,
+                             terms=[(0, 0, -i, i * s * c, limit(i)) for i in range(passes)], mask_src=bufs["X"][L], colsum=g,
                              colsum_off=below["b_off"], colsum_mod=c)
                 else:
                     for rho in range(s):

@@ -66,9 +66,10 @@ def gemm(a, a_rows, a_cols, lda, b, b_rows, b_cols, ldb, out, ldo, *, layout=0, 
     if terms is None:        # bf16x3 when residual planes are given: (a0,b0) + (a0,b1) + (a1,b0)
         terms = [(0, 0, 0), (0, 1, 0), (1, 0, 0)] if a_lo is not None else [(0, 0, 0)]
     d.n_terms = len(terms)
-    for i, term in enumerate(terms):        # (A plane, B plane, A row offset[, B row offset])
+    for i, term in enumerate(terms):        # (A plane, B plane, A row offset[, B row offset[, output-column limit]])
         d.term_a[i], d.term_b[i], d.term_a_row[i] = term[0], term[1], term[2]
         d.term_b_row[i] = term[3] if len(term) > 3 else 0
+        d.term_col_limit[i] = term[4] if len(term) > 4 else 0
     d.b_map_rows = b_map_rows
     d.post_scale, d.post_shift = _addr(post_scale), _addr(post_shift)
     d.k_splits = k_splits

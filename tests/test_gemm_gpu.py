@@ -265,3 +265,23 @@ def test_split_k_atomic_adds_the_bias_once(ops):
     ops.gemm(a, M, K, K, b, K, N, N, out, N, layout=2, bias=bias, tile_n=64, k_splits=11, epi_atomic=True)
     ref = a.double() @ b.double() + bias.double()
     _check(out, ref, a.double().abs() @ b.double().abs() + bias.double().abs(), tol=2e-5)
+
+
+def test_nt_pass_column_limit_skips_zero_tiles(ops):
+    """Same gather form with C_in = 256: the second pass only reaches the first 256 output columns
+    (term_col_limit): tiles to the right skip it instead of multiplying by the zero fill — same result."""
+    M, C, K = 900, 256, 192
+    dz = _rand((M, K), 51).bfloat16()
+    w = _rand((3 * C, K), 52, 0.05).bfloat16()
+    outs = []
+    for limit in (0, C):
+        out = torch.full((M, 2 * C), float("nan"), device="cuda")
+        ops.gemm(dz, M, K, K, w, 2 * C, K, K, out, 2 * C, b_map_rows=3 * C, terms=[(0, 0, 0, 0), (0, 0, -1, 2 * C, limit)])
+        outs.append(out)
+    dzd, wd = dz.double(), w.double()
+    prev = torch.cat([torch.zeros((1, K), device="cuda", dtype=torch.float64), dzd[:-1]])
+    ref = torch.cat([dzd @ wd[:C].T + prev @ wd[2 * C:].T, dzd @ wd[C:2 * C].T], dim=1)
+    absref = torch.cat([dzd.abs() @ wd[:C].abs().T + prev.abs() @ wd[2 * C:].abs().T, dzd.abs() @ wd[C:2 * C].abs().T], dim=1)
+    for out in outs:
+        _check(out, ref, absref)
+    assert torch.equal(outs[0], outs[1])

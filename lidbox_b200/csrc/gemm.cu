@@ -27,7 +27,9 @@ namespace lbx {
 #endif
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int EPI_WARPS = 8;                  // two warps per TMEM sub-partition, each takes half of the tile's columns
+constexpr int EPI_WARPS_WIDE = 16;            // "wide epilogue" variant: four warps per sub-partition, a quarter each
 constexpr int GEMM_THREADS = 32 * LBX_CTRL_WARPS + 32 * EPI_WARPS;   // warpgroup 0: TMA / MMA / 2 idle warps; warpgroups 1-2: epilogue
+constexpr int GEMM_THREADS_WIDE = 32 * LBX_CTRL_WARPS + 32 * EPI_WARPS_WIDE;
 constexpr int BIAS_SMEM_FLOATS = 3072;         // the bias vector is staged in shared memory when N fits
 constexpr int STAGE_PITCH = 80;                // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16-byte accesses)
 constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH;
@@ -39,15 +41,17 @@ constexpr int BAR_BYTES = 1024;                // mbarriers + TMEM pointer (keep
 // tile-N variants: 256 (large problems), 128, and 64 (the small-M dense layers: enough CTAs without split-K)
 // PAIR: two CTAs of a cluster share one 256 x BN tile through tcgen05 cta_group::2 — each CTA stages its own 128 rows of
 // A and only HALF of the B tile, which cuts the operand bytes every SM has to ingest per k-block from 48 KB to 32 KB
-template <int BN, bool PAIR = false, bool HAS_MASK = false>
+template <int BN, bool PAIR = false, bool HAS_MASK = false, bool WIDE = false>
 struct Cfg {
+  static constexpr int EW = WIDE ? EPI_WARPS_WIDE : EPI_WARPS;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // the mask tiles of the ReLU-backward launches take the shared memory of one pipeline stage
-  static constexpr int STAGES = (PAIR ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8))) - (HAS_MASK ? 1 : 0);
+  // the mask tiles of the ReLU-backward launches take the shared memory of one pipeline stage; so do the extra staging
+  // tiles of the wide epilogue
+  static constexpr int STAGES = (PAIR ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8))) - (HAS_MASK ? 1 : 0) - (WIDE ? 1 : 0);
   static constexpr int TMEM_COLS = 2 * BN;    // 2 accumulator stages x BN fp32 columns
-  static constexpr int EPI_BYTES = HAS_MASK ? EPI_WARPS * 2 * FAST_TILE_BYTES : EPI_WARPS * STAGE_BYTES_PER_WARP;
-  static_assert(EPI_BYTES >= EPI_WARPS * STAGE_BYTES_PER_WARP && EPI_BYTES >= EPI_WARPS * FAST_TILE_BYTES, "epilogue tiles");
+  static constexpr int EPI_BYTES = HAS_MASK ? EW * 2 * FAST_TILE_BYTES : (WIDE ? EW * FAST_TILE_BYTES : EW * STAGE_BYTES_PER_WARP);
+  static_assert(WIDE || (EPI_BYTES >= EW * STAGE_BYTES_PER_WARP && EPI_BYTES >= EW * FAST_TILE_BYTES), "epilogue tiles");
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + EPI_BYTES +
                                  BIAS_SMEM_FLOATS * 4;
   static_assert(SMEM <= 232448, "shared memory budget");
@@ -102,14 +106,19 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, bool vec,
   }
 }
 
-template <int LAYOUT, int BN, bool HAS_MASK, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// WIDE: 16 epilogue warps instead of 8 (four per TMEM sub-partition, a quarter of the tile's columns each) for the
+// launches whose pace is set by the epilogue (small K: the main loop of a tile is shorter than draining it).  Only the
+// lean bf16 epilogue exists in this variant (640 threads leave 102 registers per thread), without the one-chunk-ahead
+// TMEM prefetch: with four warps per scheduler the other warps hide that latency.
+template <int LAYOUT, int BN, bool HAS_MASK, bool PAIR, bool WIDE = false>
+__global__ void __launch_bounds__(WIDE ? GEMM_THREADS_WIDE : GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                      const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapMask,
                      const GemmParams p) {
-  constexpr int STAGES = Cfg<BN, PAIR, HAS_MASK>::STAGES, STAGE_BYTES = Cfg<BN, PAIR, HAS_MASK>::STAGE_BYTES,
-                TMEM_COLS = Cfg<BN, PAIR, HAS_MASK>::TMEM_COLS;
+  using C = Cfg<BN, PAIR, HAS_MASK, WIDE>;
+  constexpr int EW = C::EW;                      // epilogue warps
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, TMEM_COLS = C::TMEM_COLS;
   constexpr int BN_LOCAL = PAIR ? BN / 2 : BN;   // B columns staged by this CTA
   constexpr bool A_MN = LAYOUT == 1;            // A stored [K, M] (contraction index is the slow one)
   constexpr bool B_MN = LAYOUT != 0;            // B stored [K, N]
@@ -120,10 +129,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* mask_bar = tempty_bar + 2;          // one per epilogue warp (fast epilogue: mask tile landed)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mask_bar + EPI_WARPS);
-  static_assert((2 * 8 + 4 + EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier area");
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mask_bar + EW);
+  static_assert((2 * 8 + 4 + EW) * 8 + 4 <= BAR_BYTES, "barrier area");
   unsigned char* s_stage = smem + (size_t)STAGES * STAGE_BYTES + BAR_BYTES;        // 1024-byte aligned epilogue tiles
-  float* s_bias = reinterpret_cast<float*>(s_stage + Cfg<BN, PAIR, HAS_MASK>::EPI_BYTES);
+  float* s_bias = reinterpret_cast<float*>(s_stage + C::EPI_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -149,9 +158,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i, 1);
-      mbar_init(tempty_bar + i, PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // one arrival per epilogue warp (of both CTAs)
+      mbar_init(tempty_bar + i, PAIR ? 2 * EW : EW);   // one arrival per epilogue warp (of both CTAs)
     }
-    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(mask_bar + i, 1);
+    for (int i = 0; i < EW; ++i) mbar_init(mask_bar + i, 1);
     if (p.fast) {
       tma_prefetch_desc(&mapOut);
       if (HAS_MASK) tma_prefetch_desc(&mapMask);
@@ -289,17 +298,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   } else if (warp >= LBX_CTRL_WARPS) {
     // ===================================== epilogue =====================================
     const int sub = warp & 3;                    // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
-    const int chalf = (warp - LBX_CTRL_WARPS) >> 2;           // which half of the tile's columns this warp drains
-    constexpr int CHUNKS = BN / 64;              // 32-column chunks per warp (two warps share a sub-partition)
+    const int chalf = (warp - LBX_CTRL_WARPS) >> 2;           // which part of the tile's columns this warp drains
+    constexpr int CPARTS = EW / 4;               // warps sharing a sub-partition (2, wide epilogue: 4)
+    constexpr int WCOLS = BN / CPARTS;           // columns per warp
+    constexpr int CHUNKS = WCOLS / 32;           // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     // the bias vector is read by every tile: stage it once (global loads in the epilogue's critical path cost an L2
     // round trip per 32-column chunk with only two warps per scheduler to hide it)
     const bool bias_smem = LBX_BIAS_SMEM && p.bias != nullptr && p.N <= BIAS_SMEM_FLOATS;
     if (bias_smem) {      // zero-filled up to the next multiple of 32 so that the last (partial) chunk needs no guard
-      for (int i = threadIdx.x - 32 * LBX_CTRL_WARPS; i < ((p.N + 31) & ~31) && i < BIAS_SMEM_FLOATS; i += 32 * EPI_WARPS)
+      for (int i = threadIdx.x - 32 * LBX_CTRL_WARPS; i < ((p.N + 31) & ~31) && i < BIAS_SMEM_FLOATS; i += 32 * EW)
         s_bias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
     }
     uint32_t mphase = 0;                         // parity of this warp's mask barrier (fast epilogue)
     for (int tile = worker; tile < total_tiles; tile += n_workers) {
@@ -314,8 +325,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       // must stay zero anyway (junk rows / the next utterance's causal padding)
       const bool row_zero = p.rows_per_utt > 0 && ((m % p.rows_per_utt) >= p.valid_rows);
       const long long row_off = (long long)m * p.ldo;
-      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + chalf * (BN / 2));
-      const int col_base = n_blk * BN + chalf * (BN / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN + chalf * WCOLS);
+      const int col_base = n_blk * BN + chalf * WCOLS;
       // coalescing through a per-warp staging tile: a thread owns one accumulator ROW, so direct 16-byte accesses touch
       // 32 different lines per instruction (half sectors); staged, 4 lanes cover 64 contiguous bytes of one row
       unsigned char* st = s_stage + (warp - LBX_CTRL_WARPS) * STAGE_BYTES_PER_WARP;
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         // conversion) -> swizzled shared-memory tile -> one bulk tensor store (clipped at M / N by the tensor map)
         const int wi = warp - LBX_CTRL_WARPS;
         unsigned char* st_out = s_stage + wi * FAST_TILE_BYTES;
-        unsigned char* st_msk = s_stage + (EPI_WARPS + wi) * FAST_TILE_BYTES;
+        unsigned char* st_msk = s_stage + (EW + wi) * FAST_TILE_BYTES;
         uint64_t* mbar_m = mask_bar + wi;
         const int ncols_rem = p.N - col_base;
         const int nch = (ncols_rem <= 0 || warp_row0 >= p.M) ? 0 : min(CHUNKS, (ncols_rem + 31) >> 5);
@@ -351,17 +362,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         mbar_wait(tfull_bar + acc, acc_phase);
         tc_fence_after();
         uint32_t v[32];
-        if (nch > 0) tc_ld32(taddr, v);
+        if (!WIDE && nch > 0) tc_ld32(taddr, v);
         bool released = false;
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
           const int n0 = col_base + c * 32;
+          if (WIDE) tc_ld32(taddr + c * 32, v);            // no prefetch: four warps per scheduler hide the latency
           tc_wait_ld();
           float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
           if (c + 1 < nch) {
-            tc_ld32(taddr + (c + 1) * 32, v);
+            if (!WIDE) tc_ld32(taddr + (c + 1) * 32, v);
           } else {
             // every TMEM read of this warp has landed: hand the accumulator stage back to the MMA issuer
             tc_fence_before();
@@ -465,6 +477,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
+      if constexpr (WIDE) continue;                // (the host launches the wide variant for lean-epilogue problems only)
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
 #ifndef LBX_EPI_GROUP
@@ -734,6 +747,8 @@ int make_map(CUtensorMap* map, const void* base, long long rows, long long cols,
 static int g_num_sms = 0;
 static int g_use_pair = 1;
 static int g_use_fast_epi = 1;
+static int g_use_wide_epi = 1;
+static int g_wide_max_kb = 16;
 
 }  // namespace lbx
 
@@ -851,6 +866,11 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
     LBX_SET_SMEM(0, 128); LBX_SET_SMEM(1, 128); LBX_SET_SMEM(2, 128);
     LBX_SET_SMEM(0, 64); LBX_SET_SMEM(1, 64); LBX_SET_SMEM(2, 64);
     LBX_SET_SMEM_PAIR(0); LBX_SET_SMEM_PAIR(1); LBX_SET_SMEM_PAIR(2);
+    // wide-epilogue variants (CTA pairs, lean epilogue only): forward (NN) and ReLU-backward data gradient (NT + mask)
+    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<2, 256, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg<256, true, false, true>::SMEM));
+    LBX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, 256, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg<256, true, true, true>::SMEM));
 #undef LBX_SET_SMEM
 #undef LBX_SET_SMEM_PAIR
     g_num_sms = n;
@@ -886,6 +906,24 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   cfg.attrs = attr;
   cfg.numAttrs = na;
   cudaError_t le;
+  // Wide epilogue (16 epilogue warps): for lean-epilogue CTA-pair launches whose tiles are drained more slowly than they
+  // are computed — few k-blocks per tile (K <= 1024 per tile incl. all passes) and more than one tile per pair.
+  const int kb_per_tile = ((p.K + BK - 1) / BK) * p.n_terms;
+  const bool wide = g_use_wide_epi && pair && p.fast && p.k_splits == 1 && kb_per_tile <= g_wide_max_kb &&
+                    ((g->layout == 2 && !hm) || (g->layout == 0 && hm));
+  if (wide) {
+    cfg.blockDim = dim3(GEMM_THREADS_WIDE);
+    if (hm) {
+      cfg.dynamicSmemBytes = Cfg<256, true, true, true>::SMEM;
+      le = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<0, 256, true, true, true>, mA0, mA1, mB0, mB1, mOut, mMask, p);
+    } else {
+      cfg.dynamicSmemBytes = Cfg<256, true, false, true>::SMEM;
+      le = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<2, 256, false, true, true>, mA0, mA1, mB0, mB1, mOut, mMask, p);
+    }
+    if (le != cudaSuccess) return set_error(LBX_ECUDA, "GEMM launch failed: %s", cudaGetErrorString(le));
+    LBX_LAUNCH_CHECK();
+    return LBX_OK;
+  }
 #define LBX_GEMM_LAUNCH(L, N_, P_)                                                                          \
   le = p.mask_src ? cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, true, P_>, mA0, mA1, mB0, mB1, mOut, mMask, p)  \
                   : cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<L, N_, false, P_>, mA0, mA1, mB0, mB1, mOut, mMask, p)
@@ -907,6 +945,13 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
 // lean bf16 epilogue (TMA stores, TMA mask loads, prefetched TMEM loads); LBX_GEMM_FAST_EPI=0 selects the general one
 extern "C" int lbx_set_gemm_fast_epilogue(int enabled) {
   g_use_fast_epi = enabled ? 1 : 0;
+  return LBX_OK;
+}
+
+// 16-warp epilogue for epilogue-bound lean launches (tiles of at most max_kb 64-wide k-blocks); 0 disables
+extern "C" int lbx_set_gemm_wide_epilogue(int enabled, int max_kb) {
+  g_use_wide_epi = enabled ? 1 : 0;
+  if (max_kb > 0) g_wide_max_kb = max_kb;
   return LBX_OK;
 }
 

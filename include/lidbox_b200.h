@@ -266,7 +266,7 @@ int lbx_set_pdl(int enabled);
 /* 1: the 256-wide GEMM tiles run on CTA pairs (clusters of 2, tcgen05 cta_group::2: a 256x256 tile per pair, every
  * CTA stages half of the B operand); 0: single-CTA 128x256 tiles. */
 int lbx_set_gemm_pair(int enabled);
-/* 1 (default): lean-epilogue CTA-pair launches with at most max_kb (default 16) k-blocks per tile run with 16 epilogue
+/* 1 (default): lean-epilogue CTA-pair launches with at most max_kb (default 64) k-blocks per tile run with 16 epilogue
  * warps instead of 8 (their pace is set by draining the accumulators, not by the tensor pipe); 0 disables */
 int lbx_set_gemm_wide_epilogue(int enabled, int max_kb);
 /* 1 (default): bf16-output GEMMs use the lean epilogue (bulk tensor stores / mask loads); 0: the general epilogue */

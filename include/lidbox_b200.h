@@ -261,6 +261,9 @@ typedef struct {
   float* out; long long ldo;
 } lbx_wgrad_t;
 int lbx_wgrad_grouped(const lbx_wgrad_t* problems, int n, void* stream);
+/* 1: clusters of two CTA pairs that share the A tile through TMA multicast (every problem needs an even number of
+ * 256-column tiles); 0 (default): independent CTA pairs */
+int lbx_set_wgrad_quad(int enabled);
 /* GEMMs are launched with programmatic dependent launch (prologue overlaps the previous kernel's tail); 0 disables. */
 int lbx_set_pdl(int enabled);
 /* 1: the 256-wide GEMM tiles run on CTA pairs (clusters of 2, tcgen05 cta_group::2: a 256x256 tile per pair, every

@@ -98,6 +98,7 @@ SIGNATURES = {
     "lbx_ap_loss": (c_int, [_P, _P, c_ll, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_int, _P, c_float, _P, _P]),
     "lbx_wgrad_grouped": (c_int, [_P, c_int, _P]),
     "lbx_set_gemm_wide_epilogue": (c_int, [c_int, c_int]),
+    "lbx_set_wgrad_quad": (c_int, [c_int]),
     "lbx_head_fwd": (c_int, [_P, c_ll, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_ll, _P, _P]),
     "lbx_head_bwd": (c_int, [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P, c_int, _P]),
@@ -137,6 +138,7 @@ def lib():
             handle.lbx_set_pdl(0)
         handle.lbx_set_gemm_pair(0 if os.environ.get("LBX_GEMM_PAIR", "1") == "0" else 1)
         handle.lbx_set_gemm_fast_epilogue(0 if os.environ.get("LBX_GEMM_FAST_EPI", "1") == "0" else 1)
+        handle.lbx_set_wgrad_quad(1 if os.environ.get("LBX_WGRAD_QUAD", "0") == "1" else 0)
         handle.lbx_set_gemm_wide_epilogue(0 if os.environ.get("LBX_GEMM_WIDE_EPI", "1") == "0" else 1,
                                           int(os.environ.get("LBX_GEMM_WIDE_MAX_KB", "0")))
         if os.environ.get("LBX_DP_BLOCKS_PER_SM"):

@@ -58,6 +58,7 @@ struct GwSegment {
 
 // Decodes line position x (x < x_end) into the segment that starts there and ends at the end of its (tile, k-chunk) or
 // at x_end, whichever comes first; returns the position after the segment.
+// (n_tiles counts 256-column tiles, or PAIRS of them when two CTA pairs of a cluster share the A tile)
 __device__ __forceinline__ long long gw_decode(const GwParams& P, long long x, long long x_end, GwSegment& s) {
   int p = 0;
   while (p + 1 < P.n_problems && x >= P.prob[p + 1].line_start) ++p;
@@ -80,6 +81,29 @@ __device__ __forceinline__ long long gw_decode(const GwParams& P, long long x, l
   return x + n;
 }
 
+// TMA load multicast to the CTAs of `mask`; the completion bytes are counted on the pair leader of every destination
+// (the mbarrier operand names the leader's barrier of the issuing CTA's pair: its CTA-relative offset and its "peer
+// bit" select the barrier in each destination pair)
+__device__ __forceinline__ void tma_load_2d_pair_mc(const CUtensorMap* map, uint32_t mbar_cluster_addr, void* dst, int c0,
+                                                    int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mask(uint64_t* bar, uint16_t mask) {   // arrives at this offset in the CTAs of mask
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+// QUAD: clusters of 4 = two CTA pairs that work on the SAME rows of A (same 256 output rows) and on neighbouring
+// 256-column tiles of B.  Every CTA loads half of its A tile and multicasts it to the CTA of the other pair that needs
+// the same rows, so a pair ingests 48 KB instead of 64 KB per k-block: the launch is bound by the L2 -> SM fabric.
+template <bool QUAD>
 __global__ void __launch_bounds__(GW_THREADS, 1) wgrad_grouped_kernel(const __grid_constant__ GwParams P) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -91,8 +115,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) wgrad_grouped_kernel(const __gr
   static_assert((2 * GW_STAGES + 4) * 8 + 4 <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cta_rank = (int)cluster_ctarank();
-  const long long worker = blockIdx.x >> 1, n_workers = gridDim.x >> 1;
+  const int cluster_rank = (int)cluster_ctarank();            // 0..1, QUAD: 0..3
+  const int pair = QUAD ? cluster_rank >> 1 : 0;              // which CTA pair of the cluster
+  const int cta_rank = cluster_rank & 1;                      // rank inside the pair (0 = leader, issues the MMAs)
+  const int lead_rank = cluster_rank & ~1;                    // cluster rank of this pair's leader
+  constexpr int CSZ = QUAD ? 4 : 2;
+  const long long worker = blockIdx.x / CSZ, n_workers = gridDim.x / CSZ;
   const long long x_begin = P.line_total * worker / n_workers, x_end = P.line_total * (worker + 1) / n_workers;
 
   if (threadIdx.x == 0) {
@@ -102,7 +130,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) wgrad_grouped_kernel(const __gr
     }
     for (int i = 0; i < GW_STAGES; ++i) {
       mbar_init(full_bar + i, 2);               // the producers of both CTAs arrive on the leader's barrier
-      mbar_init(empty_bar + i, 1);
+      mbar_init(empty_bar + i, QUAD ? 2 : 1);   // QUAD: a stage is refilled from BOTH pairs: both MMA issuers release it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i, 1);
@@ -134,16 +162,24 @@ __global__ void __launch_bounds__(GW_THREADS, 1) wgrad_grouped_kernel(const __gr
         const CUtensorMap* mA = &P.mapA[s.p];
         const CUtensorMap* mB = &P.mapB[s.p];
         const int m0 = (2 * s.m_unit + cta_rank) * BM;
-        const int n0 = s.n_blk * GW_BN + cta_rank * (GW_BN / 2);
+        const int n_blk = QUAD ? 2 * s.n_blk + pair : s.n_blk;
+        const int n0 = n_blk * GW_BN + cta_rank * (GW_BN / 2);
         for (int kb = s.kb0; kb < s.kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           unsigned char* sA = smem + (size_t)stage * GW_STAGE_BYTES;
           unsigned char* sB = sA + GW_A_BYTES;
-          const uint32_t lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
+          const uint32_t lead_full = mapa_u32(smem_u32(full_bar + stage), lead_rank);
           if (cta_rank == 0) mbar_expect_tx(full_bar + stage, 2u * (uint32_t)GW_STAGE_BYTES);
           else mbar_arrive_remote(lead_full);
+          if (QUAD) {
+            // this CTA fetches 64 of its 128 A columns (box `pair`) for itself AND for the CTA with the same rank in the
+            // other pair; the other 64 arrive from there
+            tma_load_2d_pair_mc(mA, lead_full, sA + pair * 8192, m0 + pair * 64, kb * BK,
+                                (uint16_t)((1u << cta_rank) | (1u << (cta_rank + 2))));
+          } else {
 #pragma unroll
-          for (int i = 0; i < BM / 64; ++i) tma_load_2d_pair(mA, lead_full, sA + i * 8192, m0 + i * 64, kb * BK);
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d_pair(mA, lead_full, sA + i * 8192, m0 + i * 64, kb * BK);
+          }
 #pragma unroll
           for (int i = 0; i < GW_BN / 2 / 64; ++i) tma_load_2d_pair(mB, lead_full, sB + i * 8192, n0 + i * 64, kb * BK);
           if (++stage == GW_STAGES) { stage = 0; phase ^= 1; }
@@ -177,10 +213,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) wgrad_grouped_kernel(const __gr
             const uint64_t db = make_smem_desc(sB + k * (UMMA_K * 128), 8192, 1024);
             tc_mma_bf16_pair(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit_pair(empty_bar + stage);
+          if (QUAD) tc_commit_mask(empty_bar + stage, (uint16_t)0xF);   // the stage is free in all four CTAs (for this pair)
+          else tc_commit_pair(empty_bar + stage);
           if (++stage == GW_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit_pair(tfull_bar + acc);
+        if (QUAD) tc_commit_mask(tfull_bar + acc, (uint16_t)(3u << (2 * pair)));
+        else tc_commit_pair(tfull_bar + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -195,7 +233,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) wgrad_grouped_kernel(const __gr
       x = gw_decode(P, x, x_end, s);
       const GwProblem& q = P.prob[s.p];
       const int m = (2 * s.m_unit + cta_rank) * BM + sub * 32 + lane;
-      const int col_base = s.n_blk * GW_BN + chalf * (GW_BN / 2);
+      const int col_base = (QUAD ? 2 * s.n_blk + pair : s.n_blk) * GW_BN + chalf * (GW_BN / 2);
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * GW_BN + chalf * (GW_BN / 2));
       float* orow = q.out + (long long)m * q.ldo;
       const bool row_ok = m < q.M;
@@ -212,7 +250,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) wgrad_grouped_kernel(const __gr
         } else {
           tc_fence_before();                                  // all TMEM reads of this warp have landed
           __syncwarp();
-          if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(tempty_bar + acc), 0));
+          if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(tempty_bar + acc), lead_rank));
         }
         const int n0 = col_base + c * 32;
         if (row_ok && n0 < q.N) {
@@ -249,34 +287,55 @@ __global__ void __launch_bounds__(GW_THREADS, 1) wgrad_grouped_kernel(const __gr
 
 using namespace lbx;
 
+static int g_wgrad_quad = 0;
+
+// max co-resident clusters of `csz` CTAs of kernel `k`
+template <typename K>
+static int gw_max_clusters(K k, int csz, int sms) {
+  cudaLaunchConfig_t occ{};
+  occ.gridDim = dim3((unsigned)(sms / csz * csz));
+  occ.blockDim = dim3(GW_THREADS);
+  occ.dynamicSmemBytes = GW_SMEM;
+  cudaLaunchAttribute oa[1];
+  oa[0].id = cudaLaunchAttributeClusterDimension;
+  oa[0].val.clusterDim.x = (unsigned)csz; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+  occ.attrs = oa; occ.numAttrs = 1;
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, k, &occ) != cudaSuccess || clusters < 1) {
+    (void)cudaGetLastError();
+    clusters = sms / csz;
+  }
+  return clusters < sms / csz ? clusters : sms / csz;
+}
+
+extern "C" int lbx_set_wgrad_quad(int enabled) {
+  g_wgrad_quad = enabled ? 1 : 0;
+  return LBX_OK;
+}
+
 extern "C" int lbx_wgrad_grouped(const lbx_wgrad_t* problems, int n, void* stream) {
   LBX_CHECK_ARG(problems != nullptr && n >= 1 && n <= GW_MAX_PROBLEMS, "1..%d problems per launch", GW_MAX_PROBLEMS);
-  static int max_pairs = 0;
+  static int max_pairs = 0, max_quads = 0;
   if (max_pairs == 0) {
     int dev = 0, sms = 0;
     LBX_CUDA(cudaGetDevice(&dev));
     LBX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    LBX_CUDA(cudaFuncSetAttribute(wgrad_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GW_SMEM));
-    // the line is cut into one range per pair: every pair must be resident at once, or the last ones would run alone
-    cudaLaunchConfig_t occ{};
-    occ.gridDim = dim3((unsigned)(sms & ~1));
-    occ.blockDim = dim3(GW_THREADS);
-    occ.dynamicSmemBytes = GW_SMEM;
-    cudaLaunchAttribute oa[1];
-    oa[0].id = cudaLaunchAttributeClusterDimension;
-    oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
-    occ.attrs = oa; occ.numAttrs = 1;
-    int clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&clusters, wgrad_grouped_kernel, &occ) != cudaSuccess || clusters < 1) {
-      (void)cudaGetLastError();
-      clusters = sms / 2;
-    }
-    max_pairs = clusters < sms / 2 ? clusters : sms / 2;
+    LBX_CUDA(cudaFuncSetAttribute(wgrad_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GW_SMEM));
+    LBX_CUDA(cudaFuncSetAttribute(wgrad_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GW_SMEM));
+    // the line is cut into one range per cluster: every cluster must be resident at once, or the last ones would run alone
+    max_pairs = gw_max_clusters(wgrad_grouped_kernel<false>, 2, sms);
+    max_quads = gw_max_clusters(wgrad_grouped_kernel<true>, 4, sms);
   }
-  const int pairs = max_pairs;
+  // QUAD (clusters of two pairs sharing the A tile): every problem must have an even number of 256-column tiles
+  bool quad = g_wgrad_quad != 0 && max_quads >= 1;
+  for (int i = 0; i < n && quad; ++i)
+    if (problems[i].rows > 0 && problems[i].a_cols > 0 && problems[i].b_cols > 0 &&
+        ((problems[i].b_cols + GW_BN - 1) / GW_BN) % 2 != 0)
+      quad = false;
+  const int workers_max = quad ? max_quads : max_pairs;
   GwParams P{};
-  // work per problem in (tile, k-block) units; the k-chunk length is the pair's share of the line, so that neighbouring
-  // pairs run the same k-blocks of neighbouring tiles at the same time
+  // work per problem in (tile, k-block) units; the k-chunk length is the worker's share of the line, so that
+  // neighbouring workers run the same k-blocks of neighbouring tiles at the same time
   long long total = 0;
   int np = 0;
   for (int i = 0; i < n; ++i) {
@@ -292,6 +351,7 @@ extern "C" int lbx_wgrad_grouped(const lbx_wgrad_t* problems, int n, void* strea
     q.kb_total = (int)((g.rows + BK - 1) / BK);
     q.m_units = ((q.M + BM - 1) / BM + 1) / 2;
     q.n_tiles = (q.N + GW_BN - 1) / GW_BN;
+    if (quad) q.n_tiles /= 2;                        // pairs of tiles: one per CTA pair of the cluster
     q.ldo = g.ldo; q.out = g.out;
     int rc;
     if ((rc = make_map(&P.mapA[np], g.a, g.rows, g.a_cols, g.lda, 64, 64))) return rc;
@@ -300,7 +360,7 @@ extern "C" int lbx_wgrad_grouped(const lbx_wgrad_t* problems, int n, void* strea
     ++np;
   }
   if (np == 0) return LBX_OK;
-  const long long share = (total + pairs - 1) / pairs;
+  const long long share = (total + workers_max - 1) / workers_max;
   long long pos = 0;
   for (int i = 0; i < np; ++i) {
     GwProblem& q = P.prob[i];
@@ -313,9 +373,10 @@ extern "C" int lbx_wgrad_grouped(const lbx_wgrad_t* problems, int n, void* strea
   }
   P.n_problems = np;
   P.line_total = total;
-  const int workers = (int)(total < pairs ? total : pairs);
+  const int workers = (int)(total < workers_max ? total : workers_max);
+  const int csz = quad ? 4 : 2;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(2 * workers));
+  cfg.gridDim = dim3((unsigned)(csz * workers));
   cfg.blockDim = dim3(GW_THREADS);
   cfg.dynamicSmemBytes = GW_SMEM;
   cfg.stream = (cudaStream_t)stream;
@@ -327,13 +388,14 @@ extern "C" int lbx_wgrad_grouped(const lbx_wgrad_t* problems, int n, void* strea
     ++na;
   }
   attr[na].id = cudaLaunchAttributeClusterDimension;
-  attr[na].val.clusterDim.x = 2;
+  attr[na].val.clusterDim.x = (unsigned)csz;
   attr[na].val.clusterDim.y = 1;
   attr[na].val.clusterDim.z = 1;
   ++na;
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, wgrad_grouped_kernel, P);
+  cudaError_t le = quad ? cudaLaunchKernelEx(&cfg, wgrad_grouped_kernel<true>, P)
+                        : cudaLaunchKernelEx(&cfg, wgrad_grouped_kernel<false>, P);
   if (le != cudaSuccess) return set_error(LBX_ECUDA, "grouped weight-gradient launch failed: %s", cudaGetErrorString(le));
   LBX_LAUNCH_CHECK();
   return LBX_OK;

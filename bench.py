@@ -306,13 +306,16 @@ class XVectorTrainWorkload:
         self.x = self.pipe["xs"][0]
         self.graphed = self.pipe["steps"][0] if self.use_graph else None
 
-    def _build_pipe(self, x_host):
+    def _build_pipe(self, x_host, loss_to_host=False):
         """Two signal buffers (dtype of x_host: float32 or 16-bit PCM) and the two input buffers of the model: while
         the model trains on the features of batch i, the log-mel of batch i+1 is written into the other input buffer
         on a second stream (the prefetch a tf.data input pipeline does), and in the end-to-end path the H2D copy of
         batch i+2 runs on a copy stream.  Every replay = one log-mel + one training step."""
         dev, audio, xvector = self.device, self.audio, self.xvector
-        pipe = {"x_host": x_host, "xs": [x_host.to(dev), x_host.to(dev)], "i": 0, "steps": [], "e2e": None}
+        pipe = {"x_host": x_host, "xs": [x_host.to(dev), x_host.to(dev)], "i": 0, "steps": [], "e2e": None,
+                # end-to-end loop: the per-sample losses of every step land here through a copy node inside the graph
+                "loss_host": [torch.empty((self.B,), dtype=torch.float32).pin_memory() for _ in range(2)]
+                if (loss_to_host and self.use_graph) else None}
         audio.logmelspectrograms(pipe["xs"][0], SR, out=self.sinks[0])          # prime the pipeline
         for k in range(2):
             nxt = (lambda k=k: audio.logmelspectrograms(pipe["xs"][1 - k], SR, out=self.sinks[1 - k]))
@@ -320,7 +323,11 @@ class XVectorTrainWorkload:
             if self.use_graph:
                 pipe["steps"].append(xvector.GraphedTrainStep(
                     self.model, self.sinks[k], self.y, loss=self.loss, process_group=self.pg,
-                    pre=None if self.pipelined else inline, concurrent=nxt if self.pipelined else None, **self.kw))
+                    pre=None if self.pipelined else inline, concurrent=nxt if self.pipelined else None,
+                    loss_host=pipe["loss_host"][k] if pipe["loss_host"] else None,
+                    # end-to-end loop: the H2D transfer of batch i+2 into signal buffer k (free during replay k) is a
+                    # branch of the same graph: a whole end-to-end step is ONE graph launch
+                    copies=[(pipe["xs"][k], x_host)] if pipe["loss_host"] else None, **self.kw))
             else:
                 pipe["steps"].append(lambda inline=inline: self.model.train_step(inline(), self.y, loss=self.loss,
                                                                                  process_group=self.pg, **self.kw))
@@ -365,6 +372,13 @@ class XVectorTrainWorkload:
         of batch i (input buffer k) and extracts the features of batch i+1 from device buffer 1-k, while batch i+2 is
         copied host->device into buffer k on the copy stream; the per-sample losses of batch i are copied back."""
         pipe = pipe or self.pipe
+        if pipe["loss_host"] is not None:
+            # CUDA-graph pipeline: host->device copy of batch i+2, log-mel of batch i+1, training step on batch i and the
+            # device->host copy of its losses are all nodes of the replayed graph
+            self.step(pipe)
+            if (pipe["i"] - 1) % E2E_LOSS_RING == E2E_LOSS_RING - 1:
+                torch.cuda.current_stream(self.device).synchronize()   # the host reads the losses that have arrived
+            return
         if pipe["e2e"] is None:
             self._setup_e2e(pipe)
         e = pipe["e2e"]
@@ -380,13 +394,16 @@ class XVectorTrainWorkload:
             pipe["xs"][k].copy_(pipe["x_host"], non_blocking=True)
             e["h2d_done"][k].record(e["copy"])
         slot = (pipe["i"] - 1) % E2E_LOSS_RING                 # pipe["i"] was advanced by self.step()
-        e["loss_host"][slot].copy_(losses, non_blocking=True)  # every step's losses are copied to the host
+        if pipe["loss_host"] is None:                          # (no CUDA graph: copy the losses with a stream operation)
+            e["loss_host"][slot].copy_(losses, non_blocking=True)
+        # with CUDA graphs every replay copies its per-sample losses into pinned host memory itself (a copy node inside
+        # the graph, GraphedTrainStep(loss_host=...)): nothing is enqueued between two replays for it
         if slot == E2E_LOSS_RING - 1:
-            cur.synchronize()                                  # the host reads the losses of the last ring of steps
+            cur.synchronize()                                  # the host reads the losses that have arrived
 
     def e2e_run(self, x_host, steps, barrier):
         """Times `steps` end-to-end steps fed from the pinned host tensor x_host (int16 PCM or float32)."""
-        pipe = self._build_pipe(x_host)
+        pipe = self._build_pipe(x_host, loss_to_host=True)
         for _ in range(4):
             self.step_e2e(pipe)
         barrier()

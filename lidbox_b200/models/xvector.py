@@ -967,15 +967,29 @@ class GraphedTrainStep:
     tensors given at construction; copy new data into them before calling."""
 
     def __init__(self, model, x_static, y_static, loss="xent", process_group=None, pre=None, concurrent=None,
-                 warmup=3, **kw):
+                 warmup=3, loss_host=None, copies=None, **kw):
         """pre: optional callable producing the features inline (same stream, before the step).
         concurrent: optional callable enqueued on a second stream alongside the step and joined at its end — e.g. the
-        feature extraction of the NEXT batch (input-pipeline prefetch), which is independent of this step."""
+        feature extraction of the NEXT batch (input-pipeline prefetch), which is independent of this step.
+        loss_host: optional pinned host tensor [B] float32: the per-sample losses of every replay are copied into it by
+        a copy node INSIDE the graph (no separate stream operation between two replays); read it after a synchronise.
+        copies: optional list of (dst, src) tensor pairs copied on a third branch of the graph, concurrently with the
+        step — e.g. the host-to-device transfer of the batch after next from a pinned staging buffer into a signal
+        buffer that nothing in this replay reads."""
         self.model, self.x, self.y = model, x_static, y_static
         lib = _lib.lib()
         aux = torch.cuda.Stream(device=model.device) if concurrent is not None else None
+        cpy = torch.cuda.Stream(device=model.device) if copies else None
 
         def body():
+            if cpy is not None:
+                cur = torch.cuda.current_stream(model.device)
+                evc = torch.cuda.Event()
+                evc.record(cur)
+                cpy.wait_event(evc)
+                with torch.cuda.stream(cpy):
+                    for dst, src in copies:
+                        dst.copy_(src, non_blocking=True)
             if aux is not None:
                 cur = torch.cuda.current_stream(model.device)
                 ev = torch.cuda.Event()
@@ -985,10 +999,16 @@ class GraphedTrainStep:
                     concurrent()
             feats = pre() if pre is not None else self.x
             out = model.train_step(feats, self.y, loss=loss, process_group=process_group, **kw)
+            if loss_host is not None:
+                loss_host.copy_(out, non_blocking=True)
             if aux is not None:
                 ev2 = torch.cuda.Event()
                 ev2.record(aux)
                 torch.cuda.current_stream(model.device).wait_event(ev2)
+            if cpy is not None:
+                ev3 = torch.cuda.Event()
+                ev3.record(cpy)
+                torch.cuda.current_stream(model.device).wait_event(ev3)
             return out
 
         side = torch.cuda.Stream(device=model.device)

@@ -314,17 +314,21 @@ class XVectorTrainWorkload:
         dev, audio, xvector = self.device, self.audio, self.xvector
         pipe = {"x_host": x_host, "xs": [x_host.to(dev), x_host.to(dev)], "i": 0, "steps": [], "e2e": None,
                 # end-to-end loop: the per-sample losses of every step land here through a copy node inside the graph
-                "loss_host": [torch.empty((self.B,), dtype=torch.float32).pin_memory() for _ in range(2)]
+                "loss_host": [torch.empty((self.B,), dtype=torch.float32).pin_memory() for _ in range(E2E_LOSS_RING)]
                 if (loss_to_host and self.use_graph) else None}
         audio.logmelspectrograms(pipe["xs"][0], SR, out=self.sinks[0])          # prime the pipeline
-        for k in range(2):
+        # two alternating input buffers; the end-to-end pipe captures one graph per slot of the host-side loss ring
+        # (slot j trains from input buffer j % 2 and copies its losses into pinned buffer j), so that the host finds the
+        # losses of ALL steps since its last synchronisation
+        for j in range(E2E_LOSS_RING if pipe["loss_host"] else 2):
+            k = j % 2
             nxt = (lambda k=k: audio.logmelspectrograms(pipe["xs"][1 - k], SR, out=self.sinks[1 - k]))
             inline = (lambda k=k: audio.logmelspectrograms(pipe["xs"][k], SR, out=self.sinks[k]))
             if self.use_graph:
                 pipe["steps"].append(xvector.GraphedTrainStep(
                     self.model, self.sinks[k], self.y, loss=self.loss, process_group=self.pg,
                     pre=None if self.pipelined else inline, concurrent=nxt if self.pipelined else None,
-                    loss_host=pipe["loss_host"][k] if pipe["loss_host"] else None,
+                    loss_host=pipe["loss_host"][j] if pipe["loss_host"] else None,
                     # end-to-end loop: the H2D transfer of batch i+2 into signal buffer k (free during replay k) is a
                     # branch of the same graph: a whole end-to-end step is ONE graph launch
                     copies=[(pipe["xs"][k], x_host)] if pipe["loss_host"] else None, **self.kw))
@@ -342,7 +346,7 @@ class XVectorTrainWorkload:
 
     def step(self, pipe=None):
         pipe = pipe or self.pipe
-        out = pipe["steps"][pipe["i"] % 2]()
+        out = pipe["steps"][pipe["i"] % len(pipe["steps"])]()
         pipe["i"] += 1
         return out
 

@@ -261,6 +261,11 @@ typedef struct {
   float* out; long long ldo;
 } lbx_wgrad_t;
 int lbx_wgrad_grouped(const lbx_wgrad_t* problems, int n, void* stream);
+/* Host-side replay of lbx_wgrad_grouped's work partition (no launch, no GPU needed; the same decode function the kernel
+ * runs): the k-blocks of all problems cut into `workers` contiguous ranges.  Fills `segments` with rows of 6 ints
+ * (worker, problem, m_unit, n_tile, first k-block, end k-block); pointers in `problems` are not dereferenced. */
+int lbx_wgrad_grouped_plan(const lbx_wgrad_t* problems, int n, int workers, int quad, int* segments, int max_segments,
+                           int* n_segments);
 /* 1: clusters of two CTA pairs that share the A tile through TMA multicast (every problem needs an even number of
  * 256-column tiles); 0 (default): independent CTA pairs */
 int lbx_set_wgrad_quad(int enabled);

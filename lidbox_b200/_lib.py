@@ -99,6 +99,7 @@ SIGNATURES = {
     "lbx_wgrad_grouped": (c_int, [_P, c_int, _P]),
     "lbx_set_gemm_wide_epilogue": (c_int, [c_int, c_int]),
     "lbx_set_wgrad_quad": (c_int, [c_int]),
+    "lbx_wgrad_grouped_plan": (c_int, [_P, c_int, c_int, c_int, _P, c_int, _P]),
     "lbx_head_fwd": (c_int, [_P, c_ll, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_ll, _P, _P]),
     "lbx_head_bwd": (c_int, [_P, _P, _P, c_ll, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "lbx_adam_step": (c_int, [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, _P, _P, c_float, _P, c_int, _P]),

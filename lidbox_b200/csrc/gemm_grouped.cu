@@ -59,7 +59,7 @@ struct GwSegment {
 // Decodes line position x (x < x_end) into the segment that starts there and ends at the end of its (tile, k-chunk) or
 // at x_end, whichever comes first; returns the position after the segment.
 // (n_tiles counts 256-column tiles, or PAIRS of them when two CTA pairs of a cluster share the A tile)
-__device__ __forceinline__ long long gw_decode(const GwParams& P, long long x, long long x_end, GwSegment& s) {
+__host__ __device__ __forceinline__ long long gw_decode(const GwParams& P, long long x, long long x_end, GwSegment& s) {
   int p = 0;
   while (p + 1 < P.n_problems && x >= P.prob[p + 1].line_start) ++p;
   const GwProblem& q = P.prob[p];
@@ -68,7 +68,7 @@ __device__ __forceinline__ long long gw_decode(const GwParams& P, long long x, l
   const long long per_chunk = units * q.chunk;
   const int c = (int)(r / per_chunk);
   const long long r2 = r - (long long)c * per_chunk;
-  const int len = min(q.chunk, q.kb_total - c * q.chunk);
+  const int len = q.chunk < q.kb_total - c * q.chunk ? q.chunk : q.kb_total - c * q.chunk;
   const int u = (int)(r2 / len);
   const int koff = (int)(r2 - (long long)u * len);
   long long n = len - koff;
@@ -308,6 +308,78 @@ static int gw_max_clusters(K k, int csz, int sms) {
   return clusters < sms / csz ? clusters : sms / csz;
 }
 
+// Lays the problems on the work line (tile counts, k-chunk lengths, line offsets) and, when with_maps, encodes the
+// tensor maps.  The k-chunk length is the worker's share of the line, so that neighbouring workers run the same
+// k-blocks of neighbouring tiles at the same time.
+static int gw_plan(const lbx_wgrad_t* problems, int n, int workers_max, bool quad, GwParams& P, bool with_maps) {
+  long long total = 0;
+  int np = 0;
+  for (int i = 0; i < n; ++i) {
+    const lbx_wgrad_t& g = problems[i];
+    LBX_CHECK_ARG(g.rows >= 0 && g.rows <= 2147483647LL && g.a_cols >= 0 && g.b_cols >= 0, "bad extent in problem %d", i);
+    if (with_maps) {
+      LBX_CHECK_ARG(g.a && g.b && g.out, "NULL operand in problem %d", i);
+      LBX_CHECK_ARG(g.lda % 8 == 0 && g.ldb % 8 == 0, "operand pitches must be multiples of 8 elements (16 bytes)");
+      LBX_CHECK_ARG((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0,
+                    "operands must be 16-byte aligned");
+    }
+    if (g.rows == 0 || g.a_cols == 0 || g.b_cols == 0) continue;
+    GwProblem& q = P.prob[np];
+    q.M = g.a_cols; q.N = g.b_cols;
+    q.kb_total = (int)((g.rows + BK - 1) / BK);
+    q.m_units = ((q.M + BM - 1) / BM + 1) / 2;
+    q.n_tiles = (q.N + GW_BN - 1) / GW_BN;
+    if (quad) q.n_tiles /= 2;                        // pairs of tiles: one per CTA pair of the cluster
+    q.ldo = g.ldo; q.out = g.out;
+    if (with_maps) {
+      int rc;
+      if ((rc = make_map(&P.mapA[np], g.a, g.rows, g.a_cols, g.lda, 64, 64))) return rc;
+      if ((rc = make_map(&P.mapB[np], g.b, g.rows, g.b_cols, g.ldb, 64, 64))) return rc;
+    }
+    total += (long long)q.m_units * q.n_tiles * q.kb_total;
+    ++np;
+  }
+  P.n_problems = np;
+  P.line_total = total;
+  if (np == 0) return LBX_OK;
+  const long long share = (total + workers_max - 1) / workers_max;
+  long long pos = 0;
+  for (int i = 0; i < np; ++i) {
+    GwProblem& q = P.prob[i];
+    long long splits = (q.kb_total + share / 2) / (share > 0 ? share : 1);      // round(kb_total / share)
+    if (splits < 1) splits = 1;
+    if (splits > q.kb_total) splits = q.kb_total;
+    q.chunk = (int)((q.kb_total + splits - 1) / splits);
+    q.line_start = pos;
+    pos += (long long)q.m_units * q.n_tiles * q.kb_total;
+  }
+  return LBX_OK;
+}
+
+extern "C" int lbx_wgrad_grouped_plan(const lbx_wgrad_t* problems, int n, int workers, int quad, int* segments,
+                                      int max_segments, int* n_segments) {
+  LBX_CHECK_ARG(problems != nullptr && n >= 1 && n <= GW_MAX_PROBLEMS && workers >= 1 && segments && n_segments,
+                "bad arguments");
+  GwParams P{};
+  int rc = gw_plan(problems, n, workers, quad != 0, P, false);
+  if (rc) return rc;
+  const long long total = P.line_total;
+  const long long nw = total < workers ? total : workers;
+  int count = 0;
+  for (long long w = 0; w < nw; ++w) {
+    const long long x_end = total * (w + 1) / nw;
+    for (long long x = total * w / nw; x < x_end;) {
+      GwSegment sg;
+      x = gw_decode(P, x, x_end, sg);
+      LBX_CHECK_ARG(count < max_segments, "segment buffer too small");
+      int* o = segments + 6 * count++;
+      o[0] = (int)w; o[1] = sg.p; o[2] = sg.m_unit; o[3] = sg.n_blk; o[4] = sg.kb0; o[5] = sg.kb1;
+    }
+  }
+  *n_segments = count;
+  return LBX_OK;
+}
+
 extern "C" int lbx_set_wgrad_quad(int enabled) {
   g_wgrad_quad = enabled ? 1 : 0;
   return LBX_OK;
@@ -334,45 +406,11 @@ extern "C" int lbx_wgrad_grouped(const lbx_wgrad_t* problems, int n, void* strea
       quad = false;
   const int workers_max = quad ? max_quads : max_pairs;
   GwParams P{};
-  // work per problem in (tile, k-block) units; the k-chunk length is the worker's share of the line, so that
-  // neighbouring workers run the same k-blocks of neighbouring tiles at the same time
-  long long total = 0;
-  int np = 0;
-  for (int i = 0; i < n; ++i) {
-    const lbx_wgrad_t& g = problems[i];
-    LBX_CHECK_ARG(g.a && g.b && g.out, "NULL operand in problem %d", i);
-    LBX_CHECK_ARG(g.rows >= 0 && g.rows <= 2147483647LL && g.a_cols >= 0 && g.b_cols >= 0, "bad extent in problem %d", i);
-    LBX_CHECK_ARG(g.lda % 8 == 0 && g.ldb % 8 == 0, "operand pitches must be multiples of 8 elements (16 bytes)");
-    LBX_CHECK_ARG((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0,
-                  "operands must be 16-byte aligned");
-    if (g.rows == 0 || g.a_cols == 0 || g.b_cols == 0) continue;
-    GwProblem& q = P.prob[np];
-    q.M = g.a_cols; q.N = g.b_cols;
-    q.kb_total = (int)((g.rows + BK - 1) / BK);
-    q.m_units = ((q.M + BM - 1) / BM + 1) / 2;
-    q.n_tiles = (q.N + GW_BN - 1) / GW_BN;
-    if (quad) q.n_tiles /= 2;                        // pairs of tiles: one per CTA pair of the cluster
-    q.ldo = g.ldo; q.out = g.out;
-    int rc;
-    if ((rc = make_map(&P.mapA[np], g.a, g.rows, g.a_cols, g.lda, 64, 64))) return rc;
-    if ((rc = make_map(&P.mapB[np], g.b, g.rows, g.b_cols, g.ldb, 64, 64))) return rc;
-    total += (long long)q.m_units * q.n_tiles * q.kb_total;
-    ++np;
-  }
+  int rc = gw_plan(problems, n, workers_max, quad, P, true);
+  if (rc) return rc;
+  const int np = P.n_problems;
+  const long long total = P.line_total;
   if (np == 0) return LBX_OK;
-  const long long share = (total + workers_max - 1) / workers_max;
-  long long pos = 0;
-  for (int i = 0; i < np; ++i) {
-    GwProblem& q = P.prob[i];
-    long long splits = (q.kb_total + share / 2) / (share > 0 ? share : 1);      // round(kb_total / share)
-    if (splits < 1) splits = 1;
-    if (splits > q.kb_total) splits = q.kb_total;
-    q.chunk = (int)((q.kb_total + splits - 1) / splits);
-    q.line_start = pos;
-    pos += (long long)q.m_units * q.n_tiles * q.kb_total;
-  }
-  P.n_problems = np;
-  P.line_total = total;
   const int workers = (int)(total < workers_max ? total : workers_max);
   const int csz = quad ? 4 : 2;
   cudaLaunchConfig_t cfg{};

@@ -81,3 +81,51 @@ def test_bad_arguments_raise_without_gpu(built_lib):
     assert lib.lbx_spectrogram_f32(None, -1, 1000, 400, 160, 512, 2.0, None, None) == -1
     assert lib.lbx_spectrogram_f32(None, 1, 100, 400, 160, 512, 2.0, None, None) == -1    # NULL signal with B*N > 0
     assert lib.lbx_spectrogram_f32(None, 0, 100, 400, 160, 512, 2.0, None, None) == 0     # empty batch is a no-op
+
+
+def _plan(handle, shapes, workers, quad=0):
+    from lidbox_b200 import _lib
+    probs = (_lib.WgradDesc * len(shapes))()
+    for d, (rows, a_cols, b_cols) in zip(probs, shapes):
+        d.rows, d.a_cols, d.b_cols, d.lda, d.ldb, d.ldo = rows, a_cols, b_cols, a_cols, b_cols, b_cols
+    seg = (ctypes.c_int * (6 * 4096))()
+    n = ctypes.c_int(0)
+    handle.lbx_wgrad_grouped_plan.restype = ctypes.c_int
+    rc = handle.lbx_wgrad_grouped_plan(probs, len(shapes), workers, quad, seg, 4096, ctypes.byref(n))
+    assert rc == 0
+    return np.array(seg[:6 * n.value]).reshape(-1, 6)
+
+
+def test_wgrad_grouped_partition_covers_every_k_block_once(built_lib):
+    """lbx_wgrad_grouped cuts the (problem, tile, k-block) space of all weight-gradient problems into one contiguous
+    range per CTA pair (stream-K).  The host-side replay runs the same decode function as the kernel: every k-block of
+    every 256 x 256 tile must be covered exactly once, the ranges must be equal (+-1) and a worker must not see more
+    than a handful of segments."""
+    handle = ctypes.CDLL(built_lib)
+    cases = [
+        ([(26112, 1536, 512), (8704, 1536, 512), (8704, 512, 1500), (8704, 512, 512), (52224, 200, 512)], 74, 0),   # config 3
+        ([(26112, 1536, 512), (8704, 1536, 512), (8704, 512, 1500), (8704, 512, 512), (52224, 200, 512)], 37, 1),   # 4-CTA clusters
+        ([(5000, 512, 1500), (64, 64, 4), (3, 8, 8), (777, 264, 72), (12800, 1536, 512), (1, 512, 512)], 74, 0),
+        ([(100, 128, 256)], 74, 0),                                                   # fewer k-blocks than workers
+    ]
+    for shapes, workers, quad in cases:
+        seg = _plan(handle, shapes, workers, quad)
+        live = [s for s in shapes if min(s) > 0]
+        expect = {}
+        for p, (rows, a_cols, b_cols) in enumerate(live):
+            kb = -(-rows // 64)
+            m_units = (-(-a_cols // 128) + 1) // 2
+            n_tiles = -(-b_cols // 256) // (2 if quad else 1)
+            for mu in range(m_units):
+                for nt in range(n_tiles):
+                    expect[(p, mu, nt)] = kb
+        seen = {key: np.zeros(kb, dtype=np.int32) for key, kb in expect.items()}
+        per_worker = {}
+        for w, p, mu, nt, k0, k1 in seg:
+            assert 0 <= k0 < k1 <= expect[(p, mu, nt)]
+            seen[(p, mu, nt)][k0:k1] += 1
+            per_worker.setdefault(w, []).append(k1 - k0)
+        assert all((v == 1).all() for v in seen.values())                             # exactly once
+        loads = [sum(v) for v in per_worker.values()]
+        assert max(loads) - min(loads) <= 1                                           # equal shares
+        assert max(len(v) for v in per_worker.values()) <= 6                          # few segments (few epilogues) per worker

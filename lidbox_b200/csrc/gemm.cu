@@ -48,12 +48,15 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // the mask tiles of the ReLU-backward launches take the shared memory of one pipeline stage; so do the extra staging
   // tiles of the wide epilogue
-  static constexpr int STAGES = (PAIR ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8))) - (HAS_MASK ? 1 : 0) - (WIDE ? 1 : 0);
+  // (the wide ReLU-backward variant keeps 5 stages: it has no bias staging area, see AUX_BYTES)
+  static constexpr int STAGES = (PAIR ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8))) - (HAS_MASK ? 1 : 0) -
+                                ((WIDE && !HAS_MASK) ? 1 : 0);
   static constexpr int TMEM_COLS = 2 * BN;    // 2 accumulator stages x BN fp32 columns
   static constexpr int EPI_BYTES = HAS_MASK ? EW * 2 * FAST_TILE_BYTES : (WIDE ? EW * FAST_TILE_BYTES : EW * STAGE_BYTES_PER_WARP);
   static_assert(WIDE || (EPI_BYTES >= EW * STAGE_BYTES_PER_WARP && EPI_BYTES >= EW * FAST_TILE_BYTES), "epilogue tiles");
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + EPI_BYTES +
-                                 BIAS_SMEM_FLOATS * 4;
+  // ReLU-backward launches of the wide variant take the lean epilogue only with bias == NULL: no bias staging area
+  static constexpr int AUX_BYTES = (WIDE && HAS_MASK) ? 0 : BIAS_SMEM_FLOATS * 4;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + EPI_BYTES + AUX_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -912,7 +915,7 @@ extern "C" int lbx_gemm_bf16(const lbx_gemm_t* g, void* stream) {
   // contractions, where one pipeline stage more is worth more than the extra warps.
   const int kb_per_tile = ((p.K + BK - 1) / BK) * p.n_terms;
   const bool wide = g_use_wide_epi && pair && p.fast && p.k_splits == 1 && kb_per_tile <= g_wide_max_kb &&
-                    ((g->layout == 2 && !hm) || (g->layout == 0 && hm));
+                    ((g->layout == 2 && !hm) || (g->layout == 0 && hm && g->bias == nullptr));
   if (wide) {
     cfg.blockDim = dim3(GEMM_THREADS_WIDE);
     if (hm) {

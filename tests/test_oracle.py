@@ -326,13 +326,18 @@ def test_activation_row_geometry_for_any_layer_list():
     from lidbox_b200.models.xvector import _Geometry, frame_layer
     from lidbox_b200.models.xvector_extended import frame_layers
     lists = [frame_layers(), [frame_layer(8, 5, 1), frame_layer(8, 3, 2), frame_layer(8, 3, 3), frame_layer(8, 1, 1)],
-             [frame_layer(8, 3, 4)], [frame_layer(8, 2, 5), frame_layer(8, 7, 2)]]
+             [frame_layer(8, 3, 4)], [frame_layer(8, 2, 5), frame_layer(8, 7, 2)],
+             # dilated TDNN (extension): causal padding dilation * (k - 1)
+             [frame_layer(8, 5, 1), frame_layer(8, 3, 1, dilation_rate=2), frame_layer(8, 3, 1, dilation_rate=3),
+              frame_layer(8, 1, 1)],
+             [frame_layer(8, 3, 2), frame_layer(8, 5, 1, dilation_rate=4)]]
     for frames in lists:
         for T in (1, 2, 5, 23, 24, 25, 198, 400, 499):
             geo = _Geometry(T, frames)
             for L, f in enumerate(frames):
                 assert geo.T[L + 1] == -(-geo.T[L] // f.strides)
-                assert geo.Tpad[L] >= geo.T[L] + f.kernel_size - 1            # room for the causal left padding
+                pad = (f.kernel_size - 1) * f.dilation_rate
+                assert geo.pad[L] == pad and geo.Tpad[L] >= geo.T[L] + pad   # room for the causal left padding
                 assert geo.Tpad[L] % f.strides == 0 and geo.R[L] >= geo.T[L + 1]
                 if L + 1 < len(frames):
                     assert geo.R[L] == geo.Tpad[L + 1]

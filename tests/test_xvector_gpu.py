@@ -187,6 +187,34 @@ def test_dropout_mask_changes_between_cuda_graph_replays(xv):
     assert 0.2 < a.mean() < 0.8 and (a != b).mean() > 0.3
 
 
+def test_graphed_step_copies_and_loss_read_back(xv):
+    """GraphedTrainStep(copies=..., loss_host=...): the host-to-device transfer of a later batch and the read-back of the
+    per-sample losses are nodes of the replayed graph — after a replay + synchronise the pinned loss buffer holds this
+    replay's losses and the staged batch has arrived in its device buffer; the training result equals the plain step."""
+    rng = np.random.default_rng(12)
+    B, T = 8, 40
+    x = torch.tensor(rng.standard_normal((B, T, 40)).astype(np.float32), device="cuda")
+    y = torch.tensor(np.arange(B) % 4, dtype=torch.int32, device="cuda")
+    staged_host = torch.tensor(rng.standard_normal((B, 1000)).astype(np.float32)).pin_memory()
+    staged_dev = torch.zeros((B, 1000), device="cuda")
+    loss_host = torch.full((B,), float("nan")).pin_memory()
+    m = xv.create((T, 40), 4, precision="bf16", seed=2)
+    m.configure_optimizer(lr=1e-3)
+    ref = xv.create((T, 40), 4, precision="bf16", seed=2)
+    ref.configure_optimizer(lr=1e-3)
+    step = xv.GraphedTrainStep(m, x, y, copies=[(staged_dev, staged_host)], loss_host=loss_host, warmup=0)
+    staged_dev.zero_()
+    out = step()
+    torch.cuda.synchronize()
+    expect = ref.train_step(x, y)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(loss_host.numpy(), expect.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out.cpu().numpy(), loss_host.numpy(), rtol=0, atol=0)
+    assert torch.equal(staged_dev.cpu(), staged_host)
+    n = ref.params.numel()
+    assert float((m.params[:n] - ref.params).abs().max()) < 1e-5          # same update up to fp32 atomics order
+
+
 @pytest.mark.parametrize("B,T,n_out", [(6, 37, 5), (32, 198, 4)])
 def test_training_gradients_bf16_xent(xv, B, T, n_out):
     rng = np.random.default_rng(4)
